@@ -1,0 +1,191 @@
+/*
+ * pe_b200.h — C ABI of libpe_b200.so, the B200 (sm_100a) pose-refinement path.
+ *
+ * This is the drop-in boundary. Every entry point replaces one PCL 1.10 call that the
+ * north-star path substitutes into the refinement / normals / down-sample slots of
+ * yumi-crew/pose_estimation:
+ *
+ *   refinement slot   pose_estimation/src/opencv_surface_match.cpp:85-94
+ *   normals slot      pose_estimation/src/opencv_surface_match.cpp:57-59
+ *   down-sample slot  pose_estimation/src/pose_estimation.cpp:261-263
+ *
+ * PCL itself is not vendored in the reference; "[PCL] file" below names the upstream
+ * pcl-1.10.0 file whose behaviour the entry point reproduces.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++ or torch types, no exceptions across the ABI.
+ *   - point clouds are passed as (pointer, count, stride-in-bytes); the first three
+ *     floats of every record are x,y,z.  stride 16 = pcl::PointXYZ, 48 = pcl::PointNormal,
+ *     12 / 24 = rows of a cv::Mat N x 3 / N x 6 CV_32F.
+ *   - every call returns 0 (PEB_OK) or a negative peb_status; the text of the last error
+ *     is available from peb_last_error().  Numerical outcomes (too few correspondences,
+ *     iteration cap) are not errors: they are reported in peb_icp_result like PCL does.
+ *   - a peb_ctx is bound to one CUDA device and one stream; calls on one context must be
+ *     serialised by the caller (the node has a single executor thread).  Distinct
+ *     contexts are independent.
+ *   - there is no CPU fallback: every entry point either runs the CUDA path or fails.
+ */
+#ifndef PE_B200_H_
+#define PE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define PEB_API
+#else
+#define PEB_API __attribute__((visibility("default")))
+#endif
+
+typedef struct peb_ctx peb_ctx;
+
+typedef enum peb_status {
+  PEB_OK = 0,
+  PEB_E_INVALID_ARG = -1,
+  PEB_E_NO_TARGET = -2,  /* align / fitness called before peb_target_set            */
+  PEB_E_NO_SOURCE = -3,  /* align called before peb_source_set                      */
+  PEB_E_CUDA = -4,
+  PEB_E_OOM = -5,
+  PEB_E_UNSUPPORTED = -6 /* PCL option with no CUDA implementation (no CPU fallback) */
+} peb_status;
+
+/* pcl::registration::DefaultConvergenceCriteria<float>::ConvergenceState, same order.
+ * [PCL] registration/include/pcl/registration/default_convergence_criteria.h */
+typedef enum peb_convergence_state {
+  PEB_NOT_CONVERGED = 0,
+  PEB_ITERATIONS = 1,
+  PEB_TRANSFORM = 2,
+  PEB_ABS_MSE = 3,
+  PEB_REL_MSE = 4,
+  PEB_NO_CORRESPONDENCES = 5,
+  PEB_FAILURE_AFTER_MAX_ITERATIONS = 6
+} peb_convergence_state;
+
+enum { PEB_ESTIMATOR_SVD = 0, PEB_ESTIMATOR_POINT_TO_PLANE_LLS = 1 };
+
+/* The setters of pcl::Registration / pcl::IterativeClosestPoint and of its
+ * DefaultConvergenceCriteria, as one POD.  peb_icp_params_default() fills PCL 1.10's
+ * defaults.  [PCL] registration/include/pcl/registration/registration.h, icp.h */
+typedef struct peb_icp_params {
+  int32_t max_iterations;             /* setMaximumIterations           (10)            */
+  int32_t min_correspondences;        /* min_number_correspondences_    (3)             */
+  int32_t estimator;                  /* PEB_ESTIMATOR_*                (SVD)           */
+  int32_t max_iterations_similar;     /* setMaximumIterationsSimilarTransforms (0)      */
+  double max_corr_dist;               /* setMaxCorrespondenceDistance   (sqrt(DBL_MAX)) */
+  double transformation_epsilon;      /* setTransformationEpsilon       (0)             */
+  double rotation_epsilon;            /* setTransformationRotationEpsilon (0)           */
+  double euclidean_fitness_epsilon;   /* setEuclideanFitnessEpsilon     (-DBL_MAX)      */
+  double abs_mse_threshold;           /* getConvergeCriteria()->setAbsoluteMSE (1e-12)  */
+  double rejector_max_dist;           /* CorrespondenceRejectorDistance::setMaximumDistance;
+                                         <= 0 : no rejector (PCL's ICP default)        */
+  double fitness_max_range;           /* getFitnessScore(max_range)     (DBL_MAX)       */
+} peb_icp_params;
+
+/* What pcl::Registration exposes after align().  T is column-major, i.e. memcpy-compatible
+ * with Eigen::Matrix4f::data() of getFinalTransformation(). */
+typedef struct peb_icp_result {
+  float T[16];
+  double fitness;          /* getFitnessScore(fitness_max_range)                        */
+  double last_mse;         /* correspondences_cur_mse_ of the last evaluated iteration  */
+  int32_t iterations;      /* nr_iterations_                                            */
+  int32_t converged;       /* hasConverged()                                            */
+  int32_t state;           /* peb_convergence_state                                     */
+  int32_t n_correspondences; /* size of the last correspondence set                     */
+} peb_icp_result;
+
+/* ---- context ------------------------------------------------------------------- */
+PEB_API int peb_ctx_create(int device, peb_ctx** out);
+PEB_API void peb_ctx_destroy(peb_ctx* ctx);
+/* never NULL; valid until the next call on ctx (ctx == NULL: message of the last failed
+ * peb_ctx_create on this thread) */
+PEB_API const char* peb_last_error(const peb_ctx* ctx);
+PEB_API const char* peb_version(void);
+PEB_API void peb_icp_params_default(peb_icp_params* p);
+/* the cudaStream_t all work of this context is ordered on (for event timing) */
+PEB_API void* peb_ctx_stream(peb_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches claim) */
+PEB_API uint64_t peb_ctx_launch_count(const peb_ctx* ctx);
+
+/* ---- pcl::VoxelGrid<PointXYZ>::filter  [PCL] filters/.../impl/voxel_grid.hpp -------- */
+/* out_xyz4 must hold n x 4 floats (the overflow guard returns the input unchanged).
+ * Output order: ascending voxel index, x fastest, like PCL.  min_pts = setMinimumPointsNumberPerVoxel. */
+PEB_API int peb_voxel_grid(peb_ctx* ctx, const void* pts, size_t n, size_t stride,
+                           float leaf_x, float leaf_y, float leaf_z, unsigned min_pts,
+                           float* out_xyz4, size_t* out_n);
+
+/* ---- pcl::NormalEstimation<PointXYZ,Normal>::compute  [PCL] features/.../impl/normal_3d.hpp */
+/* out_normal8: n x 8 floats = pcl::Normal memory image (nx ny nz 0 | curvature 0 0 0). */
+PEB_API int peb_normals_knn(peb_ctx* ctx, const void* pts, size_t n, size_t stride, int k,
+                            const float viewpoint[3], float* out_normal8);
+
+/* ---- pcl::KdTreeFLANN::nearestKSearch over the resident target (k = 1) ------------ */
+/* out_idx: original target index (-1 if the target is empty), out_d2: squared distance. */
+PEB_API int peb_nn_search(peb_ctx* ctx, const void* queries, size_t nq, size_t stride,
+                          int32_t* out_idx, float* out_d2);
+/* the brute-force FP32 validator (shared-memory tiled, no grid): same outputs */
+PEB_API int peb_nn_search_bruteforce(peb_ctx* ctx, const void* queries, size_t nq, size_t stride,
+                                     int32_t* out_idx, float* out_d2);
+
+/* ---- pcl::Registration::setInputTarget / setInputSource ---------------------------- */
+/* normals: nullable; n records of nstride bytes whose first three floats are the normal
+ * (pcl::Normal: 32, inside pcl::PointNormal: pass pts+16 and 48).  Builds the search grid;
+ * it persists until the next peb_target_set (PCL: target_cloud_updated_). */
+PEB_API int peb_target_set(peb_ctx* ctx, const void* pts, size_t n, size_t stride,
+                           const void* normals, size_t nstride);
+PEB_API int peb_source_set(peb_ctx* ctx, const void* pts, size_t n, size_t stride);
+
+/* ---- pcl::IterativeClosestPoint::align(output, guess) ------------------------------ */
+/* guess: column-major 4x4 (NULL = identity).  Optional outputs (nullable):
+ *   out_aligned_xyz4  n x 4 floats, final * input  (w = 1)
+ *   out_corr_idx      n ints, the target index matched in the LAST iteration, -1 = rejected
+ *   out_corr_d2       n floats, its squared distance */
+PEB_API int peb_icp_align(peb_ctx* ctx, const float guess[16], const peb_icp_params* params,
+                          peb_icp_result* result, float* out_aligned_xyz4,
+                          int32_t* out_corr_idx, float* out_corr_d2);
+
+/* one source, one target, H initial poses (guesses: H x 16 floats, column-major each):
+ * the shape of cv::ppf_match_3d::ICP::registerModelToScene(model, scene, poses),
+ * pose_estimation/src/opencv_surface_match.cpp:94.  results: H records. */
+PEB_API int peb_icp_align_batch(peb_ctx* ctx, const float* guesses, size_t n_guesses,
+                                const peb_icp_params* params, peb_icp_result* results);
+
+/* pcl::Registration::getFitnessScore(max_range) for an arbitrary transform */
+PEB_API int peb_fitness_score(peb_ctx* ctx, const float T[16], double max_range, double* out_fitness,
+                              int32_t* out_n_inliers);
+
+/* ---- device-resident variants (bench harness: inputs already in HBM) ---------------- */
+/* d_*: device pointers on the context's device, float4 records (xyz + pad), 16-byte aligned.
+ * Asynchronous on peb_ctx_stream(); *_dev results are device pointers too. */
+PEB_API int peb_target_set_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, const void* d_normal4);
+PEB_API int peb_source_set_dev(peb_ctx* ctx, const void* d_xyz4, size_t n);
+PEB_API int peb_icp_align_dev(peb_ctx* ctx, const float guess[16], const peb_icp_params* params,
+                              peb_icp_result* d_result);
+PEB_API int peb_icp_align_batch_dev(peb_ctx* ctx, const float* d_guesses, size_t n_guesses,
+                                    const peb_icp_params* params, peb_icp_result* d_results);
+PEB_API int peb_voxel_grid_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, float leaf_x, float leaf_y,
+                               float leaf_z, unsigned min_pts, void* d_out_xyz4, size_t* out_n);
+PEB_API int peb_normals_knn_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, int k,
+                                const float viewpoint[3], void* d_out_normal8);
+PEB_API int peb_sync(peb_ctx* ctx);
+
+/* ---- introspection used by the parity tests ---------------------------------------- */
+typedef struct peb_grid_info {
+  float origin[3];
+  float cell;          /* cell edge length                      */
+  int32_t dims[3];
+  int32_t n_points;    /* finite target points in the grid      */
+  int64_t n_cells;
+} peb_grid_info;
+PEB_API int peb_target_grid_info(peb_ctx* ctx, peb_grid_info* out);
+/* per-iteration increments of the last peb_icp_align (column-major 4x4 each);
+ * copies min(cap, iterations) matrices, returns the count via *out_n */
+PEB_API int peb_icp_trace(peb_ctx* ctx, float* out_T, size_t cap, size_t* out_n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PE_B200_H_ */
