@@ -109,6 +109,10 @@ PEB_API void peb_icp_params_default(peb_icp_params* p);
 PEB_API void* peb_ctx_stream(peb_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches claim) */
 PEB_API uint64_t peb_ctx_launch_count(const peb_ctx* ctx);
+/* tuning knobs that change speed, never results: "nn_group" (lanes per nearest-neighbour query:
+ * 1, 2, 4, 8, 16), "grid_occupancy_x100" (wanted points per occupied target-grid cell x 100;
+ * takes effect at the next peb_target_set), "profile" (0/1, see peb_profile_read) */
+PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value);
 
 /* ---- pcl::VoxelGrid<PointXYZ>::filter  [PCL] filters/.../impl/voxel_grid.hpp -------- */
 /* out_xyz4 must hold n x 4 floats (the overflow guard returns the input unchanged).
@@ -121,6 +125,10 @@ PEB_API int peb_voxel_grid(peb_ctx* ctx, const void* pts, size_t n, size_t strid
 /* out_normal8: n x 8 floats = pcl::Normal memory image (nx ny nz 0 | curvature 0 0 0). */
 PEB_API int peb_normals_knn(peb_ctx* ctx, const void* pts, size_t n, size_t stride, int k,
                             const float viewpoint[3], float* out_normal8);
+/* same, and also returns the neighbour lists KdTreeFLANN::nearestKSearch(p, k) would:
+ * out_nn_idx (nullable) n x k original indices, ascending squared distance, -1 padded */
+PEB_API int peb_normals_knn_ex(peb_ctx* ctx, const void* pts, size_t n, size_t stride, int k,
+                               const float viewpoint[3], float* out_normal8, int32_t* out_nn_idx);
 
 /* ---- pcl::KdTreeFLANN::nearestKSearch over the resident target (k = 1) ------------ */
 /* out_idx: original target index (-1 if the target is empty), out_d2: squared distance. */
@@ -181,6 +189,9 @@ typedef struct peb_grid_info {
   int64_t n_cells;
 } peb_grid_info;
 PEB_API int peb_target_grid_info(peb_ctx* ctx, peb_grid_info* out);
+/* with peb_ctx_set_int(ctx, "profile", 1): device time (ms, CUDA events on the context's stream)
+ * of every ICP kernel launch of the last align — the iteration launches, then the fitness launch */
+PEB_API int peb_profile_read(peb_ctx* ctx, float* out_ms, size_t cap, size_t* out_n);
 /* per-iteration increments of the last peb_icp_align (column-major 4x4 each);
  * copies min(cap, iterations) matrices, returns the count via *out_n */
 PEB_API int peb_icp_trace(peb_ctx* ctx, float* out_T, size_t cap, size_t* out_n);

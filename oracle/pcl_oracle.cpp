@@ -867,6 +867,8 @@ struct Icp {
       if (out_idx || out_d2) {
         if (out_idx)
           for (size_t i = 0; i < n; ++i) out_idx[i] = -1;
+        if (out_d2)
+          for (size_t i = 0; i < n; ++i) out_d2[i] = 0.0f;
         for (const Corr& c : corrs) {
           if (out_idx) out_idx[c.q] = c.m;
           if (out_d2) out_d2[c.q] = c.d2;

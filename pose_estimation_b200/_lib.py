@@ -1,0 +1,129 @@
+"""ctypes binding of libpe_b200.so (include/pe_b200.h).
+
+The shared library is the product; this module only declares its entry points.  There is no
+fallback of any kind: if the library is missing, import of the package fails, and if no B200 is
+present, `Context()` raises with the library's own message.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libpe_b200.so"
+
+PEB_OK = 0
+STATUS_NAMES = {
+    0: "PEB_OK",
+    -1: "PEB_E_INVALID_ARG",
+    -2: "PEB_E_NO_TARGET",
+    -3: "PEB_E_NO_SOURCE",
+    -4: "PEB_E_CUDA",
+    -5: "PEB_E_OOM",
+    -6: "PEB_E_UNSUPPORTED",
+}
+
+# pcl::registration::DefaultConvergenceCriteria<float>::ConvergenceState
+CONVERGENCE_CRITERIA_NOT_CONVERGED = 0
+CONVERGENCE_CRITERIA_ITERATIONS = 1
+CONVERGENCE_CRITERIA_TRANSFORM = 2
+CONVERGENCE_CRITERIA_ABS_MSE = 3
+CONVERGENCE_CRITERIA_REL_MSE = 4
+CONVERGENCE_CRITERIA_NO_CORRESPONDENCES = 5
+CONVERGENCE_CRITERIA_FAILURE_AFTER_MAX_ITERATIONS = 6
+
+ESTIMATOR_SVD = 0
+ESTIMATOR_POINT_TO_PLANE_LLS = 1
+
+
+class IcpParams(C.Structure):
+    """peb_icp_params."""
+
+    _fields_ = [
+        ("max_iterations", C.c_int32),
+        ("min_correspondences", C.c_int32),
+        ("estimator", C.c_int32),
+        ("max_iterations_similar", C.c_int32),
+        ("max_corr_dist", C.c_double),
+        ("transformation_epsilon", C.c_double),
+        ("rotation_epsilon", C.c_double),
+        ("euclidean_fitness_epsilon", C.c_double),
+        ("abs_mse_threshold", C.c_double),
+        ("rejector_max_dist", C.c_double),
+        ("fitness_max_range", C.c_double),
+    ]
+
+
+class IcpResult(C.Structure):
+    """peb_icp_result (96 bytes)."""
+
+    _fields_ = [
+        ("T", C.c_float * 16),
+        ("fitness", C.c_double),
+        ("last_mse", C.c_double),
+        ("iterations", C.c_int32),
+        ("converged", C.c_int32),
+        ("state", C.c_int32),
+        ("n_correspondences", C.c_int32),
+    ]
+
+
+class GridInfo(C.Structure):
+    _fields_ = [
+        ("origin", C.c_float * 3),
+        ("cell", C.c_float),
+        ("dims", C.c_int32 * 3),
+        ("n_points", C.c_int32),
+        ("n_cells", C.c_int64),
+    ]
+
+
+# every symbol include/pe_b200.h declares: name -> (restype, argtypes)
+_vp, _sz, _i, _f, _d = C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_double
+_pp = C.POINTER
+SYMBOLS = {
+    "peb_ctx_create": (_i, [_i, _pp(_vp)]),
+    "peb_ctx_destroy": (None, [_vp]),
+    "peb_last_error": (C.c_char_p, [_vp]),
+    "peb_version": (C.c_char_p, []),
+    "peb_icp_params_default": (None, [_pp(IcpParams)]),
+    "peb_ctx_stream": (_vp, [_vp]),
+    "peb_ctx_launch_count": (C.c_uint64, [_vp]),
+    "peb_ctx_set_int": (_i, [_vp, C.c_char_p, _i]),
+    "peb_voxel_grid": (_i, [_vp, _vp, _sz, _sz, _f, _f, _f, C.c_uint, _vp, _pp(_sz)]),
+    "peb_normals_knn": (_i, [_vp, _vp, _sz, _sz, _i, _vp, _vp]),
+    "peb_normals_knn_ex": (_i, [_vp, _vp, _sz, _sz, _i, _vp, _vp, _vp]),
+    "peb_nn_search": (_i, [_vp, _vp, _sz, _sz, _vp, _vp]),
+    "peb_nn_search_bruteforce": (_i, [_vp, _vp, _sz, _sz, _vp, _vp]),
+    "peb_target_set": (_i, [_vp, _vp, _sz, _sz, _vp, _sz]),
+    "peb_source_set": (_i, [_vp, _vp, _sz, _sz]),
+    "peb_icp_align": (_i, [_vp, _vp, _pp(IcpParams), _pp(IcpResult), _vp, _vp, _vp]),
+    "peb_icp_align_batch": (_i, [_vp, _vp, _sz, _pp(IcpParams), _vp]),
+    "peb_fitness_score": (_i, [_vp, _vp, _d, _pp(_d), _pp(C.c_int32)]),
+    "peb_target_set_dev": (_i, [_vp, _vp, _sz, _vp]),
+    "peb_source_set_dev": (_i, [_vp, _vp, _sz]),
+    "peb_icp_align_dev": (_i, [_vp, _vp, _pp(IcpParams), _vp]),
+    "peb_icp_align_batch_dev": (_i, [_vp, _vp, _sz, _pp(IcpParams), _vp]),
+    "peb_voxel_grid_dev": (_i, [_vp, _vp, _sz, _f, _f, _f, C.c_uint, _vp, _pp(_sz)]),
+    "peb_normals_knn_dev": (_i, [_vp, _vp, _sz, _i, _vp, _vp]),
+    "peb_sync": (_i, [_vp]),
+    "peb_target_grid_info": (_i, [_vp, _pp(GridInfo)]),
+    "peb_icp_trace": (_i, [_vp, _vp, _sz, _pp(_sz)]),
+    "peb_profile_read": (_i, [_vp, _vp, _sz, _pp(_sz)]),
+}
+
+
+def load() -> C.CDLL:
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C pose_estimation_b200/csrc).  pose_estimation_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError here = the library does not export what the header declares
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = load()

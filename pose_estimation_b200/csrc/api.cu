@@ -1,0 +1,481 @@
+// api.cu — the C ABI of libpe_b200.so (include/pe_b200.h): argument checking, host <-> device
+// staging and the mapping of every entry point onto the CUDA stages.  No exceptions leave this
+// file and there is no CPU implementation behind any entry point: if the device path cannot run,
+// the call fails with a peb_status and a message.
+#include <cstring>
+#include <new>
+
+#include "core_math.cuh"
+
+namespace peb {
+
+int fail(peb_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// raw records (x, y, z at the head of every `stride` bytes) -> float4 (x, y, z, w_fill)
+__global__ void __launch_bounds__(256) repack_kernel(const unsigned char* __restrict__ raw, size_t stride, int n,
+                                                     float w_fill, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* r = reinterpret_cast<const float*>(raw + static_cast<size_t>(i) * stride);
+  out[i] = make_float4(r[0], r[1], r[2], w_fill);
+}
+
+int check_cloud(peb_ctx* ctx, const char* what, const void* pts, size_t n, size_t stride) {
+  if (n > 0 && !pts) return fail(ctx, PEB_E_INVALID_ARG, "%s: null pointer with n = %zu", what, n);
+  if (stride < 12 || (stride & 3)) return fail(ctx, PEB_E_INVALID_ARG, "%s: stride %zu is not a multiple of 4 >= 12", what, stride);
+  if (n > static_cast<size_t>(INT32_MAX) / 2) return fail(ctx, PEB_E_INVALID_ARG, "%s: %zu points exceed the 2^30 limit", what, n);
+  return PEB_OK;
+}
+
+// host records -> device float4 array (dst must hold n float4)
+int upload_cloud(peb_ctx* ctx, const void* pts, size_t n, size_t stride, float w_fill, float4* d_dst) {
+  if (n == 0) return PEB_OK;
+  const size_t bytes = (n - 1) * stride + 12;  // the last record may be shorter than the stride
+  PEB_CUDA(ctx, ctx->d_stage.ensure(bytes));
+  PEB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage.p, pts, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  PEB_LAUNCH(ctx, repack_kernel, ceil_div(static_cast<long long>(n), 256), 256, 0,
+             static_cast<const unsigned char*>(ctx->d_stage.p), stride, static_cast<int>(n), w_fill, d_dst);
+  return PEB_OK;
+}
+
+int sync(peb_ctx* ctx) {
+  PEB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PEB_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int target_finish(peb_ctx* ctx, size_t n, bool has_normals) {
+  ctx->n_tgt = n;
+  ctx->tgt_has_normals = has_normals;
+  return grid_build(ctx, &ctx->tgt_grid, ctx->tgt_raw.as<float4>(), has_normals ? ctx->tgt_nrm_raw.as<float4>() : nullptr,
+                    static_cast<int>(n), ctx->grid_occupancy);
+}
+
+int upload_guesses(peb_ctx* ctx, const float* guesses, size_t H, const float** d_out) {
+  *d_out = nullptr;
+  if (!guesses) return PEB_OK;
+  PEB_CUDA(ctx, ctx->d_guesses.ensure(H * 16 * sizeof(float)));
+  PEB_CUDA(ctx, cudaMemcpyAsync(ctx->d_guesses.p, guesses, H * 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  *d_out = ctx->d_guesses.as<float>();
+  return PEB_OK;
+}
+
+}  // namespace
+}  // namespace peb
+
+using namespace peb;
+
+extern "C" {
+
+PEB_API const char* peb_version(void) { return "pe_b200 0.1 (sm_100a)"; }
+
+PEB_API void peb_icp_params_default(peb_icp_params* p) {
+  if (!p) return;
+  p->max_iterations = 10;
+  p->min_correspondences = 3;
+  p->estimator = PEB_ESTIMATOR_SVD;
+  p->max_iterations_similar = 0;
+  p->max_corr_dist = sqrt(DBL_MAX);
+  p->transformation_epsilon = 0.0;
+  p->rotation_epsilon = 0.0;
+  p->euclidean_fitness_epsilon = -DBL_MAX;
+  p->abs_mse_threshold = 1e-12;
+  p->rejector_max_dist = 0.0;
+  p->fitness_max_range = DBL_MAX;
+}
+
+PEB_API int peb_ctx_create(int device, peb_ctx** out) {
+  if (!out) return PEB_E_INVALID_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    g_create_error = std::string("peb_ctx_create: no CUDA device (") + cudaGetErrorString(e) +
+                     "); libpe_b200 has no CPU fallback";
+    return PEB_E_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    g_create_error = "peb_ctx_create: device index out of range";
+    return PEB_E_INVALID_ARG;
+  }
+  cudaDeviceProp prop{};
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    g_create_error = std::string("peb_ctx_create: device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                     std::to_string(prop.minor) + "; this library carries sm_100a code only";
+    return PEB_E_UNSUPPORTED;
+  }
+  peb_ctx* ctx = new (std::nothrow) peb_ctx();
+  if (!ctx) return PEB_E_OOM;
+  ctx->device = device;
+  DeviceGuard guard(device);
+  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = ctx->d_small.ensure(1 << 20);
+  if (e == cudaSuccess) e = ctx->h_small.ensure(1 << 16);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("peb_ctx_create: ") + cudaGetErrorString(e);
+    cudaGetLastError();
+    peb_ctx_destroy(ctx);
+    return PEB_E_CUDA;
+  }
+  *out = ctx;
+  return PEB_OK;
+}
+
+PEB_API void peb_ctx_destroy(peb_ctx* ctx) {
+  if (!ctx) return;
+  DeviceGuard guard(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->d_small, &ctx->d_scratch, &ctx->d_stage, &ctx->tgt_raw, &ctx->tgt_nrm_raw, &ctx->src, &ctx->work,
+                    &ctx->corr_idx, &ctx->corr_d2, &ctx->partials, &ctx->state, &ctx->trace, &ctx->d_guesses,
+                    &ctx->d_results, &ctx->d_aligned, &ctx->vg_in, &ctx->vg_out, &ctx->vg_flags, &ctx->vg_scan,
+                    &ctx->vg_starts, &ctx->nrm_in, &ctx->nrm_out, &ctx->nn_q, &ctx->nn_idx, &ctx->nn_d2};
+  for (DevBuf* b : bufs) b->release();
+  for (Grid* g : {&ctx->tgt_grid, &ctx->aux_grid}) {
+    g->pts.release();
+    g->normals.release();
+    g->cell_start.release();
+    g->keys.release();
+    g->vals.release();
+    g->keys_tmp.release();
+    g->vals_tmp.release();
+  }
+  for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+  ctx->h_stage.release();
+  ctx->h_small.release();
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+PEB_API const char* peb_last_error(const peb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+PEB_API void* peb_ctx_stream(peb_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
+PEB_API uint64_t peb_ctx_launch_count(const peb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
+  if (!ctx || !key) return PEB_E_INVALID_ARG;
+  if (!strcmp(key, "nn_group")) {
+    if (value != 1 && value != 2 && value != 4 && value != 8 && value != 16)
+      return fail(ctx, PEB_E_INVALID_ARG, "nn_group must be 1, 2, 4, 8 or 16");
+    ctx->nn_group = value;
+    return PEB_OK;
+  }
+  if (!strcmp(key, "grid_occupancy_x100")) {
+    if (value < 25 || value > 6400) return fail(ctx, PEB_E_INVALID_ARG, "grid_occupancy_x100 out of [25, 6400]");
+    ctx->grid_occupancy = value / 100.0f;
+    return PEB_OK;
+  }
+  if (!strcmp(key, "profile")) {
+    ctx->profile = value != 0;
+    ctx->prof_launches = 0;
+    return PEB_OK;
+  }
+  return fail(ctx, PEB_E_INVALID_ARG, "unknown option '%s'", key);
+}
+
+PEB_API int peb_sync(peb_ctx* ctx) {
+  if (!ctx) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  return sync(ctx);
+}
+
+// ---- VoxelGrid ---------------------------------------------------------------------------------
+PEB_API int peb_voxel_grid_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, float lx, float ly, float lz, unsigned min_pts,
+                               void* d_out_xyz4, size_t* out_n) {
+  if (!ctx || !out_n) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  if (n > 0 && (!d_xyz4 || !d_out_xyz4)) return fail(ctx, PEB_E_INVALID_ARG, "voxel_grid_dev: null device pointer");
+  if (n > static_cast<size_t>(INT32_MAX) / 2) return fail(ctx, PEB_E_INVALID_ARG, "voxel_grid: too many points");
+  return voxel_grid_device(ctx, static_cast<const float4*>(d_xyz4), static_cast<int>(n), lx, ly, lz, min_pts,
+                           static_cast<float4*>(d_out_xyz4), out_n);
+}
+
+PEB_API int peb_voxel_grid(peb_ctx* ctx, const void* pts, size_t n, size_t stride, float lx, float ly, float lz,
+                           unsigned min_pts, float* out_xyz4, size_t* out_n) {
+  if (!ctx || !out_n) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  *out_n = 0;
+  PEB_TRY(check_cloud(ctx, "voxel_grid", pts, n, stride));
+  if (n > 0 && !out_xyz4) return fail(ctx, PEB_E_INVALID_ARG, "voxel_grid: null output");
+  PEB_CUDA(ctx, ctx->vg_in.ensure(n * sizeof(float4)));
+  PEB_CUDA(ctx, ctx->vg_out.ensure(n * sizeof(float4)));
+  PEB_TRY(upload_cloud(ctx, pts, n, stride, 1.0f, ctx->vg_in.as<float4>()));
+  size_t m = 0;
+  PEB_TRY(voxel_grid_device(ctx, ctx->vg_in.as<float4>(), static_cast<int>(n), lx, ly, lz, min_pts,
+                            ctx->vg_out.as<float4>(), &m));
+  if (m > 0)
+    PEB_CUDA(ctx, cudaMemcpyAsync(out_xyz4, ctx->vg_out.p, m * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  PEB_TRY(sync(ctx));
+  *out_n = m;
+  return PEB_OK;
+}
+
+// ---- NormalEstimation ---------------------------------------------------------------------------
+PEB_API int peb_normals_knn_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, int k, const float viewpoint[3],
+                                void* d_out_normal8) {
+  if (!ctx) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  if (n > 0 && (!d_xyz4 || !d_out_normal8)) return fail(ctx, PEB_E_INVALID_ARG, "normals_knn_dev: null device pointer");
+  if (n > static_cast<size_t>(INT32_MAX) / 2) return fail(ctx, PEB_E_INVALID_ARG, "normals_knn: too many points");
+  const float zero[3] = {0.f, 0.f, 0.f};
+  return normals_knn_device(ctx, static_cast<const float4*>(d_xyz4), static_cast<int>(n), k, viewpoint ? viewpoint : zero,
+                            static_cast<float*>(d_out_normal8), nullptr);
+}
+
+PEB_API int peb_normals_knn_ex(peb_ctx* ctx, const void* pts, size_t n, size_t stride, int k, const float viewpoint[3],
+                               float* out_normal8, int32_t* out_nn_idx) {
+  if (!ctx) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  PEB_TRY(check_cloud(ctx, "normals_knn", pts, n, stride));
+  if (n > 0 && !out_normal8) return fail(ctx, PEB_E_INVALID_ARG, "normals_knn: null output");
+  if (k < 1) return fail(ctx, PEB_E_INVALID_ARG, "normals_knn: k must be >= 1 (got %d)", k);
+  const float zero[3] = {0.f, 0.f, 0.f};
+  PEB_CUDA(ctx, ctx->nrm_in.ensure(n * sizeof(float4)));
+  PEB_CUDA(ctx, ctx->nrm_out.ensure(n * 8 * sizeof(float)));
+  int32_t* d_nn = nullptr;
+  if (out_nn_idx) {
+    PEB_CUDA(ctx, ctx->nn_idx.ensure(n * static_cast<size_t>(k) * sizeof(int32_t)));
+    d_nn = ctx->nn_idx.as<int32_t>();
+  }
+  PEB_TRY(upload_cloud(ctx, pts, n, stride, 1.0f, ctx->nrm_in.as<float4>()));
+  PEB_TRY(normals_knn_device(ctx, ctx->nrm_in.as<float4>(), static_cast<int>(n), k, viewpoint ? viewpoint : zero,
+                             ctx->nrm_out.as<float>(), d_nn));
+  if (n > 0) {
+    PEB_CUDA(ctx, cudaMemcpyAsync(out_normal8, ctx->nrm_out.p, n * 8 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_nn_idx)
+      PEB_CUDA(ctx, cudaMemcpyAsync(out_nn_idx, d_nn, n * static_cast<size_t>(k) * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                    ctx->stream));
+  }
+  return sync(ctx);
+}
+
+PEB_API int peb_normals_knn(peb_ctx* ctx, const void* pts, size_t n, size_t stride, int k, const float viewpoint[3],
+                            float* out_normal8) {
+  return peb_normals_knn_ex(ctx, pts, n, stride, k, viewpoint, out_normal8, nullptr);
+}
+
+// ---- target / source -----------------------------------------------------------------------------
+PEB_API int peb_target_set(peb_ctx* ctx, const void* pts, size_t n, size_t stride, const void* normals, size_t nstride) {
+  if (!ctx) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  ctx->tgt_grid.valid = false;
+  PEB_TRY(check_cloud(ctx, "target_set", pts, n, stride));
+  if (normals) PEB_TRY(check_cloud(ctx, "target_set(normals)", normals, n, nstride));
+  PEB_CUDA(ctx, ctx->tgt_raw.ensure(n * sizeof(float4)));
+  PEB_TRY(upload_cloud(ctx, pts, n, stride, 1.0f, ctx->tgt_raw.as<float4>()));
+  if (normals) {
+    PEB_CUDA(ctx, ctx->tgt_nrm_raw.ensure(n * sizeof(float4)));
+    PEB_TRY(upload_cloud(ctx, normals, n, nstride, 0.0f, ctx->tgt_nrm_raw.as<float4>()));
+  }
+  return target_finish(ctx, n, normals != nullptr);
+}
+
+PEB_API int peb_target_set_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, const void* d_normal4) {
+  if (!ctx) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  ctx->tgt_grid.valid = false;
+  if (n > 0 && !d_xyz4) return fail(ctx, PEB_E_INVALID_ARG, "target_set_dev: null device pointer");
+  if (n > static_cast<size_t>(INT32_MAX) / 2) return fail(ctx, PEB_E_INVALID_ARG, "target_set: too many points");
+  PEB_CUDA(ctx, ctx->tgt_raw.ensure(n * sizeof(float4)));
+  if (n) PEB_CUDA(ctx, cudaMemcpyAsync(ctx->tgt_raw.p, d_xyz4, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (d_normal4) {
+    PEB_CUDA(ctx, ctx->tgt_nrm_raw.ensure(n * sizeof(float4)));
+    if (n) PEB_CUDA(ctx, cudaMemcpyAsync(ctx->tgt_nrm_raw.p, d_normal4, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  return target_finish(ctx, n, d_normal4 != nullptr);
+}
+
+PEB_API int peb_source_set(peb_ctx* ctx, const void* pts, size_t n, size_t stride) {
+  if (!ctx) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  ctx->src_set = false;
+  PEB_TRY(check_cloud(ctx, "source_set", pts, n, stride));
+  PEB_CUDA(ctx, ctx->src.ensure(n * sizeof(float4)));
+  PEB_TRY(upload_cloud(ctx, pts, n, stride, 1.0f, ctx->src.as<float4>()));
+  ctx->n_src = n;
+  ctx->src_set = true;
+  return PEB_OK;
+}
+
+PEB_API int peb_source_set_dev(peb_ctx* ctx, const void* d_xyz4, size_t n) {
+  if (!ctx) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  ctx->src_set = false;
+  if (n > 0 && !d_xyz4) return fail(ctx, PEB_E_INVALID_ARG, "source_set_dev: null device pointer");
+  if (n > static_cast<size_t>(INT32_MAX) / 2) return fail(ctx, PEB_E_INVALID_ARG, "source_set: too many points");
+  PEB_CUDA(ctx, ctx->src.ensure(n * sizeof(float4)));
+  if (n) PEB_CUDA(ctx, cudaMemcpyAsync(ctx->src.p, d_xyz4, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  ctx->n_src = n;
+  ctx->src_set = true;
+  return PEB_OK;
+}
+
+// ---- nearest neighbour ------------------------------------------------------------------------------
+static int nn_common(peb_ctx* ctx, const void* queries, size_t nq, size_t stride, int32_t* out_idx, float* out_d2,
+                     bool brute) {
+  if (!ctx) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  PEB_TRY(check_cloud(ctx, "nn_search", queries, nq, stride));
+  if (nq > 0 && (!out_idx || !out_d2)) return fail(ctx, PEB_E_INVALID_ARG, "nn_search: null output");
+  if (!ctx->tgt_grid.valid) return fail(ctx, PEB_E_NO_TARGET, "nn_search: no target set (peb_target_set)");
+  PEB_CUDA(ctx, ctx->nn_q.ensure(nq * sizeof(float4)));
+  PEB_CUDA(ctx, ctx->nn_idx.ensure(nq * sizeof(int32_t)));
+  PEB_CUDA(ctx, ctx->nn_d2.ensure(nq * sizeof(float)));
+  PEB_TRY(upload_cloud(ctx, queries, nq, stride, 1.0f, ctx->nn_q.as<float4>()));
+  if (brute)
+    PEB_TRY(nn_bruteforce_device(ctx, ctx->nn_q.as<float4>(), static_cast<int>(nq), ctx->nn_idx.as<int32_t>(), ctx->nn_d2.as<float>()));
+  else
+    PEB_TRY(nn_search_device(ctx, ctx->nn_q.as<float4>(), static_cast<int>(nq), ctx->nn_idx.as<int32_t>(), ctx->nn_d2.as<float>()));
+  if (nq) {
+    PEB_CUDA(ctx, cudaMemcpyAsync(out_idx, ctx->nn_idx.p, nq * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PEB_CUDA(ctx, cudaMemcpyAsync(out_d2, ctx->nn_d2.p, nq * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  return sync(ctx);
+}
+
+PEB_API int peb_nn_search(peb_ctx* ctx, const void* queries, size_t nq, size_t stride, int32_t* out_idx, float* out_d2) {
+  return nn_common(ctx, queries, nq, stride, out_idx, out_d2, false);
+}
+PEB_API int peb_nn_search_bruteforce(peb_ctx* ctx, const void* queries, size_t nq, size_t stride, int32_t* out_idx,
+                                     float* out_d2) {
+  return nn_common(ctx, queries, nq, stride, out_idx, out_d2, true);
+}
+
+// ---- ICP ---------------------------------------------------------------------------------------------
+PEB_API int peb_icp_align_batch_dev(peb_ctx* ctx, const float* d_guesses, size_t n_guesses, const peb_icp_params* params,
+                                    peb_icp_result* d_results) {
+  if (!ctx || !params) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  if (n_guesses > 0 && !d_results) return fail(ctx, PEB_E_INVALID_ARG, "align_batch_dev: null results");
+  return icp_align_device(ctx, d_guesses, n_guesses, params, d_results, false);
+}
+
+PEB_API int peb_icp_align_dev(peb_ctx* ctx, const float guess[16], const peb_icp_params* params, peb_icp_result* d_result) {
+  if (!ctx || !params || !d_result) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  const float* d_g = nullptr;
+  PEB_TRY(upload_guesses(ctx, guess, 1, &d_g));
+  return icp_align_device(ctx, d_g, 1, params, d_result, true);
+}
+
+PEB_API int peb_icp_align(peb_ctx* ctx, const float guess[16], const peb_icp_params* params, peb_icp_result* result,
+                          float* out_aligned_xyz4, int32_t* out_corr_idx, float* out_corr_d2) {
+  if (!ctx || !params || !result) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  const float* d_g = nullptr;
+  PEB_TRY(upload_guesses(ctx, guess, 1, &d_g));
+  PEB_CUDA(ctx, ctx->d_results.ensure(sizeof(peb_icp_result)));
+  PEB_TRY(icp_align_device(ctx, d_g, 1, params, ctx->d_results.as<peb_icp_result>(), true));
+  const size_t n = ctx->n_src;
+  PEB_CUDA(ctx, cudaMemcpyAsync(result, ctx->d_results.p, sizeof(peb_icp_result), cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_aligned_xyz4 && n) {
+    PEB_CUDA(ctx, ctx->d_aligned.ensure(n * sizeof(float4)));
+    PEB_TRY(icp_output_device(ctx, ctx->d_aligned.as<float4>()));
+    PEB_CUDA(ctx, cudaMemcpyAsync(out_aligned_xyz4, ctx->d_aligned.p, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (out_corr_idx && n)
+    PEB_CUDA(ctx, cudaMemcpyAsync(out_corr_idx, ctx->corr_idx.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_corr_d2 && n)
+    PEB_CUDA(ctx, cudaMemcpyAsync(out_corr_d2, ctx->corr_d2.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  PEB_TRY(sync(ctx));
+  ctx->last_iterations = result->iterations;
+  return PEB_OK;
+}
+
+PEB_API int peb_icp_align_batch(peb_ctx* ctx, const float* guesses, size_t n_guesses, const peb_icp_params* params,
+                                peb_icp_result* results) {
+  if (!ctx || !params) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  if (n_guesses == 0) return PEB_OK;
+  if (!guesses || !results) return fail(ctx, PEB_E_INVALID_ARG, "align_batch: null guesses / results");
+  const float* d_g = nullptr;
+  PEB_TRY(upload_guesses(ctx, guesses, n_guesses, &d_g));
+  PEB_CUDA(ctx, ctx->d_results.ensure(n_guesses * sizeof(peb_icp_result)));
+  PEB_TRY(icp_align_device(ctx, d_g, n_guesses, params, ctx->d_results.as<peb_icp_result>(), false));
+  PEB_CUDA(ctx, cudaMemcpyAsync(results, ctx->d_results.p, n_guesses * sizeof(peb_icp_result), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+  return sync(ctx);
+}
+
+PEB_API int peb_fitness_score(peb_ctx* ctx, const float T[16], double max_range, double* out_fitness, int32_t* out_n_inliers) {
+  if (!ctx || !T || !out_fitness) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  const float* d_g = nullptr;
+  PEB_TRY(upload_guesses(ctx, T, 1, &d_g));
+  PEB_CUDA(ctx, ctx->d_results.ensure(sizeof(peb_icp_result)));
+  PEB_TRY(fitness_device(ctx, d_g, max_range, ctx->d_results.as<peb_icp_result>()));
+  peb_icp_result* h = ctx->h_small.as<peb_icp_result>() + 8;
+  PEB_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_results.p, sizeof(peb_icp_result), cudaMemcpyDeviceToHost, ctx->stream));
+  PEB_TRY(sync(ctx));
+  *out_fitness = h->fitness;
+  if (out_n_inliers) *out_n_inliers = h->n_correspondences;
+  return PEB_OK;
+}
+
+// ---- introspection ----------------------------------------------------------------------------------
+PEB_API int peb_target_grid_info(peb_ctx* ctx, peb_grid_info* out) {
+  if (!ctx || !out) return PEB_E_INVALID_ARG;
+  if (!ctx->tgt_grid.valid) return fail(ctx, PEB_E_NO_TARGET, "grid_info: no target set");
+  const GridView& v = ctx->tgt_grid.view;
+  out->origin[0] = v.ox;
+  out->origin[1] = v.oy;
+  out->origin[2] = v.oz;
+  out->cell = v.h;
+  out->dims[0] = v.dx;
+  out->dims[1] = v.dy;
+  out->dims[2] = v.dz;
+  out->n_points = v.n;
+  out->n_cells = ctx->tgt_grid.n_cells;
+  return PEB_OK;
+}
+
+PEB_API int peb_profile_read(peb_ctx* ctx, float* out_ms, size_t cap, size_t* out_n) {
+  if (!ctx || !out_n) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  PEB_TRY(sync(ctx));
+  size_t cnt = static_cast<size_t>(ctx->prof_launches);
+  if (cnt > cap) cnt = cap;
+  *out_n = cnt;
+  for (size_t i = 0; i < cnt && out_ms; ++i)
+    PEB_CUDA(ctx, cudaEventElapsedTime(&out_ms[i], ctx->prof_events[2 * i], ctx->prof_events[2 * i + 1]));
+  return PEB_OK;
+}
+
+PEB_API int peb_icp_trace(peb_ctx* ctx, float* out_T, size_t cap, size_t* out_n) {
+  if (!ctx || !out_n) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  size_t cnt = static_cast<size_t>(ctx->last_iterations > 0 ? ctx->last_iterations : 0);
+  if (cnt > static_cast<size_t>(ctx->last_trace_cap)) cnt = ctx->last_trace_cap;
+  if (cnt > cap) cnt = cap;
+  *out_n = cnt;
+  if (cnt && out_T) {
+    PEB_CUDA(ctx, cudaMemcpyAsync(out_T, ctx->trace.p, cnt * 16 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PEB_TRY(sync(ctx));
+  }
+  return PEB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,197 @@
+// common.cuh — context, buffers and launch helpers shared by every translation unit of
+// libpe_b200.so.  sm_100a only; the whole library is compiled with -fmad=false so that float
+// expressions keep PCL's source-level rounding; fused operations are written
+// explicitly (fma()) where they are wanted.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/pe_b200.h"
+
+#define PEB_HD __host__ __device__ __forceinline__
+
+namespace peb {
+
+constexpr int kSmCount = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+
+// The uniform grid over a cloud (the kd-tree replacement, SURVEY.md 8a-2').  Points are sorted
+// by cell id (x fastest), cell_start has n_cells + 1 entries, so the points of the x-run of
+// cells [c0, c1] of one (y, z) row are the contiguous range [cell_start[c0], cell_start[c1 + 1]).
+struct GridView {
+  const float4* pts;            // sorted; .w carries the ORIGINAL index (int bits)
+  const float4* normals;        // sorted like pts (nullable)
+  const uint32_t* cell_start;   // n_cells + 1
+  float ox, oy, oz;             // origin = min corner of the finite bounding box
+  float h, inv_h;               // cell edge and its reciprocal
+  int dx, dy, dz;               // cells per axis
+  int n;                        // finite points
+};
+
+struct Grid {
+  DevBuf pts, normals, cell_start, keys, vals, keys_tmp, vals_tmp;
+  GridView view{};
+  long long n_cells = 0;
+  int n_input = 0;    // records handed in (including non-finite)
+  bool valid = false;
+};
+
+}  // namespace peb
+
+// ---- the context ---------------------------------------------------------------------------
+struct peb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  int nn_group = 8;             // lanes that share one nearest-neighbour query (1, 2, 4, 8, 16)
+  float grid_occupancy = 2.0f;  // wanted mean points per occupied cell of the target grid
+
+  peb::PinnedBuf h_stage;    // host repack / readback staging
+  peb::PinnedBuf h_small;    // small results (bbox, counters, peb_icp_result)
+  peb::DevBuf d_small;       // device side of h_small
+  peb::DevBuf d_scratch;     // sort histograms, scan block sums, ...
+  peb::DevBuf d_stage;       // raw host records before the repack kernel
+
+  // target (scene)
+  peb::DevBuf tgt_raw;       // float4 xyz(w) in original order
+  peb::DevBuf tgt_nrm_raw;   // float4 normals in original order (if any)
+  size_t n_tgt = 0;
+  bool tgt_has_normals = false;
+  peb::Grid tgt_grid;
+
+  // source (model)
+  peb::DevBuf src;           // float4 xyz1, original order
+  size_t n_src = 0;
+  bool src_set = false;
+
+  // ICP working set
+  peb::DevBuf work;          // float4 working cloud (single align)
+  peb::DevBuf corr_idx, corr_d2;
+  peb::DevBuf partials;      // per-block double partial sums
+  peb::DevBuf state;         // IcpState per hypothesis
+  peb::DevBuf trace;         // per-iteration increments of the last single align
+  peb::DevBuf d_guesses, d_results, d_aligned;
+  int last_trace_cap = 0;
+  int last_iterations = 0;
+  // optional per-launch timing of the ICP kernels (bench.py's roofline leg): event pairs around
+  // every iteration launch + the fitness launch of the last align
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_events;
+  int prof_launches = 0;
+  peb::DevBuf nn_q, nn_idx, nn_d2;   // peb_nn_search staging
+
+  // voxel grid / normals scratch
+  peb::Grid aux_grid;
+  peb::DevBuf vg_in, vg_out, vg_flags, vg_scan, vg_starts;
+  peb::DevBuf nrm_in, nrm_out;
+};
+
+namespace peb {
+
+int fail(peb_ctx* ctx, int code, const char* fmt, ...);
+
+#define PEB_CUDA(ctx, expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      cudaGetLastError();                                                                     \
+      return peb::fail((ctx), _e == cudaErrorMemoryAllocation ? PEB_E_OOM : PEB_E_CUDA,       \
+                       "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+    }                                                                                         \
+  } while (0)
+
+#define PEB_TRY(expr)          \
+  do {                         \
+    int _rc = (expr);          \
+    if (_rc != PEB_OK) return _rc; \
+  } while (0)
+
+// launch + count (bench.py's gpu_launches reads the counter)
+#define PEB_LAUNCH(ctx, kernel, grid, block, smem, ...)                        \
+  do {                                                                         \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);           \
+    (ctx)->launches++;                                                         \
+    PEB_CUDA((ctx), cudaGetLastError());                                       \
+  } while (0)
+
+static inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+// ---- stages implemented in the other translation units -------------------------------------
+// radix_sort.cu
+int sort_pairs(peb_ctx* ctx, uint32_t* keys, uint32_t* vals, uint32_t* keys_tmp, uint32_t* vals_tmp, int n,
+               int key_bits, uint32_t** keys_out, uint32_t** vals_out);
+int exclusive_scan_u32(peb_ctx* ctx, const uint32_t* in, uint32_t* out, int n, uint32_t* d_total);
+// grid.cu
+int grid_build(peb_ctx* ctx, Grid* g, const float4* d_pts, const float4* d_normals, int n, float occupancy);
+int bbox_finite(peb_ctx* ctx, const float4* d_pts, int n, float mn[3], float mx[3], int* n_finite);
+// icp.cu
+int icp_align_device(peb_ctx* ctx, const float* d_guesses /*nullable: identity*/, size_t H, const peb_icp_params* prm,
+                     peb_icp_result* d_results, bool single_mode);
+int icp_output_device(peb_ctx* ctx, float4* d_out);
+int nn_search_device(peb_ctx* ctx, const float4* d_q, int nq, int32_t* d_idx, float* d_d2);
+// fitness of one transform (device, 16 floats); the record's n_correspondences carries the inlier count
+int fitness_device(peb_ctx* ctx, const float* d_T, double max_range, peb_icp_result* d_result);
+// brute.cu
+int nn_bruteforce_device(peb_ctx* ctx, const float4* d_q, int nq, int32_t* d_idx, float* d_d2);
+// voxel.cu
+int voxel_grid_device(peb_ctx* ctx, const float4* d_in, int n, float lx, float ly, float lz, unsigned min_pts,
+                      float4* d_out, size_t* out_n);
+// normals.cu
+int normals_knn_device(peb_ctx* ctx, const float4* d_in, int n, int k, const float vp[3], float* d_out8,
+                       int32_t* d_out_nn /*nullable, n x k original indices*/);
+
+}  // namespace peb

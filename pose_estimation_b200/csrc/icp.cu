@@ -1,0 +1,560 @@
+// icp.cu — pcl::IterativeClosestPoint / IterativeClosestPointWithNormals on the device.
+//
+// One launch per ICP iteration, no host round trip inside an align:
+//
+//   icp_iteration_kernel   grid = (blocks_per_hypothesis, H)
+//     every query:  working point <- increment of the previous iteration * working point
+//                   ([PCL] registration/impl/icp.hpp : transformCloud, in place, float)
+//                   exact 1-NN over the uniform grid (nn_search.cuh)
+//                   [PCL] registration/impl/correspondence_estimation.hpp : determineCorrespondences
+//                   (d2 > max_dist^2 rejected) and correspondence_rejection_distance.cpp (keep iff <)
+//                   moments of the estimator accumulated in double
+//     every block:  warp shuffle -> shared memory -> one partial record in global memory
+//     last block :  (atomic ticket) sums the partial records in block order — deterministic —
+//                   and runs the solve + convergence criteria in double (core_math.cuh),
+//                   leaving the increment and the state for the next launch.
+//   icp_fitness_kernel     [PCL] registration/impl/registration.hpp : getFitnessScore, then packs
+//                   the peb_icp_result record.
+//
+// Later launches of an align that has already converged return at once (state.active == 0).
+// The batched mode is the same code with H > 1: one working cloud per hypothesis so that PCL's
+// incremental float update is reproduced exactly for every hypothesis.
+#include "nn_search.cuh"
+
+namespace peb {
+
+namespace {
+
+constexpr int kIcpThreads = 256;
+
+struct IcpLaunch {
+  GridView grid;
+  const float4* src;     // n_src records, original order
+  float4* work;          // H x n_src working clouds
+  IcpState* states;      // H
+  double* partials;      // H x blocks_per_hyp x kAccMax
+  int32_t* corr_idx;     // nullable, n_src (single align only)
+  float* corr_d2;        // nullable
+  Mat4* trace;           // nullable, trace_cap increments (single align only)
+  peb_icp_result* results;  // H (fitness kernel)
+  IcpCriteria crit;
+  double max_dist_sqr;
+  double fitness_max_range;
+  float stop_d2;         // NN search may stop once every unexamined point is farther than this
+  float fitness_stop_d2;
+  float rej_max2;
+  int use_rejector;
+  int n_src;
+  int blocks_per_hyp;
+  int trace_cap;
+  int fitness_only;      // peb_fitness_score: the record's n_correspondences carries the inlier count
+};
+
+__global__ void icp_init_kernel(IcpState* __restrict__ states, const float* __restrict__ guesses, int H) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  IcpState st;
+  st.inc = mat4_identity();
+  if (guesses) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) st.final_t.m[i] = guesses[16 * h + i];
+  } else {
+    st.final_t = mat4_identity();
+  }
+  st.prev_mse = DBL_MAX;
+  st.cur_mse = DBL_MAX;
+  st.fit_sum = 0.0;
+  st.iterations = 0;
+  st.state = PEB_NOT_CONVERGED;
+  st.converged = 0;
+  st.similar = 0;
+  st.ncorr = 0;
+  st.active = 1;
+  st.fit_n = 0;
+  st.pad0 = 0;
+  st.ticket = 0;
+  st.ticket_fit = 0;
+  st.pad1[0] = st.pad1[1] = 0;
+  states[h] = st;
+}
+
+// sums NACC doubles over the block; the result is valid in threads [0, NACC) of warp 0
+template <int NACC>
+__device__ __forceinline__ double block_reduce_acc(double (&acc)[NACC], double (*sm)[kAccMax]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) {
+    double v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if (lane == 0) sm[warp][i] = v;
+  }
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x < NACC) {
+#pragma unroll
+    for (int w = 0; w < kIcpThreads / 32; ++w) r += sm[w][threadIdx.x];
+  }
+  return r;
+}
+
+// the last block of a hypothesis sums the per-block records in block order (fixed order => the
+// double sums do not depend on scheduling); result in sm_out[0..NACC)
+template <int NACC>
+__device__ __forceinline__ void reduce_partials(const double* __restrict__ part, int n_blocks, double (*sm)[kAccMax],
+                                                double* sm_out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kW = kIcpThreads / 32;
+  double v = 0.0;
+  if (lane < NACC) {
+    const int per = (n_blocks + kW - 1) / kW;
+    const int b0 = warp * per, b1 = min(b0 + per, n_blocks);
+    for (int b = b0; b < b1; ++b) v += __ldcg(part + static_cast<size_t>(b) * kAccMax + lane);
+    sm[warp][lane] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NACC) {
+    double r = 0.0;
+#pragma unroll
+    for (int w = 0; w < kW; ++w) r += sm[w][threadIdx.x];
+    sm_out[threadIdx.x] = r;
+  }
+  __syncthreads();
+}
+
+template <int G, int EST>
+__global__ void __launch_bounds__(kIcpThreads) icp_iteration_kernel(const IcpLaunch L) {
+  constexpr int NACC = (EST == PEB_ESTIMATOR_SVD) ? kAccSvd : kAccLls;
+  __shared__ double sm[kIcpThreads / 32][kAccMax];
+  __shared__ double sm_tot[kAccMax];
+  __shared__ float s_inc[16];
+  __shared__ int s_flags[3];  // active, first iteration, apply transform
+  const int h = blockIdx.y;
+  IcpState* st = L.states + h;
+  if (threadIdx.x < 16) s_inc[threadIdx.x] = __ldcg(&st->inc.m[threadIdx.x]);
+  if (threadIdx.x == 32) {
+    const int active = __ldcg(&st->active);
+    const int first = __ldcg(&st->iterations) == 0;
+    int apply = 1;
+    if (first) {
+      // [PCL] icp.hpp: the guess is applied only if it differs from the identity
+      apply = 0;
+      for (int i = 0; i < 16; ++i) {
+        const float g = __ldcg(&st->final_t.m[i]);
+        if (g != ((i % 5 == 0) ? 1.0f : 0.0f)) apply = 1;
+      }
+    }
+    s_flags[0] = active;
+    s_flags[1] = first;
+    s_flags[2] = apply;
+  }
+  __syncthreads();
+  if (!s_flags[0]) return;
+  const bool first = s_flags[1] != 0;
+  const bool apply = s_flags[2] != 0;
+  float T[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) T[i] = first ? __ldcg(&st->final_t.m[i]) : s_inc[i];
+
+  double acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+
+  float4* work = L.work + static_cast<size_t>(h) * L.n_src;
+  const int lane_in_group = threadIdx.x & (G - 1);
+  constexpr int kQ = kIcpThreads / G;  // queries per block per pass
+  const int q_local = threadIdx.x / G;
+  for (int base = blockIdx.x * kQ; base < L.n_src; base += L.blocks_per_hyp * kQ) {
+    const int i = base + q_local;
+    const bool in = i < L.n_src;
+    float4 p = make_float4(0.f, 0.f, 0.f, 1.f);
+    if (in) p = first ? L.src[i] : work[i];
+    const bool valid = in && finite3(p.x, p.y, p.z);
+    if (valid && apply) {
+      float ox, oy, oz;
+      transform_icp(T, p.x, p.y, p.z, ox, oy, oz);
+      p.x = ox;
+      p.y = oy;
+      p.z = oz;
+    }
+    p.w = 1.0f;
+    if (in && lane_in_group == 0 && (first || (valid && apply))) work[i] = p;
+    // queries of a group run the search together; invalid ones idle through it
+    NnBest best;
+    best.d2 = pos_inf();
+    best.idx = -1;
+    best.j = -1;
+    if (valid) best = grid_nn<G>(L.grid, p.x, p.y, p.z, L.stop_d2);
+    bool keep = valid && best.idx >= 0;
+    if (keep && static_cast<double>(best.d2) > L.max_dist_sqr) keep = false;
+    if (keep && L.use_rejector && !(best.d2 < L.rej_max2)) keep = false;
+    if (in && lane_in_group == 0) {
+      if (L.corr_idx) L.corr_idx[i] = keep ? best.idx : -1;
+      if (L.corr_d2) L.corr_d2[i] = keep ? best.d2 : 0.0f;
+    }
+    if (keep && lane_in_group == 0) {
+      const float4 t = L.grid.pts[best.j];
+      if (EST == PEB_ESTIMATOR_SVD) {
+        const double sx = p.x, sy = p.y, sz = p.z, tx = t.x, ty = t.y, tz = t.z;
+        acc[0] += 1.0;
+        acc[1] += sx;
+        acc[2] += sy;
+        acc[3] += sz;
+        acc[4] += tx;
+        acc[5] += ty;
+        acc[6] += tz;
+        acc[7] += tx * sx;
+        acc[8] += tx * sy;
+        acc[9] += tx * sz;
+        acc[10] += ty * sx;
+        acc[11] += ty * sy;
+        acc[12] += ty * sz;
+        acc[13] += tz * sx;
+        acc[14] += tz * sy;
+        acc[15] += tz * sz;
+        acc[16] += static_cast<double>(best.d2);
+      } else {
+        acc[0] += 1.0;
+        acc[28] += static_cast<double>(best.d2);
+        const float4 nr = L.grid.normals[best.j];
+        // [PCL] transformation_estimation_point_to_plane_lls.hpp: pairs with a non-finite
+        // member are left out of the normal equations (they still count as correspondences)
+        if (finite3(t.x, t.y, t.z) && finite3(nr.x, nr.y, nr.z)) {
+          const float sx = p.x, sy = p.y, sz = p.z, dx = t.x, dy = t.y, dz = t.z;
+          const float nx = nr.x, ny = nr.y, nz = nr.z;
+          const double a = nz * sy - ny * sz;  // float expressions, widened afterwards
+          const double b = nx * sz - nz * sx;
+          const double c = ny * sx - nx * sy;
+          acc[1] += a * a;
+          acc[2] += a * b;
+          acc[3] += a * c;
+          acc[4] += a * nx;
+          acc[5] += a * ny;
+          acc[6] += a * nz;
+          acc[7] += b * b;
+          acc[8] += b * c;
+          acc[9] += b * nx;
+          acc[10] += b * ny;
+          acc[11] += b * nz;
+          acc[12] += c * c;
+          acc[13] += c * nx;
+          acc[14] += c * ny;
+          acc[15] += c * nz;
+          acc[16] += nx * nx;  // float products
+          acc[17] += nx * ny;
+          acc[18] += nx * nz;
+          acc[19] += ny * ny;
+          acc[20] += ny * nz;
+          acc[21] += nz * nz;
+          const double d = nx * dx + ny * dy + nz * dz - nx * sx - ny * sy - nz * sz;
+          acc[22] += a * d;
+          acc[23] += b * d;
+          acc[24] += c * d;
+          acc[25] += nx * d;
+          acc[26] += ny * d;
+          acc[27] += nz * d;
+        }
+      }
+    }
+  }
+
+  const double r = block_reduce_acc<NACC>(acc, sm);
+  double* part = L.partials + (static_cast<size_t>(h) * L.blocks_per_hyp) * kAccMax;
+  if (threadIdx.x < NACC) __stcg(part + static_cast<size_t>(blockIdx.x) * kAccMax + threadIdx.x, r);
+  __threadfence();
+  __syncthreads();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(&st->ticket, 1u);
+    s_last = (t == static_cast<unsigned>(L.blocks_per_hyp) - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  reduce_partials<NACC>(part, L.blocks_per_hyp, sm, sm_tot);
+  if (threadIdx.x == 0) {
+    IcpState s = *st;
+    icp_finish_iteration(s, L.crit, sm_tot);
+    s.ticket = 0;
+    if (L.trace && s.state != PEB_NO_CORRESPONDENCES && s.iterations >= 1 && s.iterations <= L.trace_cap)
+      L.trace[s.iterations - 1] = s.inc;
+    *st = s;
+  }
+}
+
+// [PCL] registration/impl/registration.hpp : getFitnessScore(max_range) with the final transform
+// applied by pcl::transformPointCloud's association (transform_tpc), then the result record.
+template <int G>
+__global__ void __launch_bounds__(kIcpThreads) icp_fitness_kernel(const IcpLaunch L) {
+  __shared__ double sm[kIcpThreads / 32][kAccMax];
+  __shared__ double sm_tot[kAccMax];
+  const int h = blockIdx.y;
+  IcpState* st = L.states + h;
+  float T[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) T[i] = __ldcg(&st->final_t.m[i]);
+  double acc[2] = {0.0, 0.0};
+  const int lane_in_group = threadIdx.x & (G - 1);
+  constexpr int kQ = kIcpThreads / G;
+  const int q_local = threadIdx.x / G;
+  for (int base = blockIdx.x * kQ; base < L.n_src; base += L.blocks_per_hyp * kQ) {
+    const int i = base + q_local;
+    float4 p = make_float4(0.f, 0.f, 0.f, 1.f);
+    if (i < L.n_src) p = L.src[i];
+    const bool valid = i < L.n_src && finite3(p.x, p.y, p.z);
+    NnBest best;
+    best.d2 = pos_inf();
+    best.idx = -1;
+    best.j = -1;
+    if (valid) {
+      float qx, qy, qz;
+      transform_tpc(T, p.x, p.y, p.z, qx, qy, qz);
+      best = grid_nn<G>(L.grid, qx, qy, qz, L.fitness_stop_d2);
+    }
+    if (valid && best.idx >= 0 && lane_in_group == 0 && static_cast<double>(best.d2) <= L.fitness_max_range) {
+      acc[0] += static_cast<double>(best.d2);
+      acc[1] += 1.0;
+    }
+  }
+  const double r = block_reduce_acc<2>(acc, sm);
+  double* part = L.partials + (static_cast<size_t>(h) * L.blocks_per_hyp) * kAccMax;
+  if (threadIdx.x < 2) __stcg(part + static_cast<size_t>(blockIdx.x) * kAccMax + threadIdx.x, r);
+  __threadfence();
+  __syncthreads();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(&st->ticket_fit, 1u);
+    s_last = (t == static_cast<unsigned>(L.blocks_per_hyp) - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  reduce_partials<2>(part, L.blocks_per_hyp, sm, sm_tot);
+  if (threadIdx.x == 0) {
+    IcpState s = *st;
+    s.fit_sum = sm_tot[0];
+    s.fit_n = static_cast<int>(sm_tot[1]);
+    s.ticket_fit = 0;
+    *st = s;
+    peb_icp_result res;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) res.T[i] = s.final_t.m[i];
+    res.fitness = s.fit_n > 0 ? s.fit_sum / static_cast<double>(s.fit_n) : DBL_MAX;
+    res.last_mse = s.cur_mse;
+    res.iterations = s.iterations;
+    res.converged = s.converged;
+    res.state = s.state;
+    res.n_correspondences = L.fitness_only ? s.fit_n : s.ncorr;
+    L.results[h] = res;
+  }
+}
+
+// output = final * input ([PCL] icp.hpp: transformCloud(*input_, output, final_transformation_))
+__global__ void __launch_bounds__(256) icp_output_kernel(const float4* __restrict__ src, int n,
+                                                         const IcpState* __restrict__ st, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float T[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) T[k] = __ldg(&st->final_t.m[k]);
+  float4 p = src[i];
+  if (finite3(p.x, p.y, p.z)) {
+    float ox, oy, oz;
+    transform_icp(T, p.x, p.y, p.z, ox, oy, oz);
+    p.x = ox;
+    p.y = oy;
+    p.z = oz;
+  }
+  p.w = 1.0f;
+  out[i] = p;
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) nn_search_kernel(const GridView g, const float4* __restrict__ q, int nq,
+                                                        int32_t* __restrict__ out_idx, float* __restrict__ out_d2) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int lane_in_group = threadIdx.x & (G - 1);
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < nq) p = q[i];
+  const bool valid = i < nq && finite3(p.x, p.y, p.z);
+  NnBest best;
+  best.d2 = pos_inf();
+  best.idx = -1;
+  best.j = -1;
+  if (valid) best = grid_nn<G>(g, p.x, p.y, p.z, pos_inf());
+  if (i < nq && lane_in_group == 0) {
+    out_idx[i] = best.idx;
+    out_d2[i] = best.d2;
+  }
+}
+
+float stop_bound(double max_dist_sqr) {
+  // smallest float that is >= max_dist_sqr (so that nothing acceptable is cut off), inf if it does not fit
+  if (!(max_dist_sqr < static_cast<double>(FLT_MAX))) return INFINITY;
+  if (max_dist_sqr < 0.0) return 0.0f;
+  float f = static_cast<float>(max_dist_sqr);
+  if (static_cast<double>(f) < max_dist_sqr) f = nextafterf(f, INFINITY);
+  return f;
+}
+
+int prof_mark(peb_ctx* ctx, int slot) {
+  if (!ctx->profile) return PEB_OK;
+  while (static_cast<int>(ctx->prof_events.size()) <= slot) {
+    cudaEvent_t e;
+    PEB_CUDA(ctx, cudaEventCreate(&e));
+    ctx->prof_events.push_back(e);
+  }
+  PEB_CUDA(ctx, cudaEventRecord(ctx->prof_events[slot], ctx->stream));
+  return PEB_OK;
+}
+
+template <int G>
+int launch_iterations(peb_ctx* ctx, const IcpLaunch& L, size_t H, int max_iterations, int estimator) {
+  dim3 grid(L.blocks_per_hyp, static_cast<unsigned>(H));
+  ctx->prof_launches = 0;
+  for (int it = 0; it < max_iterations; ++it) {
+    PEB_TRY(prof_mark(ctx, 2 * it));
+    if (estimator == PEB_ESTIMATOR_SVD)
+      PEB_LAUNCH(ctx, (icp_iteration_kernel<G, PEB_ESTIMATOR_SVD>), grid, kIcpThreads, 0, L);
+    else
+      PEB_LAUNCH(ctx, (icp_iteration_kernel<G, PEB_ESTIMATOR_POINT_TO_PLANE_LLS>), grid, kIcpThreads, 0, L);
+    PEB_TRY(prof_mark(ctx, 2 * it + 1));
+  }
+  PEB_TRY(prof_mark(ctx, 2 * max_iterations));
+  PEB_LAUNCH(ctx, icp_fitness_kernel<G>, grid, kIcpThreads, 0, L);
+  PEB_TRY(prof_mark(ctx, 2 * max_iterations + 1));
+  if (ctx->profile) ctx->prof_launches = max_iterations + 1;
+  return PEB_OK;
+}
+
+}  // namespace
+
+namespace {
+
+// fills everything of the launch record that does not depend on the mode
+int prepare_launch(peb_ctx* ctx, size_t H, const peb_icp_params* prm, IcpLaunch& L) {
+  const int n = static_cast<int>(ctx->n_src);
+  const int G = ctx->nn_group;
+  L.grid = ctx->tgt_grid.view;
+  L.src = ctx->src.as<float4>();
+  L.n_src = n;
+  // one block handles 256/G queries per pass; single aligns spread over the whole chip, batched
+  // aligns give every hypothesis a few blocks and let grid.y fill the machine
+  const int want = ceil_div(std::max(n, 1), kIcpThreads / G);
+  int bph;
+  if (H == 1)
+    bph = std::min(want, kSmCount * 8);
+  else
+    bph = std::min(want, std::max(1, static_cast<int>((kSmCount * 16 + H - 1) / H)));
+  L.blocks_per_hyp = std::max(bph, 1);
+  PEB_CUDA(ctx, ctx->work.ensure(std::max<size_t>(H * static_cast<size_t>(n), 1) * sizeof(float4)));
+  PEB_CUDA(ctx, ctx->state.ensure(H * sizeof(IcpState)));
+  PEB_CUDA(ctx, ctx->partials.ensure(H * static_cast<size_t>(L.blocks_per_hyp) * kAccMax * sizeof(double)));
+  L.work = ctx->work.as<float4>();
+  L.states = ctx->state.as<IcpState>();
+  L.partials = ctx->partials.as<double>();
+  L.crit.max_iterations = prm->max_iterations;
+  L.crit.min_correspondences = prm->min_correspondences;
+  L.crit.max_similar = prm->max_iterations_similar;
+  L.crit.estimator = prm->estimator;
+  L.crit.mse_abs = prm->abs_mse_threshold;
+  L.crit.mse_rel = prm->euclidean_fitness_epsilon;
+  L.crit.translation_threshold = prm->transformation_epsilon;
+  L.crit.rotation_threshold = prm->rotation_epsilon > 0 ? prm->rotation_epsilon : 1.0 - prm->transformation_epsilon;
+  L.max_dist_sqr = prm->max_corr_dist * prm->max_corr_dist;
+  L.use_rejector = prm->rejector_max_dist > 0 ? 1 : 0;
+  L.rej_max2 = static_cast<float>(prm->rejector_max_dist * prm->rejector_max_dist);
+  float stop = stop_bound(L.max_dist_sqr);
+  if (L.use_rejector) stop = fminf(stop, L.rej_max2);
+  L.stop_d2 = stop;
+  L.fitness_max_range = prm->fitness_max_range;
+  L.fitness_stop_d2 = stop_bound(prm->fitness_max_range);
+  return PEB_OK;
+}
+
+}  // namespace
+
+int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_icp_params* prm,
+                     peb_icp_result* d_results, bool single_mode) {
+  if (!ctx->tgt_grid.valid) return fail(ctx, PEB_E_NO_TARGET, "align: no target set (peb_target_set)");
+  if (!ctx->src_set) return fail(ctx, PEB_E_NO_SOURCE, "align: no source set (peb_source_set)");
+  if (H == 0) return PEB_OK;
+  if (prm->max_iterations < 0) return fail(ctx, PEB_E_INVALID_ARG, "align: max_iterations < 0");
+  if (prm->estimator != PEB_ESTIMATOR_SVD && prm->estimator != PEB_ESTIMATOR_POINT_TO_PLANE_LLS)
+    return fail(ctx, PEB_E_UNSUPPORTED, "align: unknown estimator %d (no CPU fallback)", prm->estimator);
+  if (prm->estimator == PEB_ESTIMATOR_POINT_TO_PLANE_LLS && !ctx->tgt_has_normals)
+    return fail(ctx, PEB_E_INVALID_ARG, "align: point-to-plane needs target normals (peb_target_set normals)");
+  const int n = static_cast<int>(ctx->n_src);
+  IcpLaunch L{};
+  PEB_TRY(prepare_launch(ctx, H, prm, L));
+  L.results = d_results;
+  if (single_mode) {
+    PEB_CUDA(ctx, ctx->corr_idx.ensure(std::max(n, 1) * sizeof(int32_t)));
+    PEB_CUDA(ctx, ctx->corr_d2.ensure(std::max(n, 1) * sizeof(float)));
+    const int cap = std::max(prm->max_iterations, 1);
+    PEB_CUDA(ctx, ctx->trace.ensure(static_cast<size_t>(cap) * sizeof(Mat4)));
+    L.corr_idx = ctx->corr_idx.as<int32_t>();
+    L.corr_d2 = ctx->corr_d2.as<float>();
+    L.trace = ctx->trace.as<Mat4>();
+    L.trace_cap = cap;
+    ctx->last_trace_cap = cap;
+  }
+  PEB_LAUNCH(ctx, icp_init_kernel, ceil_div(static_cast<long long>(H), 128), 128, 0, L.states, d_guesses,
+             static_cast<int>(H));
+  // PCL runs the loop body at least once (do ... while), also for max_iterations <= 1
+  const int launches = std::max(prm->max_iterations, 1);
+  switch (ctx->nn_group) {
+    case 1: return launch_iterations<1>(ctx, L, H, launches, prm->estimator);
+    case 2: return launch_iterations<2>(ctx, L, H, launches, prm->estimator);
+    case 4: return launch_iterations<4>(ctx, L, H, launches, prm->estimator);
+    case 8: return launch_iterations<8>(ctx, L, H, launches, prm->estimator);
+    case 16: return launch_iterations<16>(ctx, L, H, launches, prm->estimator);
+    default: return fail(ctx, PEB_E_INVALID_ARG, "nn group width %d is not one of 1,2,4,8,16", ctx->nn_group);
+  }
+}
+
+int fitness_device(peb_ctx* ctx, const float* d_T, double max_range, peb_icp_result* d_result) {
+  if (!ctx->tgt_grid.valid) return fail(ctx, PEB_E_NO_TARGET, "fitness_score: no target set (peb_target_set)");
+  if (!ctx->src_set) return fail(ctx, PEB_E_NO_SOURCE, "fitness_score: no source set (peb_source_set)");
+  peb_icp_params prm;
+  peb_icp_params_default(&prm);
+  prm.fitness_max_range = max_range;
+  IcpLaunch L{};
+  PEB_TRY(prepare_launch(ctx, 1, &prm, L));
+  L.results = d_result;
+  L.fitness_only = 1;
+  PEB_LAUNCH(ctx, icp_init_kernel, 1, 128, 0, L.states, d_T, 1);
+  dim3 grid(L.blocks_per_hyp, 1);
+  switch (ctx->nn_group) {
+    case 1: PEB_LAUNCH(ctx, icp_fitness_kernel<1>, grid, kIcpThreads, 0, L); break;
+    case 2: PEB_LAUNCH(ctx, icp_fitness_kernel<2>, grid, kIcpThreads, 0, L); break;
+    case 4: PEB_LAUNCH(ctx, icp_fitness_kernel<4>, grid, kIcpThreads, 0, L); break;
+    case 8: PEB_LAUNCH(ctx, icp_fitness_kernel<8>, grid, kIcpThreads, 0, L); break;
+    default: PEB_LAUNCH(ctx, icp_fitness_kernel<16>, grid, kIcpThreads, 0, L); break;
+  }
+  return PEB_OK;
+}
+
+int icp_output_device(peb_ctx* ctx, float4* d_out) {
+  const int n = static_cast<int>(ctx->n_src);
+  if (n == 0) return PEB_OK;
+  PEB_LAUNCH(ctx, icp_output_kernel, ceil_div(n, 256), 256, 0, ctx->src.as<float4>(), n, ctx->state.as<IcpState>(),
+             d_out);
+  return PEB_OK;
+}
+
+int nn_search_device(peb_ctx* ctx, const float4* d_q, int nq, int32_t* d_idx, float* d_d2) {
+  if (!ctx->tgt_grid.valid) return fail(ctx, PEB_E_NO_TARGET, "nn_search: no target set");
+  if (nq == 0) return PEB_OK;
+  const GridView& g = ctx->tgt_grid.view;
+  switch (ctx->nn_group) {
+    case 1: PEB_LAUNCH(ctx, nn_search_kernel<1>, ceil_div(nq, 256), 256, 0, g, d_q, nq, d_idx, d_d2); break;
+    case 2: PEB_LAUNCH(ctx, nn_search_kernel<2>, ceil_div(2ll * nq, 256), 256, 0, g, d_q, nq, d_idx, d_d2); break;
+    case 4: PEB_LAUNCH(ctx, nn_search_kernel<4>, ceil_div(4ll * nq, 256), 256, 0, g, d_q, nq, d_idx, d_d2); break;
+    case 8: PEB_LAUNCH(ctx, nn_search_kernel<8>, ceil_div(8ll * nq, 256), 256, 0, g, d_q, nq, d_idx, d_d2); break;
+    default: PEB_LAUNCH(ctx, nn_search_kernel<16>, ceil_div(16ll * nq, 256), 256, 0, g, d_q, nq, d_idx, d_d2); break;
+  }
+  return PEB_OK;
+}
+
+}  // namespace peb

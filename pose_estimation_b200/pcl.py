@@ -1,0 +1,383 @@
+"""Host-side mirror of the PCL 1.10 classes the north-star path substitutes into the reference's
+slots: same method names, defaults and error behaviour as
+
+    pcl::VoxelGrid<PointXYZ>                 down-sample slot  pose_estimation/src/pose_estimation.cpp:261-263
+    pcl::NormalEstimation<PointXYZ, Normal>  normals slot      pose_estimation/src/opencv_surface_match.cpp:57-59
+    pcl::IterativeClosestPoint(+WithNormals) refinement slot   pose_estimation/src/opencv_surface_match.cpp:85-94
+
+Every method is a thin call into libpe_b200.so through its C ABI (include/pe_b200.h); this file
+holds no arithmetic.  Clouds are numpy float32 arrays of shape (N, >=3); rows are the records,
+so (N,3) cv::Mat-style, (N,4) pcl::PointXYZ-style and (N,12) pcl::PointNormal-style all work.
+The C++ facade with the same surface is include/pe_b200/pcl_facade.hpp.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import IcpParams, IcpResult, GridInfo, lib
+
+DBL_MAX = float(np.finfo(np.float64).max)
+
+
+class PebError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{_lib.STATUS_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+def _cloud(a) -> np.ndarray:
+    a = np.asarray(a)
+    if a.dtype != np.float32 or a.ndim != 2 or a.shape[1] < 3 or (a.shape[0] > 1 and a.strides[1] != 4):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] < 3:
+        raise ValueError("point cloud must have shape (N, >=3)")
+    return a
+
+
+def _stride(a: np.ndarray) -> int:
+    return int(a.strides[0]) if a.shape[0] > 1 else max(int(a.strides[0]), 12)
+
+
+def _col_major(T) -> np.ndarray:
+    """4x4 row-indexed numpy matrix -> the 16 floats of Eigen::Matrix4f::data()."""
+    return np.ascontiguousarray(np.asarray(T, dtype=np.float32).reshape(4, 4).T).reshape(16)
+
+
+def result_matrix(r: IcpResult) -> np.ndarray:
+    return np.array(r.T, dtype=np.float32).reshape(4, 4).T.copy()
+
+
+class Context:
+    """peb_ctx: one CUDA device + stream.  Calls on one context must be serialised."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        rc = lib.peb_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise PebError(rc, lib.peb_last_error(None).decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.peb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise PebError(rc, lib.peb_last_error(self._h).decode())
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def stream(self) -> int:
+        return int(lib.peb_ctx_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib.peb_ctx_launch_count(self._h))
+
+    def set_int(self, key: str, value: int):
+        self.check(lib.peb_ctx_set_int(self._h, key.encode(), int(value)))
+
+    def sync(self):
+        self.check(lib.peb_sync(self._h))
+
+    # ---- free functions of the ABI ---------------------------------------------------------
+    def nn_search(self, queries, bruteforce: bool = False):
+        q = _cloud(queries)
+        idx = np.empty(q.shape[0], np.int32)
+        d2 = np.empty(q.shape[0], np.float32)
+        fn = lib.peb_nn_search_bruteforce if bruteforce else lib.peb_nn_search
+        self.check(fn(self._h, q.ctypes.data, q.shape[0], _stride(q), idx.ctypes.data, d2.ctypes.data))
+        return idx, d2
+
+    def target_set(self, pts, normals=None):
+        t = _cloud(pts)
+        self._keep_t = t
+        if normals is not None:
+            nr = _cloud(normals)
+            self.check(lib.peb_target_set(self._h, t.ctypes.data, t.shape[0], _stride(t), nr.ctypes.data, _stride(nr)))
+        else:
+            self.check(lib.peb_target_set(self._h, t.ctypes.data, t.shape[0], _stride(t), None, 0))
+
+    def source_set(self, pts):
+        s = _cloud(pts)
+        self.check(lib.peb_source_set(self._h, s.ctypes.data, s.shape[0], _stride(s)))
+        self._n_src = s.shape[0]
+
+    def grid_info(self) -> GridInfo:
+        gi = GridInfo()
+        self.check(lib.peb_target_grid_info(self._h, C.byref(gi)))
+        return gi
+
+    def fitness_score(self, T, max_range: float = DBL_MAX):
+        t = _col_major(T)
+        f = C.c_double()
+        n = C.c_int32()
+        self.check(lib.peb_fitness_score(self._h, t.ctypes.data, max_range, C.byref(f), C.byref(n)))
+        return f.value, n.value
+
+
+_default_ctx: Context | None = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+class VoxelGrid:
+    """pcl::VoxelGrid<pcl::PointXYZ> ([PCL] filters/include/pcl/filters/voxel_grid.h)."""
+
+    def __init__(self, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self._input = None
+        self._leaf = (0.0, 0.0, 0.0)
+        self._min_pts = 0
+
+    def setInputCloud(self, cloud):
+        self._input = _cloud(cloud)
+
+    def setLeafSize(self, lx: float, ly: float | None = None, lz: float | None = None):
+        self._leaf = (float(lx), float(lx if ly is None else ly), float(lx if lz is None else lz))
+
+    def getLeafSize(self):
+        return self._leaf
+
+    def setMinimumPointsNumberPerVoxel(self, n: int):
+        self._min_pts = int(n)
+
+    def getMinimumPointsNumberPerVoxel(self) -> int:
+        return self._min_pts
+
+    def filter(self) -> np.ndarray:
+        """Returns the (M, 4) down-sampled cloud (x, y, z, 1), ascending voxel index like PCL."""
+        if self._input is None:
+            raise ValueError("VoxelGrid.filter: no input cloud (setInputCloud)")
+        p = self._input
+        out = np.empty((max(p.shape[0], 1), 4), np.float32)
+        m = C.c_size_t(0)
+        self.ctx.check(lib.peb_voxel_grid(self.ctx.handle, p.ctypes.data, p.shape[0], _stride(p), self._leaf[0],
+                                          self._leaf[1], self._leaf[2], self._min_pts, out.ctypes.data, C.byref(m)))
+        return out[: m.value].copy()
+
+
+class NormalEstimation:
+    """pcl::NormalEstimation<pcl::PointXYZ, pcl::Normal> with setKSearch ([PCL] features/normal_3d.h)."""
+
+    def __init__(self, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self._input = None
+        self._k = 0
+        self._vp = np.zeros(3, np.float32)
+
+    def setInputCloud(self, cloud):
+        self._input = _cloud(cloud)
+
+    def setKSearch(self, k: int):
+        self._k = int(k)
+
+    def getKSearch(self) -> int:
+        return self._k
+
+    def setRadiusSearch(self, radius: float):
+        if radius != 0:
+            raise PebError(-6, "NormalEstimation.setRadiusSearch: radius search has no CUDA path (no CPU fallback)")
+
+    def setViewPoint(self, x: float, y: float, z: float):
+        self._vp = np.array([x, y, z], np.float32)
+
+    def getViewPoint(self):
+        return tuple(float(v) for v in self._vp)
+
+    def compute(self, return_neighbours: bool = False):
+        """(N, 8) float32 rows = pcl::Normal (nx ny nz 0 | curvature 0 0 0)."""
+        if self._input is None:
+            raise ValueError("NormalEstimation.compute: no input cloud (setInputCloud)")
+        if self._k <= 0:
+            raise ValueError("NormalEstimation.compute: setKSearch(k) first")
+        p = self._input
+        out = np.empty((p.shape[0], 8), np.float32)
+        nn = np.empty((p.shape[0], self._k), np.int32) if return_neighbours else None
+        self.ctx.check(lib.peb_normals_knn_ex(self.ctx.handle, p.ctypes.data, p.shape[0], _stride(p), self._k,
+                                              self._vp.ctypes.data, out.ctypes.data,
+                                              nn.ctypes.data if nn is not None else None))
+        return (out, nn) if return_neighbours else out
+
+
+class ConvergenceCriteria:
+    """The part of pcl::registration::DefaultConvergenceCriteria<float> reachable through
+    IterativeClosestPoint::getConvergeCriteria()."""
+
+    def __init__(self, params: IcpParams):
+        self._p = params
+        self._state = _lib.CONVERGENCE_CRITERIA_NOT_CONVERGED
+
+    def setAbsoluteMSE(self, v: float):
+        self._p.abs_mse_threshold = float(v)
+
+    def getAbsoluteMSE(self) -> float:
+        return self._p.abs_mse_threshold
+
+    def setMaximumIterationsSimilarTransforms(self, n: int):
+        self._p.max_iterations_similar = int(n)
+
+    def getConvergenceState(self) -> int:
+        return self._state
+
+
+class IterativeClosestPoint:
+    """pcl::IterativeClosestPoint<PointXYZ, PointXYZ> ([PCL] registration/icp.h, registration.h)."""
+
+    _estimator = _lib.ESTIMATOR_SVD
+
+    def __init__(self, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.params = IcpParams()
+        lib.peb_icp_params_default(C.byref(self.params))
+        self.params.estimator = self._estimator
+        self._criteria = ConvergenceCriteria(self.params)
+        self._result: IcpResult | None = None
+        self._have_source = False
+        self._have_target = False
+        self._n_src = 0
+        self.correspondences = None
+
+    # -- pcl::Registration setters ------------------------------------------------------------
+    def setInputSource(self, cloud):
+        self.ctx.source_set(cloud)
+        self._n_src = _cloud(cloud).shape[0]
+        self._have_source = True
+
+    def setInputTarget(self, cloud, normals=None):
+        """normals: (N, >=3) target normals (needed by IterativeClosestPointWithNormals); a
+        pcl::PointNormal-style (N, 12) cloud carries them in columns 4..6."""
+        c = _cloud(cloud)
+        if normals is None and c.shape[1] >= 7 and self._estimator == _lib.ESTIMATOR_POINT_TO_PLANE_LLS:
+            normals = c[:, 4:7]
+        self.ctx.target_set(c, normals)
+        self._have_target = True
+
+    def setMaximumIterations(self, n: int):
+        self.params.max_iterations = int(n)
+
+    def getMaximumIterations(self) -> int:
+        return self.params.max_iterations
+
+    def setMaxCorrespondenceDistance(self, d: float):
+        self.params.max_corr_dist = float(d)
+
+    def getMaxCorrespondenceDistance(self) -> float:
+        return self.params.max_corr_dist
+
+    def setTransformationEpsilon(self, e: float):
+        self.params.transformation_epsilon = float(e)
+
+    def setTransformationRotationEpsilon(self, e: float):
+        self.params.rotation_epsilon = float(e)
+
+    def setEuclideanFitnessEpsilon(self, e: float):
+        self.params.euclidean_fitness_epsilon = float(e)
+
+    def setUseReciprocalCorrespondences(self, on: bool):
+        if on:
+            raise PebError(-6, "reciprocal correspondences have no CUDA path (no CPU fallback)")
+
+    def setRANSACIterations(self, n: int):
+        if n:
+            raise PebError(-6, "the RANSAC rejector has no CUDA path (no CPU fallback)")
+
+    def addCorrespondenceRejectorDistance(self, max_distance: float):
+        """addCorrespondenceRejector(CorrespondenceRejectorDistance with setMaximumDistance(d))."""
+        self.params.rejector_max_dist = float(max_distance)
+
+    def getConvergeCriteria(self) -> ConvergenceCriteria:
+        return self._criteria
+
+    # -- align ------------------------------------------------------------------------------------
+    def align(self, guess=None, want_output: bool = True, want_correspondences: bool = False) -> np.ndarray | None:
+        """align(output, guess): returns the (N, 4) transformed source (or None)."""
+        if not self._have_source or not self._have_target:
+            # let the library produce its own status / message
+            pass
+        g = _col_major(guess) if guess is not None else None
+        res = IcpResult()
+        n = self._n_src
+        out = np.empty((n, 4), np.float32) if (want_output and n) else None
+        idx = np.empty(n, np.int32) if (want_correspondences and n) else None
+        d2 = np.empty(n, np.float32) if (want_correspondences and n) else None
+        self.ctx.check(lib.peb_icp_align(self.ctx.handle, g.ctypes.data if g is not None else None, C.byref(self.params),
+                                         C.byref(res), out.ctypes.data if out is not None else None,
+                                         idx.ctypes.data if idx is not None else None,
+                                         d2.ctypes.data if d2 is not None else None))
+        self._result = res
+        self._criteria._state = res.state
+        self.correspondences = (idx, d2) if want_correspondences else None
+        return out
+
+    def alignBatch(self, guesses) -> list[IcpResult]:
+        """One source, one target, H initial poses: the shape of
+        cv::ppf_match_3d::ICP::registerModelToScene(model, scene, poses)
+        (pose_estimation/src/opencv_surface_match.cpp:94)."""
+        g = np.ascontiguousarray(np.asarray(guesses, np.float32).reshape(-1, 4, 4).transpose(0, 2, 1)).reshape(-1, 16)
+        H = g.shape[0]
+        res = (IcpResult * max(H, 1))()
+        self.ctx.check(lib.peb_icp_align_batch(self.ctx.handle, g.ctypes.data, H, C.byref(self.params), res))
+        return list(res)[:H]
+
+    def hasConverged(self) -> bool:
+        return bool(self._result and self._result.converged)
+
+    def getFinalTransformation(self) -> np.ndarray:
+        if self._result is None:
+            return np.eye(4, dtype=np.float32)
+        return result_matrix(self._result)
+
+    def getFitnessScore(self, max_range: float = DBL_MAX) -> float:
+        if self._result is None:
+            raise ValueError("getFitnessScore before align")
+        if max_range == self.params.fitness_max_range:
+            return self._result.fitness
+        return self.ctx.fitness_score(self.getFinalTransformation(), max_range)[0]
+
+    @property
+    def nr_iterations_(self) -> int:
+        return self._result.iterations if self._result else 0
+
+    @property
+    def result(self) -> IcpResult | None:
+        return self._result
+
+    def trace(self) -> np.ndarray:
+        """Per-iteration increments of the last align, (iterations, 4, 4)."""
+        cap = max(self.nr_iterations_, 1)
+        buf = np.zeros((cap, 16), np.float32)
+        n = C.c_size_t(0)
+        self.ctx.check(lib.peb_icp_trace(self.ctx.handle, buf.ctypes.data, cap, C.byref(n)))
+        return buf[: n.value].reshape(-1, 4, 4).transpose(0, 2, 1).copy()
+
+
+class IterativeClosestPointWithNormals(IterativeClosestPoint):
+    """pcl::IterativeClosestPointWithNormals<PointNormal, PointNormal>: the estimator is
+    TransformationEstimationPointToPlaneLLS ([PCL] registration/icp.h)."""
+
+    _estimator = _lib.ESTIMATOR_POINT_TO_PLANE_LLS

@@ -1,0 +1,98 @@
+"""Development probe (not part of the product or the bench contract): times the single align and
+a small batch at full C2 size for every nn_group width and a few grid occupancies, with the
+library's own per-launch CUDA-event profile."""
+import ctypes as C
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+from pose_estimation_b200 import pcl  # noqa: E402
+from pose_estimation_b200.pcl import lib  # noqa: E402
+from pose_estimation_b200.testing import synth  # noqa: E402
+
+
+def profile(ctx):
+    buf = np.zeros(256, np.float32)
+    n = C.c_size_t(0)
+    ctx.check(lib.peb_profile_read(ctx.handle, buf.ctypes.data, 256, C.byref(n)))
+    return buf[: n.value]
+
+
+def main():
+    scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+    ctx = pcl.Context(0)
+
+    def ds(points, leaf):
+        vg = pcl.VoxelGrid(ctx)
+        vg.setInputCloud(points)
+        vg.setLeafSize(leaf)
+        return vg.filter()
+
+    t0 = time.perf_counter()
+    prob = synth.make_c2(scale=scale, downsample=ds)
+    print(f"C2 scale {scale}: scene {prob.organized.shape[0]} px -> target {len(prob.target)} pts (leaf {prob.leaf:.5f}), "
+          f"model {len(prob.source)} pts, generated in {time.perf_counter() - t0:.1f} s", flush=True)
+    for _ in range(3):
+        t0 = time.perf_counter()
+        ds(prob.organized, prob.leaf)
+        print(f"  voxel grid (host buffers, e2e): {1e3 * (time.perf_counter() - t0):.2f} ms")
+
+    icp = pcl.IterativeClosestPoint(ctx)
+    icp.setInputSource(prob.source)
+    icp.setMaximumIterations(30)
+    icp.getConvergeCriteria().setAbsoluteMSE(-1.0)
+    ctx.set_int("profile", 1)
+    for occ in (100, 200, 400, 800):
+        ctx.set_int("grid_occupancy_x100", occ)
+        t0 = time.perf_counter()
+        icp.setInputTarget(prob.target)
+        t_set = time.perf_counter() - t0
+        gi = ctx.grid_info()
+        print(f"occupancy {occ / 100}: cell {gi.cell * 1e3:.3f} mm dims {list(gi.dims)} cells {gi.n_cells} "
+              f"target_set {1e3 * t_set:.2f} ms", flush=True)
+        for g in (1, 2, 4, 8, 16):
+            ctx.set_int("nn_group", g)
+            best = 1e9
+            for rep in range(5):
+                t0 = time.perf_counter()
+                icp.align(prob.guess, want_output=False)
+                best = min(best, time.perf_counter() - t0)
+            pr = profile(ctx)
+            print(f"   G={g:2d}: align wall {1e3 * best:.3f} ms | kernels sum {pr.sum():.3f} ms, iter first {pr[0] * 1e3:.1f} us "
+                  f"median {np.median(pr[:-1]) * 1e3:.1f} us, fitness {pr[-1] * 1e3:.1f} us | it {icp.nr_iterations_} "
+                  f"fitness {icp.getFitnessScore():.4e}", flush=True)
+    # small batch
+    ctx.set_int("grid_occupancy_x100", 200)
+    icp.setInputTarget(prob.target)
+    rng = np.random.default_rng(0)
+    guesses = np.stack([synth.perturb_pose(prob.gt_pose, rng, 6.0, 0.008) for _ in range(128)])
+    icp.setMaxCorrespondenceDistance(0.02)
+    for g in (1, 2, 4, 8):
+        ctx.set_int("nn_group", g)
+        best = 1e9
+        for rep in range(3):
+            t0 = time.perf_counter()
+            res = icp.alignBatch(guesses)
+            best = min(best, time.perf_counter() - t0)
+        pr = profile(ctx)
+        fit = np.array([r.fitness for r in res])
+        print(f"batch H=128 G={g}: wall {1e3 * best:.2f} ms = {128 / best:.0f} hyp/s | kernels {pr.sum():.2f} ms, "
+              f"iter0 {pr[0]:.3f} ms, median {np.median(pr[:-1]):.3f} ms | fitness median {np.median(fit):.3e}", flush=True)
+    # normals
+    ne = pcl.NormalEstimation(ctx)
+    ne.setInputCloud(prob.target)
+    ne.setKSearch(30)
+    for _ in range(3):
+        t0 = time.perf_counter()
+        ne.compute()
+        print(f"normals k=30 on {len(prob.target)} pts (host buffers, e2e): {1e3 * (time.perf_counter() - t0):.2f} ms")
+    print("launches:", ctx.launch_count)
+
+
+if __name__ == "__main__":
+    main()
