@@ -51,14 +51,14 @@ __global__ void __launch_bounds__(256) run_head_kernel(const uint32_t* __restric
   flags[j] = (j == 0 || sorted_keys[j] != sorted_keys[j - 1]) ? 1u : 0u;
 }
 
-// starts[ordinal] = j for every run head; starts[n_runs] is written by the host-side memset/copy
+// starts[ordinal] = j for every run head; the last element also writes the end sentinel starts[n_runs]
 __global__ void __launch_bounds__(256) run_start_kernel(const uint32_t* __restrict__ flags,
                                                         const uint32_t* __restrict__ ordinal, int n_finite,
                                                         uint32_t* __restrict__ starts) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_finite) return;
   if (flags[j]) starts[ordinal[j]] = static_cast<uint32_t>(j);
-  if (j == n_finite - 1) starts[ordinal[j] + 1] = static_cast<uint32_t>(n_finite);
+  if (j == n_finite - 1) starts[ordinal[j] + flags[j]] = static_cast<uint32_t>(n_finite);  // = starts[n_runs]
 }
 
 __global__ void __launch_bounds__(256) run_keep_kernel(const uint32_t* __restrict__ starts, int n_runs, unsigned min_pts,
