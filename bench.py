@@ -331,6 +331,8 @@ def run_ours(args):
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_kernel_ms, "launches_timed": len(kernel_ms),
                 "peak_source": peak_src,
+                "launch_ms_by_iteration": [round(float(np.mean(kernel_ms[i::ITERATIONS])), 3) for i in range(ITERATIONS)]
+                if len(kernel_ms) == ITERATIONS * args.steps else None,
                 "share_of_step": (sum(kernel_ms) / args.steps) / (total_ms / args.steps) if total_ms > 0 else None}
 
     line = {

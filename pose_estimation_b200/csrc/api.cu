@@ -188,6 +188,10 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
     ctx->grid_occupancy = value / 100.0f;
     return PEB_OK;
   }
+  if (!strcmp(key, "warm_start")) {
+    ctx->warm_start = value != 0;
+    return PEB_OK;
+  }
   if (!strcmp(key, "profile")) {
     ctx->profile = value != 0;
     ctx->prof_launches = 0;

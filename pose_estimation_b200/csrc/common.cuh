@@ -99,6 +99,7 @@ struct peb_ctx {
   uint64_t launches = 0;
   int nn_group = 8;             // lanes that share one nearest-neighbour query (1, 2, 4, 8, 16)
   float grid_occupancy = 2.0f;  // wanted mean points per occupied cell of the target grid
+  bool warm_start = true;       // iterations >= 1 seed the search with the previous match
 
   peb::PinnedBuf h_stage;    // host repack / readback staging
   peb::PinnedBuf h_small;    // small results (bbox, counters, peb_icp_result)

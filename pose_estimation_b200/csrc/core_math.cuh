@@ -170,6 +170,54 @@ PEB_HD float grid_ring_bound2(const GridView& g, float qx, float qy, float qz, i
   return best;
 }
 
+// Distance (>= 0) from coordinate q to the slab of cell index c along one axis, shrunk by the
+// same 1 % safety margin as grid_ring_bound2 (cell membership is decided in float arithmetic).
+PEB_HD float grid_slab_dist(float q, float origin, float h, int c) {
+  const float lo = origin + static_cast<float>(c) * h;
+  const float hi = origin + static_cast<float>(c + 1) * h;
+  return fmaxf(fmaxf(lo - q, q - hi) - 0.01f * h, 0.0f);
+}
+
+// Exact 1-NN given one candidate (sorted position j_prev, e.g. last iteration's match): its
+// distance bounds the answer, so only the cells that intersect the ball of that radius around q
+// can hold something closer — usually 1 to 8 cells instead of a 3x3x3 block plus the ring that
+// proves termination.  limit_d2: matches farther than this are rejected by the caller anyway, so
+// the ball never needs to be larger (pass +inf for plain nearest-neighbour semantics).
+// Rows (fixed y, z) whose slab is already farther than the current best are skipped, and the x
+// extent of every row is cut to the part of the ball it can still intersect.
+PEB_HD NnBest grid_nn_warm(const GridView& g, float qx, float qy, float qz, int j_prev, float limit_d2) {
+  NnBest best;
+  {
+    const float4 p = g.pts[j_prev];
+    best.d2 = l2_simple(qx, qy, qz, p.x, p.y, p.z);
+#ifdef __CUDA_ARCH__
+    best.idx = __float_as_int(p.w);
+#else
+    memcpy(&best.idx, &p.w, 4);
+#endif
+    best.j = j_prev;
+  }
+  const float lim = fminf(best.d2, limit_d2);
+  const float pad = 0.001f * g.h;  // >> one ulp of any coordinate (h >= 1e-4 * max |coordinate|)
+  const float R = sqrtf(lim) * 1.0001f + pad;
+  const int y0 = grid_coord(qy - R, g.oy, g.inv_h, g.dy), y1 = grid_coord(qy + R, g.oy, g.inv_h, g.dy);
+  const int z0 = grid_coord(qz - R, g.oz, g.inv_h, g.dz), z1 = grid_coord(qz + R, g.oz, g.inv_h, g.dz);
+  for (int z = z0; z <= z1; ++z) {
+    const float dz = grid_slab_dist(qz, g.oz, g.h, z);
+    for (int y = y0; y <= y1; ++y) {
+      const float dy = grid_slab_dist(qy, g.oy, g.h, y);
+      const float dyz2 = dy * dy + dz * dz;
+      const float cur = fminf(best.d2, limit_d2);
+      if (dyz2 > cur) continue;
+      const float rx = sqrtf(cur - dyz2) * 1.0001f + pad;
+      const int x0 = grid_coord(qx - rx, g.ox, g.inv_h, g.dx), x1 = grid_coord(qx + rx, g.ox, g.inv_h, g.dx);
+      const int base = (z * g.dy + y) * g.dx;
+      grid_scan_range(g, g.cell_start[base + x0], g.cell_start[base + x1 + 1], qx, qy, qz, best);
+    }
+  }
+  return best;
+}
+
 // After this many rings the search gives up on the grid and scans every point (still exact):
 // a query that far from all target points costs O(r^3) row visits on the grid, which beats a
 // full scan only while r stays small.  Rings 1..16 visit ~6 k rows.

@@ -16,6 +16,10 @@
 //   icp_fitness_kernel     [PCL] registration/impl/registration.hpp : getFitnessScore, then packs
 //                   the peb_icp_result record.
 //
+// Launch 0 of an align searches cold: ring search, G lanes per query (far queries touch hundreds
+// of grid rows, the lanes of a group split them).  Every later launch is warm: one thread per
+// query, seeded with the previous iteration's match, which travels in the .w slot of the working
+// point (nn grid_nn_warm: only the cells inside the ball of that candidate's distance).
 // Later launches of an align that has already converged return at once (state.active == 0).
 // The batched mode is the same code with H > 1: one working cloud per hypothesis so that PCL's
 // incremental float update is reproduced exactly for every hypothesis.
@@ -25,7 +29,10 @@ namespace peb {
 
 namespace {
 
-constexpr int kIcpThreads = 256;
+constexpr int kIcpThreads = 128;
+#ifndef PEB_ICP_MIN_BLOCKS
+#define PEB_ICP_MIN_BLOCKS 5  // 96 registers: no spills in the per-query loop, 20 warps per SM
+#endif
 
 struct IcpLaunch {
   GridView grid;
@@ -48,6 +55,7 @@ struct IcpLaunch {
   int blocks_per_hyp;
   int trace_cap;
   int fitness_only;      // peb_fitness_score: the record's n_correspondences carries the inlier count
+  int warm;              // seed every search with the match stored in the working point's .w
 };
 
 __global__ void icp_init_kernel(IcpState* __restrict__ states, const float* __restrict__ guesses, int H) {
@@ -107,9 +115,20 @@ __device__ __forceinline__ void reduce_partials(const double* __restrict__ part,
   constexpr int kW = kIcpThreads / 32;
   double v = 0.0;
   if (lane < NACC) {
+    // warp w owns the contiguous block range [b0, b1); eight independent loads in flight per lane
+    // (the L2 round trip, not the adds, is what this loop waits for); the order of the adds is fixed
     const int per = (n_blocks + kW - 1) / kW;
     const int b0 = warp * per, b1 = min(b0 + per, n_blocks);
-    for (int b = b0; b < b1; ++b) v += __ldcg(part + static_cast<size_t>(b) * kAccMax + lane);
+    const double* p = part + lane;
+    int b = b0;
+    for (; b + 8 <= b1; b += 8) {
+      double t[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t[k] = __ldcg(p + static_cast<size_t>(b + k) * kAccMax);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v += t[k];
+    }
+    for (; b < b1; ++b) v += __ldcg(p + static_cast<size_t>(b) * kAccMax);
     sm[warp][lane] = v;
   }
   __syncthreads();
@@ -122,8 +141,20 @@ __device__ __forceinline__ void reduce_partials(const double* __restrict__ part,
   __syncthreads();
 }
 
+// The solve runs once per launch in one thread; keeping it out of line keeps its registers and
+// local arrays out of the per-query loop's allocation.
+__device__ __noinline__ void finish_iteration(IcpState* st, const IcpCriteria* cr, const double* acc, Mat4* trace,
+                                              int trace_cap) {
+  IcpState s = *st;
+  icp_finish_iteration(s, *cr, acc);
+  s.ticket = 0;
+  if (trace && s.state != PEB_NO_CORRESPONDENCES && s.iterations >= 1 && s.iterations <= trace_cap)
+    trace[s.iterations - 1] = s.inc;
+  *st = s;
+}
+
 template <int G, int EST>
-__global__ void __launch_bounds__(kIcpThreads) icp_iteration_kernel(const IcpLaunch L) {
+__global__ void __launch_bounds__(kIcpThreads, PEB_ICP_MIN_BLOCKS) icp_iteration_kernel(const IcpLaunch L) {
   constexpr int NACC = (EST == PEB_ESTIMATOR_SVD) ? kAccSvd : kAccLls;
   __shared__ double sm[kIcpThreads / 32][kAccMax];
   __shared__ double sm_tot[kAccMax];
@@ -169,6 +200,7 @@ __global__ void __launch_bounds__(kIcpThreads) icp_iteration_kernel(const IcpLau
     const bool in = i < L.n_src;
     float4 p = make_float4(0.f, 0.f, 0.f, 1.f);
     if (in) p = first ? L.src[i] : work[i];
+    const int j_prev = first ? -1 : __float_as_int(p.w);  // last iteration's match (sorted position)
     const bool valid = in && finite3(p.x, p.y, p.z);
     if (valid && apply) {
       float ox, oy, oz;
@@ -177,14 +209,21 @@ __global__ void __launch_bounds__(kIcpThreads) icp_iteration_kernel(const IcpLau
       p.y = oy;
       p.z = oz;
     }
-    p.w = 1.0f;
-    if (in && lane_in_group == 0 && (first || (valid && apply))) work[i] = p;
     // queries of a group run the search together; invalid ones idle through it
     NnBest best;
     best.d2 = pos_inf();
     best.idx = -1;
     best.j = -1;
-    if (valid) best = grid_nn<G>(L.grid, p.x, p.y, p.z, L.stop_d2);
+    if (valid) {
+      if (G == 1 && L.warm && j_prev >= 0 && j_prev < L.grid.n)
+        best = grid_nn_warm(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2);
+      else
+        best = grid_nn<G>(L.grid, p.x, p.y, p.z, L.stop_d2);
+    }
+    if (in && lane_in_group == 0 && (first || valid)) {
+      p.w = __int_as_float(best.j);
+      work[i] = p;
+    }
     bool keep = valid && best.idx >= 0;
     if (keep && static_cast<double>(best.d2) > L.max_dist_sqr) keep = false;
     if (keep && L.use_rejector && !(best.d2 < L.rej_max2)) keep = false;
@@ -272,14 +311,7 @@ __global__ void __launch_bounds__(kIcpThreads) icp_iteration_kernel(const IcpLau
   if (!s_last) return;
   __threadfence();
   reduce_partials<NACC>(part, L.blocks_per_hyp, sm, sm_tot);
-  if (threadIdx.x == 0) {
-    IcpState s = *st;
-    icp_finish_iteration(s, L.crit, sm_tot);
-    s.ticket = 0;
-    if (L.trace && s.state != PEB_NO_CORRESPONDENCES && s.iterations >= 1 && s.iterations <= L.trace_cap)
-      L.trace[s.iterations - 1] = s.inc;
-    *st = s;
-  }
+  if (threadIdx.x == 0) finish_iteration(st, &L.crit, sm_tot, L.trace, L.trace_cap);
 }
 
 // [PCL] registration/impl/registration.hpp : getFitnessScore(max_range) with the final transform
@@ -309,7 +341,12 @@ __global__ void __launch_bounds__(kIcpThreads) icp_fitness_kernel(const IcpLaunc
     if (valid) {
       float qx, qy, qz;
       transform_tpc(T, p.x, p.y, p.z, qx, qy, qz);
-      best = grid_nn<G>(L.grid, qx, qy, qz, L.fitness_stop_d2);
+      int j_prev = -1;
+      if (G == 1 && L.warm) j_prev = __float_as_int(L.work[static_cast<size_t>(h) * L.n_src + i].w);
+      if (G == 1 && j_prev >= 0 && j_prev < L.grid.n)
+        best = grid_nn_warm(L.grid, qx, qy, qz, j_prev, L.fitness_stop_d2);
+      else
+        best = grid_nn<G>(L.grid, qx, qy, qz, L.fitness_stop_d2);
     }
     if (valid && best.idx >= 0 && lane_in_group == 0 && static_cast<double>(best.d2) <= L.fitness_max_range) {
       acc[0] += static_cast<double>(best.d2);
@@ -409,22 +446,49 @@ int prof_mark(peb_ctx* ctx, int slot) {
 }
 
 template <int G>
-int launch_iterations(peb_ctx* ctx, const IcpLaunch& L, size_t H, int max_iterations, int estimator) {
+int launch_one_iteration(peb_ctx* ctx, const IcpLaunch& L, size_t H, int estimator) {
   dim3 grid(L.blocks_per_hyp, static_cast<unsigned>(H));
-  ctx->prof_launches = 0;
-  for (int it = 0; it < max_iterations; ++it) {
-    PEB_TRY(prof_mark(ctx, 2 * it));
-    if (estimator == PEB_ESTIMATOR_SVD)
-      PEB_LAUNCH(ctx, (icp_iteration_kernel<G, PEB_ESTIMATOR_SVD>), grid, kIcpThreads, 0, L);
-    else
-      PEB_LAUNCH(ctx, (icp_iteration_kernel<G, PEB_ESTIMATOR_POINT_TO_PLANE_LLS>), grid, kIcpThreads, 0, L);
-    PEB_TRY(prof_mark(ctx, 2 * it + 1));
-  }
-  PEB_TRY(prof_mark(ctx, 2 * max_iterations));
-  PEB_LAUNCH(ctx, icp_fitness_kernel<G>, grid, kIcpThreads, 0, L);
-  PEB_TRY(prof_mark(ctx, 2 * max_iterations + 1));
-  if (ctx->profile) ctx->prof_launches = max_iterations + 1;
+  if (estimator == PEB_ESTIMATOR_SVD)
+    PEB_LAUNCH(ctx, (icp_iteration_kernel<G, PEB_ESTIMATOR_SVD>), grid, kIcpThreads, 0, L);
+  else
+    PEB_LAUNCH(ctx, (icp_iteration_kernel<G, PEB_ESTIMATOR_POINT_TO_PLANE_LLS>), grid, kIcpThreads, 0, L);
   return PEB_OK;
+}
+
+int launch_one_iteration_g(peb_ctx* ctx, int G, const IcpLaunch& L, size_t H, int estimator) {
+  switch (G) {
+    case 1: return launch_one_iteration<1>(ctx, L, H, estimator);
+    case 2: return launch_one_iteration<2>(ctx, L, H, estimator);
+    case 4: return launch_one_iteration<4>(ctx, L, H, estimator);
+    case 8: return launch_one_iteration<8>(ctx, L, H, estimator);
+    case 16: return launch_one_iteration<16>(ctx, L, H, estimator);
+    default: return fail(ctx, PEB_E_INVALID_ARG, "nn group width %d is not one of 1,2,4,8,16", G);
+  }
+}
+
+int launch_fitness_g(peb_ctx* ctx, int G, const IcpLaunch& L, size_t H) {
+  dim3 grid(L.blocks_per_hyp, static_cast<unsigned>(H));
+  switch (G) {
+    case 1: PEB_LAUNCH(ctx, icp_fitness_kernel<1>, grid, kIcpThreads, 0, L); break;
+    case 2: PEB_LAUNCH(ctx, icp_fitness_kernel<2>, grid, kIcpThreads, 0, L); break;
+    case 4: PEB_LAUNCH(ctx, icp_fitness_kernel<4>, grid, kIcpThreads, 0, L); break;
+    case 8: PEB_LAUNCH(ctx, icp_fitness_kernel<8>, grid, kIcpThreads, 0, L); break;
+    default: PEB_LAUNCH(ctx, icp_fitness_kernel<16>, grid, kIcpThreads, 0, L); break;
+  }
+  return PEB_OK;
+}
+
+// blocks per hypothesis for a group width: one block handles kIcpThreads / G queries per pass;
+// a single align spreads over the whole chip, batched aligns give every hypothesis a few blocks
+// and let grid.y fill the machine
+int blocks_for(int n, size_t H, int G) {
+  const int want = ceil_div(std::max(n, 1), kIcpThreads / G);
+  int bph;
+  if (H == 1)
+    bph = std::min(want, kSmCount * 8);
+  else
+    bph = std::min(want, std::max(1, static_cast<int>((kSmCount * 32 + H - 1) / H)));
+  return std::max(bph, 1);
 }
 
 }  // namespace
@@ -434,22 +498,13 @@ namespace {
 // fills everything of the launch record that does not depend on the mode
 int prepare_launch(peb_ctx* ctx, size_t H, const peb_icp_params* prm, IcpLaunch& L) {
   const int n = static_cast<int>(ctx->n_src);
-  const int G = ctx->nn_group;
   L.grid = ctx->tgt_grid.view;
   L.src = ctx->src.as<float4>();
   L.n_src = n;
-  // one block handles 256/G queries per pass; single aligns spread over the whole chip, batched
-  // aligns give every hypothesis a few blocks and let grid.y fill the machine
-  const int want = ceil_div(std::max(n, 1), kIcpThreads / G);
-  int bph;
-  if (H == 1)
-    bph = std::min(want, kSmCount * 8);
-  else
-    bph = std::min(want, std::max(1, static_cast<int>((kSmCount * 16 + H - 1) / H)));
-  L.blocks_per_hyp = std::max(bph, 1);
+  const int max_bph = std::max(blocks_for(n, H, ctx->nn_group), blocks_for(n, H, 1));
   PEB_CUDA(ctx, ctx->work.ensure(std::max<size_t>(H * static_cast<size_t>(n), 1) * sizeof(float4)));
   PEB_CUDA(ctx, ctx->state.ensure(H * sizeof(IcpState)));
-  PEB_CUDA(ctx, ctx->partials.ensure(H * static_cast<size_t>(L.blocks_per_hyp) * kAccMax * sizeof(double)));
+  PEB_CUDA(ctx, ctx->partials.ensure(H * static_cast<size_t>(max_bph) * kAccMax * sizeof(double)));
   L.work = ctx->work.as<float4>();
   L.states = ctx->state.as<IcpState>();
   L.partials = ctx->partials.as<double>();
@@ -503,14 +558,27 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
              static_cast<int>(H));
   // PCL runs the loop body at least once (do ... while), also for max_iterations <= 1
   const int launches = std::max(prm->max_iterations, 1);
-  switch (ctx->nn_group) {
-    case 1: return launch_iterations<1>(ctx, L, H, launches, prm->estimator);
-    case 2: return launch_iterations<2>(ctx, L, H, launches, prm->estimator);
-    case 4: return launch_iterations<4>(ctx, L, H, launches, prm->estimator);
-    case 8: return launch_iterations<8>(ctx, L, H, launches, prm->estimator);
-    case 16: return launch_iterations<16>(ctx, L, H, launches, prm->estimator);
-    default: return fail(ctx, PEB_E_INVALID_ARG, "nn group width %d is not one of 1,2,4,8,16", ctx->nn_group);
+  const int g_cold = ctx->nn_group;
+  const int g_warm = ctx->warm_start ? 1 : g_cold;
+  IcpLaunch Lc = L, Lw = L;
+  Lc.blocks_per_hyp = blocks_for(n, H, g_cold);
+  Lc.warm = 0;
+  Lw.blocks_per_hyp = blocks_for(n, H, g_warm);
+  Lw.warm = ctx->warm_start ? 1 : 0;
+  ctx->prof_launches = 0;
+  for (int it = 0; it < launches; ++it) {
+    PEB_TRY(prof_mark(ctx, 2 * it));
+    if (it == 0)
+      PEB_TRY(launch_one_iteration_g(ctx, g_cold, Lc, H, prm->estimator));
+    else
+      PEB_TRY(launch_one_iteration_g(ctx, g_warm, Lw, H, prm->estimator));
+    PEB_TRY(prof_mark(ctx, 2 * it + 1));
   }
+  PEB_TRY(prof_mark(ctx, 2 * launches));
+  PEB_TRY(launch_fitness_g(ctx, g_warm, Lw, H));
+  PEB_TRY(prof_mark(ctx, 2 * launches + 1));
+  if (ctx->profile) ctx->prof_launches = launches + 1;
+  return PEB_OK;
 }
 
 int fitness_device(peb_ctx* ctx, const float* d_T, double max_range, peb_icp_result* d_result) {
@@ -523,16 +591,10 @@ int fitness_device(peb_ctx* ctx, const float* d_T, double max_range, peb_icp_res
   PEB_TRY(prepare_launch(ctx, 1, &prm, L));
   L.results = d_result;
   L.fitness_only = 1;
+  L.warm = 0;  // an arbitrary transform: nothing to seed the search with
+  L.blocks_per_hyp = blocks_for(static_cast<int>(ctx->n_src), 1, ctx->nn_group);
   PEB_LAUNCH(ctx, icp_init_kernel, 1, 128, 0, L.states, d_T, 1);
-  dim3 grid(L.blocks_per_hyp, 1);
-  switch (ctx->nn_group) {
-    case 1: PEB_LAUNCH(ctx, icp_fitness_kernel<1>, grid, kIcpThreads, 0, L); break;
-    case 2: PEB_LAUNCH(ctx, icp_fitness_kernel<2>, grid, kIcpThreads, 0, L); break;
-    case 4: PEB_LAUNCH(ctx, icp_fitness_kernel<4>, grid, kIcpThreads, 0, L); break;
-    case 8: PEB_LAUNCH(ctx, icp_fitness_kernel<8>, grid, kIcpThreads, 0, L); break;
-    default: PEB_LAUNCH(ctx, icp_fitness_kernel<16>, grid, kIcpThreads, 0, L); break;
-  }
-  return PEB_OK;
+  return launch_fitness_g(ctx, ctx->nn_group, L, 1);
 }
 
 int icp_output_device(peb_ctx* ctx, float4* d_out) {

@@ -132,6 +132,25 @@ HC_API void hc_grid_nn(const float* tgt, size_t n, size_t tstride, const float* 
   }
 }
 
+// warm-started search: prev[i] = ORIGINAL index of the candidate handed to query i
+HC_API void hc_grid_nn_warm(const float* tgt, size_t n, size_t tstride, const float* q, size_t nq, size_t qstride,
+                            float occupancy, const int32_t* prev, float limit_d2, int32_t* out_idx, float* out_d2) {
+  HostGrid g;
+  build_grid(tgt, n, tstride / 4, occupancy, 0.0f, g);
+  std::vector<int> pos(n, -1);  // original index -> sorted position
+  for (int j = 0; j < g.v.n; ++j) {
+    int id;
+    memcpy(&id, &g.pts[j].w, 4);
+    pos[id] = j;
+  }
+  for (size_t i = 0; i < nq; ++i) {
+    const float* p = q + i * (qstride / 4);
+    NnBest b = grid_nn_warm(g.v, p[0], p[1], p[2], pos[prev[i]], limit_d2);
+    out_idx[i] = b.idx;
+    out_d2[i] = b.d2;
+  }
+}
+
 // one ICP iteration's solve from explicit pairs, through the same moment sums the kernel builds
 HC_API void hc_umeyama_pairs(const float* s3, const float* t3, size_t n, float* out_T) {
   double acc[kAccMax] = {0};

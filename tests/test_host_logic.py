@@ -21,6 +21,7 @@ def hc():
     L = C.CDLL(str(HOST / "libpe_hostcheck.so"))
     vp, sz = C.c_void_p, C.c_size_t
     L.hc_grid_nn.argtypes = [vp, sz, sz, vp, sz, sz, C.c_float, C.c_float, C.c_float, vp, vp, vp]
+    L.hc_grid_nn_warm.argtypes = [vp, sz, sz, vp, sz, sz, C.c_float, vp, C.c_float, vp, vp]
     L.hc_umeyama_pairs.argtypes = [vp, vp, sz, vp]
     L.hc_lls_pairs.argtypes = [vp, vp, vp, sz, vp]
     L.hc_criteria_script.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]
@@ -96,6 +97,46 @@ def test_grid_search_stop_distance_only_cuts_rejected_matches(hc, oracle):
     assert acc.any() and (~acc).any()
     assert np.array_equal(gd[acc], bd[acc]) and tie_ok(prob.target, src[acc], gi[acc], bi[acc])
     assert (gd[~acc] > stop).all()  # whatever it returns there is rejected by the caller anyway
+
+
+def grid_nn_warm(hc, tgt, q, prev, occupancy=2.0, limit=np.inf):
+    tgt = np.ascontiguousarray(tgt, np.float32)
+    q = np.ascontiguousarray(q, np.float32)
+    prev = np.ascontiguousarray(prev, np.int32)
+    idx = np.empty(len(q), np.int32)
+    d2 = np.empty(len(q), np.float32)
+    hc.hc_grid_nn_warm(tgt.ctypes.data, len(tgt), tgt.strides[0], q.ctypes.data, len(q), q.strides[0], occupancy,
+                       prev.ctypes.data, limit, idx.ctypes.data, d2.ctypes.data)
+    return idx, d2
+
+
+@pytest.mark.parametrize("occupancy", [0.5, 2.0, 8.0])
+def test_warm_started_search_is_exact_for_any_candidate(hc, oracle, occupancy):
+    """The ball search must return the exact nearest neighbour whatever candidate it is seeded
+    with: the true answer, a near miss, or an arbitrary far point."""
+    rng = np.random.default_rng(15)
+    prob = synth.make_c1(4000, seed=16)
+    tgt = prob.target.copy()
+    tgt[100:110] = tgt[100]  # exact duplicates: lowest index must win
+    q = np.concatenate([prob.source[:, :3], tgt[100:101, :3], tgt[:200, :3] + np.float32(3e-4),
+                        rng.uniform(-0.2, 0.2, (200, 3)).astype(np.float32) + tgt[:200, :3]])
+    bi, bd = oracle.nn_bruteforce(tgt, q)
+    seeds = {
+        "true": bi,
+        "near": np.clip(bi + rng.integers(-3, 4, len(bi)), 0, len(tgt) - 1),
+        "random": rng.integers(0, len(tgt), len(bi)),
+    }
+    for name, prev in seeds.items():
+        gi, gd = grid_nn_warm(hc, tgt, q, prev, occupancy)
+        assert np.array_equal(gd, bd), name
+        assert np.array_equal(gi, bi), name
+    # with a rejection limit: everything the caller would accept is still exact
+    lim = np.float32(1e-6)
+    gi, gd = grid_nn_warm(hc, tgt, q, seeds["random"], occupancy, float(lim))
+    acc = bd <= lim
+    assert acc.any() and (~acc).any()
+    assert np.array_equal(gd[acc], bd[acc]) and np.array_equal(gi[acc], bi[acc])
+    assert (gd[~acc] > lim).all()
 
 
 def test_umeyama_from_sums_matches_oracle(hc, oracle):

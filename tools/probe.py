@@ -47,7 +47,10 @@ def main():
     icp.setMaximumIterations(30)
     icp.getConvergeCriteria().setAbsoluteMSE(-1.0)
     ctx.set_int("profile", 1)
-    for occ in (100, 200, 400, 800):
+    for warm in (0, 1):
+      ctx.set_int("warm_start", warm)
+      print("warm_start", warm)
+      for occ in (200, 400):
         ctx.set_int("grid_occupancy_x100", occ)
         t0 = time.perf_counter()
         icp.setInputTarget(prob.target)
@@ -55,7 +58,7 @@ def main():
         gi = ctx.grid_info()
         print(f"occupancy {occ / 100}: cell {gi.cell * 1e3:.3f} mm dims {list(gi.dims)} cells {gi.n_cells} "
               f"target_set {1e3 * t_set:.2f} ms", flush=True)
-        for g in (1, 2, 4, 8, 16):
+        for g in (1, 4, 8, 16):
             ctx.set_int("nn_group", g)
             best = 1e9
             for rep in range(5):
@@ -72,8 +75,9 @@ def main():
     rng = np.random.default_rng(0)
     guesses = np.stack([synth.perturb_pose(prob.gt_pose, rng, 6.0, 0.008) for _ in range(128)])
     icp.setMaxCorrespondenceDistance(0.02)
-    for g in (1, 2, 4, 8):
+    for g, warm in ((1, 0), (8, 0), (1, 1), (8, 1), (16, 1)):
         ctx.set_int("nn_group", g)
+        ctx.set_int("warm_start", warm)
         best = 1e9
         for rep in range(3):
             t0 = time.perf_counter()
@@ -81,7 +85,7 @@ def main():
             best = min(best, time.perf_counter() - t0)
         pr = profile(ctx)
         fit = np.array([r.fitness for r in res])
-        print(f"batch H=128 G={g}: wall {1e3 * best:.2f} ms = {128 / best:.0f} hyp/s | kernels {pr.sum():.2f} ms, "
+        print(f"batch H=128 G={g} warm={warm} iters(ms) {np.round(pr[:8], 2).tolist()}: wall {1e3 * best:.2f} ms = {128 / best:.0f} hyp/s | kernels {pr.sum():.2f} ms, "
               f"iter0 {pr[0]:.3f} ms, median {np.median(pr[:-1]):.3f} ms | fitness median {np.median(fit):.3e}", flush=True)
     # normals
     ne = pcl.NormalEstimation(ctx)
