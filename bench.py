@@ -203,9 +203,11 @@ def run_ours(args):
         return vg.filter()
 
     c4, c2 = make_workloads(downsample, world == 1 and not args.no_single, args.hyp, args.scale)
+    from pose_estimation_b200 import multi
+
     H = len(c4.guess)
-    per = (H + world - 1) // world
-    lo, hi = min(rank * per, H), min((rank + 1) * per, H)
+    per = multi.shard_size(H, world)
+    lo, hi = multi.shard_range(H, world, rank)
     h_local = hi - lo
     params = pcl.IcpParams()
     lib.peb_icp_params_default(C.byref(params))
@@ -233,9 +235,7 @@ def run_ours(args):
     ctx.sync()
 
     def gather():
-        if world > 1:
-            d_pad[: h_local * rec].copy_(d_res[: h_local * rec])
-            dist.all_gather_into_tensor(d_all, d_pad)
+        multi.gather_results(d_res, H, world, rank, out=d_all, pad=d_pad)
 
     def step_device():
         chk(lib.peb_icp_align_batch_dev(ctx.handle, d_guess.data_ptr(), h_local, C.byref(params), d_res.data_ptr()))
@@ -355,11 +355,10 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline(c4)
     if rank == 0:
         # sanity: every hypothesis ran all its iterations
-        recs = np.frombuffer(results_bytes, dtype=np.dtype([("T", "<f4", 16), ("fitness", "<f8"), ("mse", "<f8"),
-                                                                       ("it", "<i4"), ("conv", "<i4"), ("state", "<i4"),
-                                                                       ("n", "<i4")]))[:H]
-        line["check"] = {"iterations_all": bool((recs["it"] == ITERATIONS).all()),
-                         "fitness_median": float(np.median(recs["fitness"]))}
+        recs = multi.unpack_results(results_bytes, H, world)
+        line["check"] = {"iterations_all": bool((recs["iterations"] == ITERATIONS).all()),
+                         "fitness_median": float(np.median(recs["fitness"])),
+                         "best_hypothesis": multi.best_hypothesis(recs)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

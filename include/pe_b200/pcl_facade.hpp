@@ -1,0 +1,205 @@
+// pcl_facade.hpp — header-only C++ facade over the C ABI of libpe_b200.so (include/pe_b200.h).
+//
+// The classes carry the names, setters, defaults and enum values of the PCL 1.10 classes the
+// north-star path substitutes into the reference's slots, so host code written against PCL ports
+// by a namespace swap (pcl:: -> pe_b200::):
+//
+//   pe_b200::VoxelGrid                         pcl::VoxelGrid<pcl::PointXYZ>
+//        down-sample slot  pose_estimation/src/pose_estimation.cpp:261-263
+//   pe_b200::NormalEstimation                  pcl::NormalEstimation<pcl::PointXYZ, pcl::Normal>
+//        normals slot      pose_estimation/src/opencv_surface_match.cpp:57-59
+//   pe_b200::IterativeClosestPoint             pcl::IterativeClosestPoint<PointXYZ, PointXYZ>
+//   pe_b200::IterativeClosestPointWithNormals  pcl::IterativeClosestPointWithNormals<PointNormal, PointNormal>
+//        refinement slot   pose_estimation/src/opencv_surface_match.cpp:85-94
+//
+// Clouds are passed as (pointer, count, stride in bytes): pcl::PointCloud<PointXYZ>::points.data()
+// with stride 16, pcl::PointNormal with stride 48, rows of a cv::Mat N x 3 / N x 6 CV_32F with
+// stride 12 / 24 (cv::Mat::step).  Matrices are 16 floats column-major, i.e.
+// Eigen::Matrix4f::data().  No dependency on PCL, Eigen or OpenCV.  Errors throw pe_b200::Error
+// (the C ABI itself never throws); numerical outcomes are reported like PCL reports them.
+#pragma once
+
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../pe_b200.h"
+
+namespace pe_b200 {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+struct CloudView {
+  const void* data = nullptr;
+  size_t size = 0;
+  size_t stride = 16;
+};
+
+// owns one peb_ctx; share one Context between the objects used by one thread
+class Context {
+ public:
+  explicit Context(int device = 0) {
+    if (int rc = peb_ctx_create(device, &ctx_)) throw Error(rc, peb_last_error(nullptr));
+  }
+  ~Context() { peb_ctx_destroy(ctx_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  peb_ctx* get() const { return ctx_; }
+  void check(int rc) const {
+    if (rc != PEB_OK) throw Error(rc, peb_last_error(ctx_));
+  }
+
+ private:
+  peb_ctx* ctx_ = nullptr;
+};
+
+class VoxelGrid {
+ public:
+  explicit VoxelGrid(Context& c) : c_(c) {}
+  void setInputCloud(const void* pts, size_t n, size_t stride = 16) { in_ = {pts, n, stride}; }
+  void setLeafSize(float lx, float ly, float lz) { leaf_[0] = lx, leaf_[1] = ly, leaf_[2] = lz; }
+  void setMinimumPointsNumberPerVoxel(unsigned n) { min_pts_ = n; }
+  unsigned getMinimumPointsNumberPerVoxel() const { return min_pts_; }
+  // output: x y z 1 records (pcl::PointXYZ memory image), ascending voxel index
+  void filter(std::vector<float>& out_xyz4) {
+    out_xyz4.resize(4 * (in_.size ? in_.size : 1));
+    size_t m = 0;
+    c_.check(peb_voxel_grid(c_.get(), in_.data, in_.size, in_.stride, leaf_[0], leaf_[1], leaf_[2], min_pts_,
+                            out_xyz4.data(), &m));
+    out_xyz4.resize(4 * m);
+  }
+
+ private:
+  Context& c_;
+  CloudView in_;
+  float leaf_[3] = {0, 0, 0};
+  unsigned min_pts_ = 0;
+};
+
+class NormalEstimation {
+ public:
+  explicit NormalEstimation(Context& c) : c_(c) {}
+  void setInputCloud(const void* pts, size_t n, size_t stride = 16) { in_ = {pts, n, stride}; }
+  void setKSearch(int k) { k_ = k; }
+  int getKSearch() const { return k_; }
+  void setRadiusSearch(double r) {
+    if (r != 0.0) throw Error(PEB_E_UNSUPPORTED, "NormalEstimation::setRadiusSearch has no CUDA path (no CPU fallback)");
+  }
+  void setViewPoint(float x, float y, float z) { vp_[0] = x, vp_[1] = y, vp_[2] = z; }
+  // output: pcl::Normal records (nx ny nz 0 | curvature 0 0 0), 8 floats each
+  void compute(std::vector<float>& out_normal8) {
+    out_normal8.resize(8 * in_.size);
+    c_.check(peb_normals_knn(c_.get(), in_.data, in_.size, in_.stride, k_, vp_, out_normal8.data()));
+  }
+
+ private:
+  Context& c_;
+  CloudView in_;
+  int k_ = 0;
+  float vp_[3] = {0, 0, 0};
+};
+
+// pcl::registration::DefaultConvergenceCriteria<float>, the part reachable through getConvergeCriteria()
+class ConvergenceCriteria {
+ public:
+  enum ConvergenceState {
+    CONVERGENCE_CRITERIA_NOT_CONVERGED = PEB_NOT_CONVERGED,
+    CONVERGENCE_CRITERIA_ITERATIONS = PEB_ITERATIONS,
+    CONVERGENCE_CRITERIA_TRANSFORM = PEB_TRANSFORM,
+    CONVERGENCE_CRITERIA_ABS_MSE = PEB_ABS_MSE,
+    CONVERGENCE_CRITERIA_REL_MSE = PEB_REL_MSE,
+    CONVERGENCE_CRITERIA_NO_CORRESPONDENCES = PEB_NO_CORRESPONDENCES,
+    CONVERGENCE_CRITERIA_FAILURE_AFTER_MAX_ITERATIONS = PEB_FAILURE_AFTER_MAX_ITERATIONS
+  };
+  explicit ConvergenceCriteria(peb_icp_params& p) : p_(p) {}
+  void setAbsoluteMSE(double v) { p_.abs_mse_threshold = v; }
+  double getAbsoluteMSE() const { return p_.abs_mse_threshold; }
+  void setMaximumIterationsSimilarTransforms(int n) { p_.max_iterations_similar = n; }
+  ConvergenceState getConvergenceState() const { return static_cast<ConvergenceState>(state_); }
+
+ private:
+  friend class IterativeClosestPoint;
+  peb_icp_params& p_;
+  int state_ = PEB_NOT_CONVERGED;
+};
+
+class IterativeClosestPoint {
+ public:
+  explicit IterativeClosestPoint(Context& c, int estimator = PEB_ESTIMATOR_SVD) : c_(c), criteria_(params_) {
+    peb_icp_params_default(&params_);
+    params_.estimator = estimator;
+    std::memset(&result_, 0, sizeof(result_));
+    for (int i = 0; i < 4; ++i) result_.T[5 * i] = 1.0f;
+  }
+  virtual ~IterativeClosestPoint() = default;
+
+  void setInputSource(const void* pts, size_t n, size_t stride = 16) {
+    c_.check(peb_source_set(c_.get(), pts, n, stride));
+    n_src_ = n;
+  }
+  // normals: nullable; pcl::Normal records have stride 32, the normal inside a pcl::PointNormal
+  // is at (pts + 16 bytes, stride 48)
+  void setInputTarget(const void* pts, size_t n, size_t stride = 16, const void* normals = nullptr, size_t nstride = 32) {
+    c_.check(peb_target_set(c_.get(), pts, n, stride, normals, nstride));
+  }
+  void setMaximumIterations(int n) { params_.max_iterations = n; }
+  int getMaximumIterations() const { return params_.max_iterations; }
+  void setMaxCorrespondenceDistance(double d) { params_.max_corr_dist = d; }
+  double getMaxCorrespondenceDistance() const { return params_.max_corr_dist; }
+  void setTransformationEpsilon(double e) { params_.transformation_epsilon = e; }
+  void setTransformationRotationEpsilon(double e) { params_.rotation_epsilon = e; }
+  void setEuclideanFitnessEpsilon(double e) { params_.euclidean_fitness_epsilon = e; }
+  void setUseReciprocalCorrespondences(bool on) {
+    if (on) throw Error(PEB_E_UNSUPPORTED, "reciprocal correspondences have no CUDA path (no CPU fallback)");
+  }
+  void setRANSACIterations(int n) {
+    if (n) throw Error(PEB_E_UNSUPPORTED, "the RANSAC rejector has no CUDA path (no CPU fallback)");
+  }
+  // addCorrespondenceRejector(CorrespondenceRejectorDistance with setMaximumDistance(d))
+  void addCorrespondenceRejectorDistance(double max_distance) { params_.rejector_max_dist = max_distance; }
+  ConvergenceCriteria* getConvergeCriteria() { return &criteria_; }
+
+  // align(output, guess): out_xyz4 (nullable) receives final * input as x y z 1 records
+  void align(std::vector<float>* out_xyz4 = nullptr, const float* guess16 = nullptr) {
+    if (out_xyz4) out_xyz4->resize(4 * n_src_);
+    c_.check(peb_icp_align(c_.get(), guess16, &params_, &result_, out_xyz4 && n_src_ ? out_xyz4->data() : nullptr, nullptr,
+                           nullptr));
+    criteria_.state_ = result_.state;
+  }
+  // H initial poses against one source / one target: the call shape of
+  // cv::ppf_match_3d::ICP::registerModelToScene(model, scene, poses), opencv_surface_match.cpp:94
+  void alignBatch(const float* guesses16, size_t n_guesses, std::vector<peb_icp_result>& results) {
+    results.resize(n_guesses);
+    c_.check(peb_icp_align_batch(c_.get(), guesses16, n_guesses, &params_, results.data()));
+  }
+  bool hasConverged() const { return result_.converged != 0; }
+  const float* getFinalTransformation() const { return result_.T; }  // column-major 4x4
+  double getFitnessScore(double max_range = DBL_MAX) {
+    if (max_range == params_.fitness_max_range) return result_.fitness;
+    double f = 0;
+    c_.check(peb_fitness_score(c_.get(), result_.T, max_range, &f, nullptr));
+    return f;
+  }
+  int nr_iterations() const { return result_.iterations; }
+  const peb_icp_result& result() const { return result_; }
+
+ protected:
+  Context& c_;
+  peb_icp_params params_;
+  peb_icp_result result_;
+  ConvergenceCriteria criteria_;
+  size_t n_src_ = 0;
+};
+
+class IterativeClosestPointWithNormals : public IterativeClosestPoint {
+ public:
+  explicit IterativeClosestPointWithNormals(Context& c) : IterativeClosestPoint(c, PEB_ESTIMATOR_POINT_TO_PLANE_LLS) {}
+};
+
+}  // namespace pe_b200
