@@ -74,6 +74,14 @@ int target_finish(peb_ctx* ctx, size_t n, bool has_normals) {
                     static_cast<int>(n), ctx->grid_occupancy);
 }
 
+int source_finish(peb_ctx* ctx, size_t n) {
+  ctx->n_src = n;
+  PEB_TRY(grid_build(ctx, &ctx->src_grid, ctx->src.as<float4>(), nullptr, static_cast<int>(n), ctx->src_sort_occupancy));
+  ctx->n_src_sorted = ctx->src_grid.view.n;
+  ctx->src_set = true;
+  return PEB_OK;
+}
+
 int upload_guesses(peb_ctx* ctx, const float* guesses, size_t H, const float** d_out) {
   *d_out = nullptr;
   if (!guesses) return PEB_OK;
@@ -155,7 +163,7 @@ PEB_API void peb_ctx_destroy(peb_ctx* ctx) {
                     &ctx->d_results, &ctx->d_aligned, &ctx->vg_in, &ctx->vg_out, &ctx->vg_flags, &ctx->vg_scan,
                     &ctx->vg_starts, &ctx->nrm_in, &ctx->nrm_out, &ctx->nn_q, &ctx->nn_idx, &ctx->nn_d2};
   for (DevBuf* b : bufs) b->release();
-  for (Grid* g : {&ctx->tgt_grid, &ctx->aux_grid}) {
+  for (Grid* g : {&ctx->tgt_grid, &ctx->aux_grid, &ctx->src_grid}) {
     g->pts.release();
     g->normals.release();
     g->cell_start.release();
@@ -186,6 +194,11 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
   if (!strcmp(key, "grid_occupancy_x100")) {
     if (value < 25 || value > 6400) return fail(ctx, PEB_E_INVALID_ARG, "grid_occupancy_x100 out of [25, 6400]");
     ctx->grid_occupancy = value / 100.0f;
+    return PEB_OK;
+  }
+  if (!strcmp(key, "source_sort_occupancy")) {
+    if (value < 1 || value > 1024) return fail(ctx, PEB_E_INVALID_ARG, "source_sort_occupancy out of [1, 1024]");
+    ctx->src_sort_occupancy = static_cast<float>(value);
     return PEB_OK;
   }
   if (!strcmp(key, "warm_start")) {
@@ -319,9 +332,7 @@ PEB_API int peb_source_set(peb_ctx* ctx, const void* pts, size_t n, size_t strid
   PEB_TRY(check_cloud(ctx, "source_set", pts, n, stride));
   PEB_CUDA(ctx, ctx->src.ensure(n * sizeof(float4)));
   PEB_TRY(upload_cloud(ctx, pts, n, stride, 1.0f, ctx->src.as<float4>()));
-  ctx->n_src = n;
-  ctx->src_set = true;
-  return PEB_OK;
+  return source_finish(ctx, n);
 }
 
 PEB_API int peb_source_set_dev(peb_ctx* ctx, const void* d_xyz4, size_t n) {
@@ -332,9 +343,7 @@ PEB_API int peb_source_set_dev(peb_ctx* ctx, const void* d_xyz4, size_t n) {
   if (n > static_cast<size_t>(INT32_MAX) / 2) return fail(ctx, PEB_E_INVALID_ARG, "source_set: too many points");
   PEB_CUDA(ctx, ctx->src.ensure(n * sizeof(float4)));
   if (n) PEB_CUDA(ctx, cudaMemcpyAsync(ctx->src.p, d_xyz4, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
-  ctx->n_src = n;
-  ctx->src_set = true;
-  return PEB_OK;
+  return source_finish(ctx, n);
 }
 
 // ---- nearest neighbour ------------------------------------------------------------------------------

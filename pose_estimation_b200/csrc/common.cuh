@@ -97,7 +97,7 @@ struct peb_ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   uint64_t launches = 0;
-  int nn_group = 8;             // lanes that share one nearest-neighbour query (1, 2, 4, 8, 16)
+  int nn_group = 1;             // lanes that share one COLD nearest-neighbour query (1, 2, 4, 8, 16)
   float grid_occupancy = 2.0f;  // wanted mean points per occupied cell of the target grid
   bool warm_start = true;       // iterations >= 1 seed the search with the previous match
 
@@ -118,6 +118,12 @@ struct peb_ctx {
   peb::DevBuf src;           // float4 xyz1, original order
   size_t n_src = 0;
   bool src_set = false;
+  // the finite source points sorted by the cells of a coarse grid over the source itself
+  // (~32 points per cell = one warp per compact patch): neighbouring threads get neighbouring
+  // queries, i.e. the same grid rows, the same ring counts and L1 hits.  .w = original index.
+  peb::Grid src_grid;
+  int n_src_sorted = 0;
+  float src_sort_occupancy = 32.0f;
 
   // ICP working set
   peb::DevBuf work;          // float4 working cloud (single align)

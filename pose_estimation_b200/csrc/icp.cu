@@ -36,11 +36,11 @@ constexpr int kIcpThreads = 128;
 
 struct IcpLaunch {
   GridView grid;
-  const float4* src;     // n_src records, original order
-  float4* work;          // H x n_src working clouds
+  const float4* src;     // n_src FINITE source points in patch order, .w = original index
+  float4* work;          // H x n_src working clouds (same order)
   IcpState* states;      // H
   double* partials;      // H x blocks_per_hyp x kAccMax
-  int32_t* corr_idx;     // nullable, n_src (single align only)
+  int32_t* corr_idx;     // nullable, indexed by ORIGINAL source index (single align only)
   float* corr_d2;        // nullable
   Mat4* trace;           // nullable, trace_cap increments (single align only)
   peb_icp_result* results;  // H (fitness kernel)
@@ -227,9 +227,10 @@ __global__ void __launch_bounds__(kIcpThreads, PEB_ICP_MIN_BLOCKS) icp_iteration
     bool keep = valid && best.idx >= 0;
     if (keep && static_cast<double>(best.d2) > L.max_dist_sqr) keep = false;
     if (keep && L.use_rejector && !(best.d2 < L.rej_max2)) keep = false;
-    if (in && lane_in_group == 0) {
-      if (L.corr_idx) L.corr_idx[i] = keep ? best.idx : -1;
-      if (L.corr_d2) L.corr_d2[i] = keep ? best.d2 : 0.0f;
+    if (in && lane_in_group == 0 && L.corr_idx) {
+      const int orig = __float_as_int(L.src[i].w);
+      L.corr_idx[orig] = keep ? best.idx : -1;
+      L.corr_d2[orig] = keep ? best.d2 : 0.0f;
     }
     if (keep && lane_in_group == 0) {
       const float4 t = L.grid.pts[best.j];
@@ -497,9 +498,9 @@ namespace {
 
 // fills everything of the launch record that does not depend on the mode
 int prepare_launch(peb_ctx* ctx, size_t H, const peb_icp_params* prm, IcpLaunch& L) {
-  const int n = static_cast<int>(ctx->n_src);
+  const int n = ctx->n_src_sorted;
   L.grid = ctx->tgt_grid.view;
-  L.src = ctx->src.as<float4>();
+  L.src = ctx->src_grid.view.pts;
   L.n_src = n;
   const int max_bph = std::max(blocks_for(n, H, ctx->nn_group), blocks_for(n, H, 1));
   PEB_CUDA(ctx, ctx->work.ensure(std::max<size_t>(H * static_cast<size_t>(n), 1) * sizeof(float4)));
@@ -539,13 +540,17 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
     return fail(ctx, PEB_E_UNSUPPORTED, "align: unknown estimator %d (no CPU fallback)", prm->estimator);
   if (prm->estimator == PEB_ESTIMATOR_POINT_TO_PLANE_LLS && !ctx->tgt_has_normals)
     return fail(ctx, PEB_E_INVALID_ARG, "align: point-to-plane needs target normals (peb_target_set normals)");
-  const int n = static_cast<int>(ctx->n_src);
+  const int n = ctx->n_src_sorted;
+  const int n_all = static_cast<int>(ctx->n_src);
   IcpLaunch L{};
   PEB_TRY(prepare_launch(ctx, H, prm, L));
   L.results = d_results;
   if (single_mode) {
-    PEB_CUDA(ctx, ctx->corr_idx.ensure(std::max(n, 1) * sizeof(int32_t)));
-    PEB_CUDA(ctx, ctx->corr_d2.ensure(std::max(n, 1) * sizeof(float)));
+    PEB_CUDA(ctx, ctx->corr_idx.ensure(std::max(n_all, 1) * sizeof(int32_t)));
+    PEB_CUDA(ctx, ctx->corr_d2.ensure(std::max(n_all, 1) * sizeof(float)));
+    // non-finite source points never take part: they stay "no correspondence"
+    PEB_CUDA(ctx, cudaMemsetAsync(ctx->corr_idx.p, 0xFF, std::max(n_all, 1) * sizeof(int32_t), ctx->stream));
+    PEB_CUDA(ctx, cudaMemsetAsync(ctx->corr_d2.p, 0, std::max(n_all, 1) * sizeof(float), ctx->stream));
     const int cap = std::max(prm->max_iterations, 1);
     PEB_CUDA(ctx, ctx->trace.ensure(static_cast<size_t>(cap) * sizeof(Mat4)));
     L.corr_idx = ctx->corr_idx.as<int32_t>();
@@ -592,7 +597,7 @@ int fitness_device(peb_ctx* ctx, const float* d_T, double max_range, peb_icp_res
   L.results = d_result;
   L.fitness_only = 1;
   L.warm = 0;  // an arbitrary transform: nothing to seed the search with
-  L.blocks_per_hyp = blocks_for(static_cast<int>(ctx->n_src), 1, ctx->nn_group);
+  L.blocks_per_hyp = blocks_for(ctx->n_src_sorted, 1, ctx->nn_group);
   PEB_LAUNCH(ctx, icp_init_kernel, 1, 128, 0, L.states, d_T, 1);
   return launch_fitness_g(ctx, ctx->nn_group, L, 1);
 }

@@ -43,50 +43,36 @@ def main():
         print(f"  voxel grid (host buffers, e2e): {1e3 * (time.perf_counter() - t0):.2f} ms")
 
     icp = pcl.IterativeClosestPoint(ctx)
-    icp.setInputSource(prob.source)
     icp.setMaximumIterations(30)
     icp.getConvergeCriteria().setAbsoluteMSE(-1.0)
     ctx.set_int("profile", 1)
-    for warm in (0, 1):
-      ctx.set_int("warm_start", warm)
-      print("warm_start", warm)
-      for occ in (200, 400):
-        ctx.set_int("grid_occupancy_x100", occ)
-        t0 = time.perf_counter()
-        icp.setInputTarget(prob.target)
-        t_set = time.perf_counter() - t0
-        gi = ctx.grid_info()
-        print(f"occupancy {occ / 100}: cell {gi.cell * 1e3:.3f} mm dims {list(gi.dims)} cells {gi.n_cells} "
-              f"target_set {1e3 * t_set:.2f} ms", flush=True)
-        for g in (1, 4, 8, 16):
+    icp.setInputTarget(prob.target)
+    rng = np.random.default_rng(0)
+    guesses = np.stack([synth.perturb_pose(prob.gt_pose, rng, 6.0, 0.008) for _ in range(128)])
+    for socc in (1, 8, 32, 128):
+        ctx.set_int("source_sort_occupancy", socc)
+        icp.setInputSource(prob.source)
+        for g in (1, 8):
             ctx.set_int("nn_group", g)
+            icp.setMaxCorrespondenceDistance(1e9)
             best = 1e9
             for rep in range(5):
                 t0 = time.perf_counter()
                 icp.align(prob.guess, want_output=False)
                 best = min(best, time.perf_counter() - t0)
             pr = profile(ctx)
-            print(f"   G={g:2d}: align wall {1e3 * best:.3f} ms | kernels sum {pr.sum():.3f} ms, iter first {pr[0] * 1e3:.1f} us "
-                  f"median {np.median(pr[:-1]) * 1e3:.1f} us, fitness {pr[-1] * 1e3:.1f} us | it {icp.nr_iterations_} "
-                  f"fitness {icp.getFitnessScore():.4e}", flush=True)
-    # small batch
-    ctx.set_int("grid_occupancy_x100", 200)
-    icp.setInputTarget(prob.target)
-    rng = np.random.default_rng(0)
-    guesses = np.stack([synth.perturb_pose(prob.gt_pose, rng, 6.0, 0.008) for _ in range(128)])
-    icp.setMaxCorrespondenceDistance(0.02)
-    for g, warm in ((1, 0), (8, 0), (1, 1), (8, 1), (16, 1)):
-        ctx.set_int("nn_group", g)
-        ctx.set_int("warm_start", warm)
-        best = 1e9
-        for rep in range(3):
-            t0 = time.perf_counter()
-            res = icp.alignBatch(guesses)
-            best = min(best, time.perf_counter() - t0)
-        pr = profile(ctx)
-        fit = np.array([r.fitness for r in res])
-        print(f"batch H=128 G={g} warm={warm} iters(ms) {np.round(pr[:8], 2).tolist()}: wall {1e3 * best:.2f} ms = {128 / best:.0f} hyp/s | kernels {pr.sum():.2f} ms, "
-              f"iter0 {pr[0]:.3f} ms, median {np.median(pr[:-1]):.3f} ms | fitness median {np.median(fit):.3e}", flush=True)
+            print(f"src_occ {socc:3d} G={g}: single align wall {1e3 * best:.3f} ms | kernels {pr.sum():.3f} ms, first {pr[0] * 1e3:.1f} us "
+                  f"median {np.median(pr[:-1]) * 1e3:.1f} us, fitness {pr[-1] * 1e3:.1f} us | fit {icp.getFitnessScore():.4e}", flush=True)
+            icp.setMaxCorrespondenceDistance(0.02)
+            best = 1e9
+            for rep in range(3):
+                t0 = time.perf_counter()
+                res = icp.alignBatch(guesses)
+                best = min(best, time.perf_counter() - t0)
+            pr = profile(ctx)
+            fit = np.array([r.fitness for r in res])
+            print(f"src_occ {socc:3d} G={g}: batch H=128 iters(ms) {np.round(pr[:6], 2).tolist()} wall {1e3 * best:.2f} ms = {128 / best:.0f} hyp/s | "
+                  f"median {np.median(pr[:-1]):.3f} ms | fitness median {np.median(fit):.3e}", flush=True)
     # normals
     ne = pcl.NormalEstimation(ctx)
     ne.setInputCloud(prob.target)
