@@ -117,6 +117,14 @@ def cpu_params():
     return default_params(max_iterations=ITERATIONS, abs_mse_threshold=-1.0, max_corr_dist=MAX_CORR_DIST)
 
 
+def host_threads() -> int:
+    """Host cores this process may use (torchrun pins OMP_NUM_THREADS to 1; the oracle takes an explicit count)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_batch_rate(orc_icp, source, guesses, threads: int, n: int) -> tuple[float, float]:
     g = guesses[:n]
     t0 = time.perf_counter()
@@ -134,7 +142,7 @@ def run_reference(args):
     build()
     orc = Oracle(fast=True)
     slow = Oracle()
-    cores = orc.max_threads()
+    cores = host_threads()
     c4, _ = make_workloads(lambda p, leaf: slow.voxel_grid(p, leaf)[0], False, N_HYP, args.scale)
     icp = orc.icp(c4.target)
     # calibrate the per-step sample so that the whole run stays within ~150 s
@@ -415,7 +423,7 @@ def cpu_baseline(c4):
 
     build()
     orc = Oracle(fast=True)
-    cores = orc.max_threads()
+    cores = host_threads()
     icp = orc.icp(c4.target)
     n = max(cores, 8)
     rate, dt = cpu_batch_rate(icp, c4.source, c4.guess, cores, n)

@@ -10,7 +10,10 @@ import ctypes as C
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libpe_b200.so"
+import os as _os
+
+# PEB_LIB_VARIANT is a development switch (register-cap experiments build libpe_b200_<variant>.so)
+LIB_PATH = _HERE / ("libpe_b200" + ("_" + _os.environ["PEB_LIB_VARIANT"] if _os.environ.get("PEB_LIB_VARIANT") else "") + ".so")
 
 PEB_OK = 0
 STATUS_NAMES = {

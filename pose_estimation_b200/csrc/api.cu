@@ -158,7 +158,7 @@ PEB_API void peb_ctx_destroy(peb_ctx* ctx) {
   if (!ctx) return;
   DeviceGuard guard(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->d_small, &ctx->d_scratch, &ctx->d_stage, &ctx->tgt_raw, &ctx->tgt_nrm_raw, &ctx->src, &ctx->work,
+  DevBuf* bufs[] = {&ctx->d_small, &ctx->d_scratch, &ctx->d_stage, &ctx->tgt_raw, &ctx->tgt_nrm_raw, &ctx->src, &ctx->work, &ctx->slack,
                     &ctx->corr_idx, &ctx->corr_d2, &ctx->partials, &ctx->state, &ctx->trace, &ctx->d_guesses,
                     &ctx->d_results, &ctx->d_aligned, &ctx->vg_in, &ctx->vg_out, &ctx->vg_flags, &ctx->vg_scan,
                     &ctx->vg_starts, &ctx->nrm_in, &ctx->nrm_out, &ctx->nn_q, &ctx->nn_idx, &ctx->nn_d2};
@@ -199,6 +199,11 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
   if (!strcmp(key, "source_sort_occupancy")) {
     if (value < 1 || value > 1024) return fail(ctx, PEB_E_INVALID_ARG, "source_sort_occupancy out of [1, 1024]");
     ctx->src_sort_occupancy = static_cast<float>(value);
+    return PEB_OK;
+  }
+  if (!strcmp(key, "cert_margin_x1000")) {
+    if (value < 0 || value > 4000) return fail(ctx, PEB_E_INVALID_ARG, "cert_margin_x1000 out of [0, 4000]");
+    ctx->cert_margin = value / 1000.0f;
     return PEB_OK;
   }
   if (!strcmp(key, "warm_start")) {

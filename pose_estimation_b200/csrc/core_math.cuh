@@ -218,6 +218,75 @@ PEB_HD NnBest grid_nn_warm(const GridView& g, float qx, float qy, float qz, int 
   return best;
 }
 
+// The same search with a certificate.
+// Certificate: the ball is grown by `margin`, and the search also tracks the runner-up distance.
+// On return *slack_out is a lower bound on (distance of any OTHER target point) - (distance of the
+// winner): every point within sqrt(best) + margin has been examined.  While the query has moved by
+// less than slack / 2 since then, the winner is still the exact nearest neighbour and the next
+// search can be skipped (icp.cu).  slack <= 0: no certificate (exact tie, or winner beyond limit).
+PEB_HD NnBest grid_nn_warm_cert(const GridView& g, float qx, float qy, float qz, int j_prev, float limit_d2,
+                                float margin, float* slack_out) {
+  NnBest best;
+  {
+    const float4 p = g.pts[j_prev];
+    best.d2 = l2_simple(qx, qy, qz, p.x, p.y, p.z);
+#ifdef __CUDA_ARCH__
+    best.idx = __float_as_int(p.w);
+#else
+    memcpy(&best.idx, &p.w, 4);
+#endif
+    best.j = j_prev;
+  }
+  float second = FLT_MAX;  // smallest squared distance among examined points other than the winner
+  const float pad = 0.001f * g.h + margin;  // 0.001 h >> one ulp of any coordinate (h >= 1e-4 * max |coordinate|)
+  const float R = sqrtf(fminf(best.d2, limit_d2)) * 1.0001f + pad;
+  const int y0 = grid_coord(qy - R, g.oy, g.inv_h, g.dy), y1 = grid_coord(qy + R, g.oy, g.inv_h, g.dy);
+  const int z0 = grid_coord(qz - R, g.oz, g.inv_h, g.dz), z1 = grid_coord(qz + R, g.oz, g.inv_h, g.dz);
+  for (int z = z0; z <= z1; ++z) {
+    const float dz = grid_slab_dist(qz, g.oz, g.h, z);
+    for (int y = y0; y <= y1; ++y) {
+      const float dy = grid_slab_dist(qy, g.oy, g.h, y);
+      const float dyz2 = dy * dy + dz * dz;
+      const float rc = sqrtf(fminf(best.d2, limit_d2)) * 1.0001f + pad;  // radius still to be covered
+      const float rx2 = rc * rc - dyz2;
+      if (rx2 < 0.0f) continue;
+      const float rx = sqrtf(rx2) * 1.0001f;
+      const int x0 = grid_coord(qx - rx, g.ox, g.inv_h, g.dx), x1 = grid_coord(qx + rx, g.ox, g.inv_h, g.dx);
+      const int base = (z * g.dy + y) * g.dx;
+      const uint32_t s = g.cell_start[base + x0], e = g.cell_start[base + x1 + 1];
+      for (uint32_t j = s; j < e; ++j) {
+        if (static_cast<int>(j) == best.j) continue;
+        const float4 p = g.pts[j];
+        const float d2 = l2_simple(qx, qy, qz, p.x, p.y, p.z);
+#ifdef __CUDA_ARCH__
+        const int id = __float_as_int(p.w);
+#else
+        int id;
+        memcpy(&id, &p.w, 4);
+#endif
+        if (d2 < best.d2 || (d2 == best.d2 && id < best.idx)) {
+          second = best.d2;
+          best.d2 = d2;
+          best.idx = id;
+          best.j = static_cast<int>(j);
+        } else {
+          second = fminf(second, d2);
+        }
+      }
+    }
+  }
+  if (slack_out) {
+    float slack = -1.0f;
+    if (best.d2 <= limit_d2) {
+      const float db = sqrtf(best.d2);
+      // examined points are at least sqrt(second) away, unexamined ones more than db + margin
+      slack = fminf(sqrtf(second) - db, margin) - (1e-5f * g.h + 1e-6f * db);
+    }
+    *slack_out = slack;
+  }
+  return best;
+}
+
 // After this many rings the search gives up on the grid and scans every point (still exact):
 // a query that far from all target points costs O(r^3) row visits on the grid, which beats a
 // full scan only while r stays small.  Rings 1..16 visit ~6 k rows.

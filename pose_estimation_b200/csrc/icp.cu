@@ -30,14 +30,17 @@ namespace peb {
 namespace {
 
 constexpr int kIcpThreads = 128;
-#ifndef PEB_ICP_MIN_BLOCKS
-#define PEB_ICP_MIN_BLOCKS 5  // 96 registers: no spills in the per-query loop, 20 warps per SM
-#endif
+// Register caps (measured on B200, bench C4 / C2): a single align is latency-bound per launch and
+// wants no spills (5 blocks/SM = 96 registers); the batched mode is throughput-bound and gains 17 %
+// from 8 blocks/SM (64 registers, a few spills to L1) through the extra warps that hide L2 latency.
+constexpr int kMinBlocksSingle = 5;
+constexpr int kMinBlocksBatch = 8;
 
 struct IcpLaunch {
   GridView grid;
   const float4* src;     // n_src FINITE source points in patch order, .w = original index
-  float4* work;          // H x n_src working clouds (same order)
+  float4* work;          // H x n_src working clouds (same order); .w = sorted position of the last match
+  float* slack;          // H x n_src: how far the point may still move before its match must be searched again
   IcpState* states;      // H
   double* partials;      // H x blocks_per_hyp x kAccMax
   int32_t* corr_idx;     // nullable, indexed by ORIGINAL source index (single align only)
@@ -56,6 +59,7 @@ struct IcpLaunch {
   int trace_cap;
   int fitness_only;      // peb_fitness_score: the record's n_correspondences carries the inlier count
   int warm;              // seed every search with the match stored in the working point's .w
+  float margin;          // extra search radius that buys the skip-the-search certificate (0: none)
 };
 
 __global__ void icp_init_kernel(IcpState* __restrict__ states, const float* __restrict__ guesses, int H) {
@@ -153,8 +157,8 @@ __device__ __noinline__ void finish_iteration(IcpState* st, const IcpCriteria* c
   *st = s;
 }
 
-template <int G, int EST>
-__global__ void __launch_bounds__(kIcpThreads, PEB_ICP_MIN_BLOCKS) icp_iteration_kernel(const IcpLaunch L) {
+template <int G, int EST, int MB, bool CERT>
+__global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_kernel(const IcpLaunch L) {
   constexpr int NACC = (EST == PEB_ESTIMATOR_SVD) ? kAccSvd : kAccLls;
   __shared__ double sm[kIcpThreads / 32][kAccMax];
   __shared__ double sm_tot[kAccMax];
@@ -202,9 +206,14 @@ __global__ void __launch_bounds__(kIcpThreads, PEB_ICP_MIN_BLOCKS) icp_iteration
     if (in) p = first ? L.src[i] : work[i];
     const int j_prev = first ? -1 : __float_as_int(p.w);  // last iteration's match (sorted position)
     const bool valid = in && finite3(p.x, p.y, p.z);
+    float moved = 0.0f;
     if (valid && apply) {
       float ox, oy, oz;
       transform_icp(T, p.x, p.y, p.z, ox, oy, oz);
+      if (CERT) {
+        const float mx = ox - p.x, my = oy - p.y, mz = oz - p.z;
+        moved = sqrtf(mx * mx + my * my + mz * mz);
+      }
       p.x = ox;
       p.y = oy;
       p.z = oz;
@@ -214,11 +223,30 @@ __global__ void __launch_bounds__(kIcpThreads, PEB_ICP_MIN_BLOCKS) icp_iteration
     best.d2 = pos_inf();
     best.idx = -1;
     best.j = -1;
+    float slack = -1.0f;
     if (valid) {
-      if (G == 1 && L.warm && j_prev >= 0 && j_prev < L.grid.n)
-        best = grid_nn_warm(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2);
-      else
+      float* sl = L.slack + static_cast<size_t>(h) * L.n_src + i;
+      if (G == 1 && L.warm && j_prev >= 0 && j_prev < L.grid.n) {
+        if (CERT) {
+          // certificate of the previous search (core_math.cuh : grid_nn_warm_cert): every other
+          // target point was at least `slack` farther than the match; the point has moved by `moved`
+          slack = *sl - 2.000002f * moved - 1e-5f * L.grid.h;
+          if (slack > 0.0f) {
+            const float4 t = L.grid.pts[j_prev];
+            best.d2 = l2_simple(p.x, p.y, p.z, t.x, t.y, t.z);
+            best.idx = __float_as_int(t.w);
+            best.j = j_prev;
+          } else {
+            best = grid_nn_warm_cert(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2, L.margin, &slack);
+          }
+          *sl = slack;
+        } else {
+          best = grid_nn_warm(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2);
+        }
+      } else {
         best = grid_nn<G>(L.grid, p.x, p.y, p.z, L.stop_d2);
+        if (CERT && lane_in_group == 0) *sl = -1.0f;
+      }
     }
     if (in && lane_in_group == 0 && (first || valid)) {
       p.w = __int_as_float(best.j);
@@ -343,11 +371,31 @@ __global__ void __launch_bounds__(kIcpThreads) icp_fitness_kernel(const IcpLaunc
       float qx, qy, qz;
       transform_tpc(T, p.x, p.y, p.z, qx, qy, qz);
       int j_prev = -1;
-      if (G == 1 && L.warm) j_prev = __float_as_int(L.work[static_cast<size_t>(h) * L.n_src + i].w);
-      if (G == 1 && j_prev >= 0 && j_prev < L.grid.n)
-        best = grid_nn_warm(L.grid, qx, qy, qz, j_prev, L.fitness_stop_d2);
-      else
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (G == 1 && L.warm) {
+        w = L.work[static_cast<size_t>(h) * L.n_src + i];
+        j_prev = __float_as_int(w.w);
+      }
+      if (G == 1 && j_prev >= 0 && j_prev < L.grid.n) {
+        // the working point sits where the last search ran; the fitness query is that point after
+        // the last increment (and pcl::transformPointCloud's rounding)
+        float slack = -1.0f;
+        if (L.margin > 0.0f) {
+          const float mx = qx - w.x, my = qy - w.y, mz = qz - w.z;
+          const float moved = sqrtf(mx * mx + my * my + mz * mz);
+          slack = L.slack[static_cast<size_t>(h) * L.n_src + i] - 2.000002f * moved - 1e-5f * L.grid.h;
+        }
+        if (slack > 0.0f) {
+          const float4 t = L.grid.pts[j_prev];
+          best.d2 = l2_simple(qx, qy, qz, t.x, t.y, t.z);
+          best.idx = __float_as_int(t.w);
+          best.j = j_prev;
+        } else {
+          best = grid_nn_warm(L.grid, qx, qy, qz, j_prev, L.fitness_stop_d2);
+        }
+      } else {
         best = grid_nn<G>(L.grid, qx, qy, qz, L.fitness_stop_d2);
+      }
     }
     if (valid && best.idx >= 0 && lane_in_group == 0 && static_cast<double>(best.d2) <= L.fitness_max_range) {
       acc[0] += static_cast<double>(best.d2);
@@ -449,10 +497,18 @@ int prof_mark(peb_ctx* ctx, int slot) {
 template <int G>
 int launch_one_iteration(peb_ctx* ctx, const IcpLaunch& L, size_t H, int estimator) {
   dim3 grid(L.blocks_per_hyp, static_cast<unsigned>(H));
-  if (estimator == PEB_ESTIMATOR_SVD)
-    PEB_LAUNCH(ctx, (icp_iteration_kernel<G, PEB_ESTIMATOR_SVD>), grid, kIcpThreads, 0, L);
-  else
-    PEB_LAUNCH(ctx, (icp_iteration_kernel<G, PEB_ESTIMATOR_POINT_TO_PLANE_LLS>), grid, kIcpThreads, 0, L);
+  constexpr int S = PEB_ESTIMATOR_SVD, P = PEB_ESTIMATOR_POINT_TO_PLANE_LLS;
+  const bool cert = G == 1 && L.margin > 0.0f;
+  const bool svd = estimator == PEB_ESTIMATOR_SVD;
+#define PEB_ICP_LAUNCH(EST, MB, CERT) PEB_LAUNCH(ctx, (icp_iteration_kernel<G, EST, MB, CERT>), grid, kIcpThreads, 0, L)
+  if (H == 1) {
+    if (cert) { if (svd) PEB_ICP_LAUNCH(S, kMinBlocksSingle, (G == 1)); else PEB_ICP_LAUNCH(P, kMinBlocksSingle, (G == 1)); }
+    else      { if (svd) PEB_ICP_LAUNCH(S, kMinBlocksSingle, false);    else PEB_ICP_LAUNCH(P, kMinBlocksSingle, false); }
+  } else {
+    if (cert) { if (svd) PEB_ICP_LAUNCH(S, kMinBlocksBatch, (G == 1)); else PEB_ICP_LAUNCH(P, kMinBlocksBatch, (G == 1)); }
+    else      { if (svd) PEB_ICP_LAUNCH(S, kMinBlocksBatch, false);    else PEB_ICP_LAUNCH(P, kMinBlocksBatch, false); }
+  }
+#undef PEB_ICP_LAUNCH
   return PEB_OK;
 }
 
@@ -504,9 +560,12 @@ int prepare_launch(peb_ctx* ctx, size_t H, const peb_icp_params* prm, IcpLaunch&
   L.n_src = n;
   const int max_bph = std::max(blocks_for(n, H, ctx->nn_group), blocks_for(n, H, 1));
   PEB_CUDA(ctx, ctx->work.ensure(std::max<size_t>(H * static_cast<size_t>(n), 1) * sizeof(float4)));
+  PEB_CUDA(ctx, ctx->slack.ensure(std::max<size_t>(H * static_cast<size_t>(n), 1) * sizeof(float)));
   PEB_CUDA(ctx, ctx->state.ensure(H * sizeof(IcpState)));
   PEB_CUDA(ctx, ctx->partials.ensure(H * static_cast<size_t>(max_bph) * kAccMax * sizeof(double)));
   L.work = ctx->work.as<float4>();
+  L.slack = ctx->slack.as<float>();
+  L.margin = ctx->cert_margin * L.grid.h;
   L.states = ctx->state.as<IcpState>();
   L.partials = ctx->partials.as<double>();
   L.crit.max_iterations = prm->max_iterations;
@@ -561,6 +620,8 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
   }
   PEB_LAUNCH(ctx, icp_init_kernel, ceil_div(static_cast<long long>(H), 128), 128, 0, L.states, d_guesses,
              static_cast<int>(H));
+  if (L.margin > 0.0f)  // no certificate yet (all-ones = NaN: never > 0)
+    PEB_CUDA(ctx, cudaMemsetAsync(L.slack, 0xFF, std::max<size_t>(H * static_cast<size_t>(n), 1) * sizeof(float), ctx->stream));
   // PCL runs the loop body at least once (do ... while), also for max_iterations <= 1
   const int launches = std::max(prm->max_iterations, 1);
   const int g_cold = ctx->nn_group;

@@ -134,7 +134,8 @@ HC_API void hc_grid_nn(const float* tgt, size_t n, size_t tstride, const float* 
 
 // warm-started search: prev[i] = ORIGINAL index of the candidate handed to query i
 HC_API void hc_grid_nn_warm(const float* tgt, size_t n, size_t tstride, const float* q, size_t nq, size_t qstride,
-                            float occupancy, const int32_t* prev, float limit_d2, int32_t* out_idx, float* out_d2) {
+                            float occupancy, const int32_t* prev, float limit_d2, float margin, int32_t* out_idx,
+                            float* out_d2, float* out_slack) {
   HostGrid g;
   build_grid(tgt, n, tstride / 4, occupancy, 0.0f, g);
   std::vector<int> pos(n, -1);  // original index -> sorted position
@@ -145,9 +146,12 @@ HC_API void hc_grid_nn_warm(const float* tgt, size_t n, size_t tstride, const fl
   }
   for (size_t i = 0; i < nq; ++i) {
     const float* p = q + i * (qstride / 4);
-    NnBest b = grid_nn_warm(g.v, p[0], p[1], p[2], pos[prev[i]], limit_d2);
+    float slack = 0.0f;
+    NnBest b = margin < 0.0f ? grid_nn_warm(g.v, p[0], p[1], p[2], pos[prev[i]], limit_d2)
+                             : grid_nn_warm_cert(g.v, p[0], p[1], p[2], pos[prev[i]], limit_d2, margin, &slack);
     out_idx[i] = b.idx;
     out_d2[i] = b.d2;
+    out_slack[i] = slack;
   }
 }
 

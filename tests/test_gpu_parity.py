@@ -348,6 +348,32 @@ def test_icp_batch_equals_single_and_oracle(pcl, ctx, oracle, scene_small):
         assert abs(g.fitness - r.fitness) <= FIT_RTOL * r.fitness
 
 
+@pytest.mark.parametrize("option,value", [("warm_start", 0), ("cert_margin_x1000", 300), ("nn_group", 8)])
+def test_speed_options_never_change_results(pcl, oracle, scene_small, option, value):
+    """warm start, search-skipping certificates and the cold lane-group width are exactness-preserving:
+    every combination must give the bit-identical answer."""
+    p = scene_small
+    rng = np.random.default_rng(5)
+    guesses = np.stack([synth.perturb_pose(p.gt_pose, rng, 5.0, 0.006) for _ in range(6)])
+    out = []
+    for use in (False, True):
+        c = pcl.Context(0)
+        if use:
+            c.set_int(option, value)
+        icp = pcl.IterativeClosestPoint(c)
+        icp.setInputSource(p.source)
+        icp.setInputTarget(p.target)
+        _set_params(icp, default_params(max_iterations=25, max_corr_dist=0.02, abs_mse_threshold=-1.0))
+        res = icp.alignBatch(guesses)
+        icp.align(p.guess, want_correspondences=True)
+        out.append(([bytes(r.T) + bytes(np.float64(r.fitness)) for r in res], bytes(icp.result.T), icp.result.fitness,
+                    icp.correspondences[0].copy(), icp.correspondences[1].copy()))
+        c.close()
+    a, b = out
+    assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2]
+    assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+
+
 def test_icp_edge_cases_and_errors(pcl, ctx, oracle, c1):
     fresh = pcl.Context(0)
     try:

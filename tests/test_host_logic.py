@@ -21,7 +21,7 @@ def hc():
     L = C.CDLL(str(HOST / "libpe_hostcheck.so"))
     vp, sz = C.c_void_p, C.c_size_t
     L.hc_grid_nn.argtypes = [vp, sz, sz, vp, sz, sz, C.c_float, C.c_float, C.c_float, vp, vp, vp]
-    L.hc_grid_nn_warm.argtypes = [vp, sz, sz, vp, sz, sz, C.c_float, vp, C.c_float, vp, vp]
+    L.hc_grid_nn_warm.argtypes = [vp, sz, sz, vp, sz, sz, C.c_float, vp, C.c_float, C.c_float, vp, vp, vp]
     L.hc_umeyama_pairs.argtypes = [vp, vp, sz, vp]
     L.hc_lls_pairs.argtypes = [vp, vp, vp, sz, vp]
     L.hc_criteria_script.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]
@@ -99,15 +99,17 @@ def test_grid_search_stop_distance_only_cuts_rejected_matches(hc, oracle):
     assert (gd[~acc] > stop).all()  # whatever it returns there is rejected by the caller anyway
 
 
-def grid_nn_warm(hc, tgt, q, prev, occupancy=2.0, limit=np.inf):
+def grid_nn_warm(hc, tgt, q, prev, occupancy=2.0, limit=np.inf, margin=-1.0, want_slack=False):
+    """margin < 0: the plain warm search; >= 0: the certificate-producing variant"""
     tgt = np.ascontiguousarray(tgt, np.float32)
     q = np.ascontiguousarray(q, np.float32)
     prev = np.ascontiguousarray(prev, np.int32)
     idx = np.empty(len(q), np.int32)
     d2 = np.empty(len(q), np.float32)
+    slack = np.empty(len(q), np.float32)
     hc.hc_grid_nn_warm(tgt.ctypes.data, len(tgt), tgt.strides[0], q.ctypes.data, len(q), q.strides[0], occupancy,
-                       prev.ctypes.data, limit, idx.ctypes.data, d2.ctypes.data)
-    return idx, d2
+                       prev.ctypes.data, limit, margin, idx.ctypes.data, d2.ctypes.data, slack.ctypes.data)
+    return (idx, d2, slack) if want_slack else (idx, d2)
 
 
 @pytest.mark.parametrize("occupancy", [0.5, 2.0, 8.0])
@@ -137,6 +139,36 @@ def test_warm_started_search_is_exact_for_any_candidate(hc, oracle, occupancy):
     assert acc.any() and (~acc).any()
     assert np.array_equal(gd[acc], bd[acc]) and np.array_equal(gi[acc], bi[acc])
     assert (gd[~acc] > lim).all()
+
+
+@pytest.mark.parametrize("margin", [0.0, 2e-4, 1e-3])
+def test_search_certificate_is_a_true_lower_bound(hc, oracle, margin):
+    """slack must never exceed the real gap between the runner-up and the winner, and a query moved
+    by less than slack / 2 must keep its nearest neighbour (what lets icp.cu skip searches)."""
+    rng = np.random.default_rng(17)
+    prob = synth.make_c1(4000, seed=18)
+    tgt = prob.target[:, :3].copy()
+    tgt[50:53] = tgt[50]
+    q = np.concatenate([prob.source[:, :3], tgt[50:51], tgt[:100] + np.float32(2e-4)]).astype(np.float32)
+    bi, bd = oracle.nn_bruteforce(tgt, q)
+    for prev in (bi, rng.integers(0, len(tgt), len(bi))):
+        gi, gd, slack = grid_nn_warm(hc, tgt, q, prev, 2.0, np.inf, margin, want_slack=True)
+        assert np.array_equal(gi, bi) and np.array_equal(gd, bd)
+        d = np.linalg.norm(tgt[None, :, :].astype(np.float64) - q[:, None, :].astype(np.float64), axis=2)
+        d[np.arange(len(q)), bi] = np.inf
+        gap = d.min(1) - np.sqrt(bd.astype(np.float64))
+        assert (slack <= np.maximum(gap, 0) + 1e-9).all()
+        assert (slack <= margin + 1e-9).all()
+        if margin > 0:
+            assert (slack > 0).mean() > 0.5          # most queries get a usable certificate
+            assert slack[len(prob.source)] <= 0      # the query on top of the duplicated target point does not
+        # move every certified query by just under slack / 2 in a random direction: same neighbour
+        ok = slack > 0
+        step = rng.normal(size=(ok.sum(), 3))
+        step *= (0.499 * slack[ok] / np.linalg.norm(step, axis=1))[:, None]
+        q2 = (q[ok].astype(np.float64) + step).astype(np.float32)
+        bi2, _ = oracle.nn_bruteforce(tgt, q2)
+        assert np.array_equal(bi2, bi[ok])
 
 
 def test_umeyama_from_sums_matches_oracle(hc, oracle):

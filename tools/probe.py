@@ -49,10 +49,10 @@ def main():
     icp.setInputTarget(prob.target)
     rng = np.random.default_rng(0)
     guesses = np.stack([synth.perturb_pose(prob.gt_pose, rng, 6.0, 0.008) for _ in range(128)])
-    for socc in (1, 8, 32, 128):
-        ctx.set_int("source_sort_occupancy", socc)
-        icp.setInputSource(prob.source)
-        for g in (1, 8):
+    icp.setInputSource(prob.source)
+    for socc in (0, 100, 250, 500, 1000):
+        ctx.set_int("cert_margin_x1000", socc)
+        for g in (1,):
             ctx.set_int("nn_group", g)
             icp.setMaxCorrespondenceDistance(1e9)
             best = 1e9
@@ -61,7 +61,7 @@ def main():
                 icp.align(prob.guess, want_output=False)
                 best = min(best, time.perf_counter() - t0)
             pr = profile(ctx)
-            print(f"src_occ {socc:3d} G={g}: single align wall {1e3 * best:.3f} ms | kernels {pr.sum():.3f} ms, first {pr[0] * 1e3:.1f} us "
+            print(f"margin {socc:4d} G={g}: single align wall {1e3 * best:.3f} ms | kernels {pr.sum():.3f} ms, first {pr[0] * 1e3:.1f} us "
                   f"median {np.median(pr[:-1]) * 1e3:.1f} us, fitness {pr[-1] * 1e3:.1f} us | fit {icp.getFitnessScore():.4e}", flush=True)
             icp.setMaxCorrespondenceDistance(0.02)
             best = 1e9
@@ -71,7 +71,7 @@ def main():
                 best = min(best, time.perf_counter() - t0)
             pr = profile(ctx)
             fit = np.array([r.fitness for r in res])
-            print(f"src_occ {socc:3d} G={g}: batch H=128 iters(ms) {np.round(pr[:6], 2).tolist()} wall {1e3 * best:.2f} ms = {128 / best:.0f} hyp/s | "
+            print(f"margin {socc:4d} G={g}: batch H=128 iters(ms) {np.round(pr[:12], 2).tolist()} wall {1e3 * best:.2f} ms = {128 / best:.0f} hyp/s | "
                   f"median {np.median(pr[:-1]):.3f} ms | fitness median {np.median(fit):.3e}", flush=True)
     # normals
     ne = pcl.NormalEstimation(ctx)
