@@ -202,6 +202,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = pcl.Context(local)
+    for kv in filter(None, os.environ.get("PEB_OPTS", "").split(",")):  # development: library tuning knobs
+        k, v = kv.split("=")
+        ctx.set_int(k, int(v))
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     def downsample(points, leaf):

@@ -158,7 +158,7 @@ PEB_API void peb_ctx_destroy(peb_ctx* ctx) {
   if (!ctx) return;
   DeviceGuard guard(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->d_small, &ctx->d_scratch, &ctx->d_stage, &ctx->tgt_raw, &ctx->tgt_nrm_raw, &ctx->src, &ctx->work, &ctx->slack,
+  DevBuf* bufs[] = {&ctx->d_small, &ctx->d_scratch, &ctx->d_stage, &ctx->tgt_raw, &ctx->tgt_nrm_raw, &ctx->src, &ctx->work, &ctx->slack, &ctx->anchors,
                     &ctx->corr_idx, &ctx->corr_d2, &ctx->partials, &ctx->state, &ctx->trace, &ctx->d_guesses,
                     &ctx->d_results, &ctx->d_aligned, &ctx->vg_in, &ctx->vg_out, &ctx->vg_flags, &ctx->vg_scan,
                     &ctx->vg_starts, &ctx->nrm_in, &ctx->nrm_out, &ctx->nn_q, &ctx->nn_idx, &ctx->nn_d2};
@@ -204,6 +204,14 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
   if (!strcmp(key, "cert_margin_x1000")) {
     if (value < 0 || value > 4000) return fail(ctx, PEB_E_INVALID_ARG, "cert_margin_x1000 out of [0, 4000]");
     ctx->cert_margin = value / 1000.0f;
+    return PEB_OK;
+  }
+  if (!strcmp(key, "seed_guard_x10")) {
+    ctx->seed_guard = value / 10.0f;
+    return PEB_OK;
+  }
+  if (!strcmp(key, "anchor_seed")) {
+    ctx->anchor_seed = value != 0;
     return PEB_OK;
   }
   if (!strcmp(key, "warm_start")) {

@@ -100,6 +100,9 @@ struct peb_ctx {
   int nn_group = 1;             // lanes that share one COLD nearest-neighbour query (1, 2, 4, 8, 16)
   float grid_occupancy = 2.0f;  // wanted mean points per occupied cell of the target grid
   bool warm_start = true;       // iterations >= 1 seed the search with the previous match
+  bool anchor_seed = true;      // iteration 0: one cold search per 32-point patch seeds the patch
+  float seed_guard = 10.0f;     // seeds farther than this many cells from the query are not used
+  peb::DevBuf anchors;          // H x ceil(n / 32) sorted positions
   float cert_margin = 0.0f;     // > 0: warm searches cover this fraction of a cell beyond the match, which
                                 // buys a certificate that lets later iterations skip the search while the
                                 // point has moved less than half of it.  Off by default: on surface scans the

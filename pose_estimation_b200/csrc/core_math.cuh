@@ -178,30 +178,30 @@ PEB_HD float grid_slab_dist(float q, float origin, float h, int c) {
   return fmaxf(fmaxf(lo - q, q - hi) - 0.01f * h, 0.0f);
 }
 
-// Exact 1-NN given one candidate (sorted position j_prev, e.g. last iteration's match): its
-// distance bounds the answer, so only the cells that intersect the ball of that radius around q
-// can hold something closer — usually 1 to 8 cells instead of a 3x3x3 block plus the ring that
-// proves termination.  limit_d2: matches farther than this are rejected by the caller anyway, so
-// the ball never needs to be larger (pass +inf for plain nearest-neighbour semantics).
-// Rows (fixed y, z) whose slab is already farther than the current best are skipped, and the x
-// extent of every row is cut to the part of the ball it can still intersect.
-PEB_HD NnBest grid_nn_warm(const GridView& g, float qx, float qy, float qz, int j_prev, float limit_d2) {
-  NnBest best;
-  {
-    const float4 p = g.pts[j_prev];
-    best.d2 = l2_simple(qx, qy, qz, p.x, p.y, p.z);
+PEB_HD int point_index(const float4& p) {
 #ifdef __CUDA_ARCH__
-    best.idx = __float_as_int(p.w);
+  return __float_as_int(p.w);
 #else
-    memcpy(&best.idx, &p.w, 4);
+  int id;
+  memcpy(&id, &p.w, 4);
+  return id;
 #endif
-    best.j = j_prev;
-  }
-  const float lim = fminf(best.d2, limit_d2);
+}
+
+// ---- ball search: everything closer than the current best ---------------------------------------
+// `best` holds a candidate; any point that beats it lies inside the ball of radius sqrt(best.d2)
+// (capped by limit_d2: matches farther than that are rejected by the caller anyway), so only the
+// cells intersecting that ball are examined.  Rows (fixed y, z) whose slab is farther than the
+// current best are skipped and every row is cut to the chord of the ball; both shrink as better
+// points are found.  All slab / chord tests carry the same conservative margins as the ring
+// search, so the result is exact for any starting candidate.
+
+// (A 4 x 4 x 4 occupancy bitmap that lets a large ball skip its empty bulk was built and measured:
+//  no gain on C2 / C4 — the slab test already rejects empty rows at ~10 instructions each — so the
+//  rows of the ball's bounding box are walked directly.)
+PEB_HD void grid_ball_direct(const GridView& g, float qx, float qy, float qz, float limit_d2, int y0, int y1, int z0,
+                             int z1, NnBest& best) {
   const float pad = 0.001f * g.h;  // >> one ulp of any coordinate (h >= 1e-4 * max |coordinate|)
-  const float R = sqrtf(lim) * 1.0001f + pad;
-  const int y0 = grid_coord(qy - R, g.oy, g.inv_h, g.dy), y1 = grid_coord(qy + R, g.oy, g.inv_h, g.dy);
-  const int z0 = grid_coord(qz - R, g.oz, g.inv_h, g.dz), z1 = grid_coord(qz + R, g.oz, g.inv_h, g.dz);
   for (int z = z0; z <= z1; ++z) {
     const float dz = grid_slab_dist(qz, g.oz, g.h, z);
     for (int y = y0; y <= y1; ++y) {
@@ -215,6 +215,41 @@ PEB_HD NnBest grid_nn_warm(const GridView& g, float qx, float qy, float qz, int 
       grid_scan_range(g, g.cell_start[base + x0], g.cell_start[base + x1 + 1], qx, qy, qz, best);
     }
   }
+}
+
+PEB_HD void grid_ball_search(const GridView& g, float qx, float qy, float qz, float limit_d2, NnBest& best) {
+  const float R = sqrtf(fminf(best.d2, limit_d2)) * 1.0001f + 0.001f * g.h;
+  const int y0 = grid_coord(qy - R, g.oy, g.inv_h, g.dy), y1 = grid_coord(qy + R, g.oy, g.inv_h, g.dy);
+  const int z0 = grid_coord(qz - R, g.oz, g.inv_h, g.dz), z1 = grid_coord(qz + R, g.oz, g.inv_h, g.dz);
+  grid_ball_direct(g, qx, qy, qz, limit_d2, y0, y1, z0, z1, best);
+}
+
+// Exact 1-NN given one candidate (sorted position j_prev, e.g. last iteration's match)
+PEB_HD NnBest grid_nn_warm(const GridView& g, float qx, float qy, float qz, int j_prev, float limit_d2) {
+  NnBest best;
+  const float4 p = g.pts[j_prev];
+  best.d2 = l2_simple(qx, qy, qz, p.x, p.y, p.z);
+  best.idx = point_index(p);
+  best.j = j_prev;
+  grid_ball_search(g, qx, qy, qz, limit_d2, best);
+  return best;
+}
+
+// Exact 1-NN of q given the match (sorted position j_seed) of a NEARBY query q_seed: the seed's
+// match shifted by (q - q_seed) predicts where q's own match lies; the 3 x 3 x 3 block around
+// that prediction is probed first so that the ball to verify is as small as it can be.
+PEB_HD NnBest grid_nn_seeded(const GridView& g, float qx, float qy, float qz, int j_seed, float sx, float sy, float sz,
+                             float limit_d2) {
+  NnBest best;
+  const float4 t = g.pts[j_seed];
+  best.d2 = l2_simple(qx, qy, qz, t.x, t.y, t.z);
+  best.idx = point_index(t);
+  best.j = j_seed;
+  const int cx = grid_coord(t.x + (qx - sx), g.ox, g.inv_h, g.dx);
+  const int cy = grid_coord(t.y + (qy - sy), g.oy, g.inv_h, g.dy);
+  const int cz = grid_coord(t.z + (qz - sz), g.oz, g.inv_h, g.dz);
+  grid_scan_ring(g, qx, qy, qz, cx, cy, cz, 1, true, 0, 1, best);
+  grid_ball_search(g, qx, qy, qz, limit_d2, best);
   return best;
 }
 

@@ -41,6 +41,9 @@ struct IcpLaunch {
   const float4* src;     // n_src FINITE source points in patch order, .w = original index
   float4* work;          // H x n_src working clouds (same order); .w = sorted position of the last match
   float* slack;          // H x n_src: how far the point may still move before its match must be searched again
+  const int* anchors;    // nullable, H x n_anchor: match (sorted position) of the first point of every 32-point patch
+  int n_anchor;
+  float seed_guard2;     // (cells)^2: an anchor farther than this from the query is not used as a seed
   IcpState* states;      // H
   double* partials;      // H x blocks_per_hyp x kAccMax
   int32_t* corr_idx;     // nullable, indexed by ORIGINAL source index (single align only)
@@ -145,6 +148,34 @@ __device__ __forceinline__ void reduce_partials(const double* __restrict__ part,
   __syncthreads();
 }
 
+// Iteration 0 has no previous match to start from.  The source is stored in compact 32-point
+// patches (common.cuh), so one cold ring search per patch — this kernel, one thread per patch and
+// hypothesis, all lanes busy — gives every point of the patch a nearby seed; the iteration kernel
+// then runs grid_nn_seeded for all points instead of 32 divergent ring searches per warp.
+__global__ void __launch_bounds__(128) icp_anchor_kernel(const IcpLaunch L, int* __restrict__ anchors) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int h = blockIdx.y;
+  if (a >= L.n_anchor) return;
+  const IcpState* st = L.states + h;
+  float T[16];
+  bool apply = false;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    T[i] = __ldcg(&st->final_t.m[i]);
+    if (T[i] != ((i % 5 == 0) ? 1.0f : 0.0f)) apply = true;
+  }
+  float4 p = L.src[32 * a];
+  if (apply) {
+    float ox, oy, oz;
+    transform_icp(T, p.x, p.y, p.z, ox, oy, oz);
+    p.x = ox;
+    p.y = oy;
+    p.z = oz;
+  }
+  const NnBest best = grid_nn<1>(L.grid, p.x, p.y, p.z, L.stop_d2);
+  anchors[static_cast<size_t>(h) * L.n_anchor + a] = best.j;
+}
+
 // The solve runs once per launch in one thread; keeping it out of line keeps its registers and
 // local arrays out of the per-query loop's allocation.
 __device__ __noinline__ void finish_iteration(IcpState* st, const IcpCriteria* cr, const double* acc, Mat4* trace,
@@ -244,7 +275,25 @@ __global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_kernel(const Ic
           best = grid_nn_warm(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2);
         }
       } else {
-        best = grid_nn<G>(L.grid, p.x, p.y, p.z, L.stop_d2);
+        int j_seed = -1;
+        if (G == 1 && first && L.anchors) j_seed = L.anchors[static_cast<size_t>(h) * L.n_anchor + (i >> 5)];
+        if (G == 1 && j_seed >= 0) {
+          // the patch's anchor query, recomputed (same arithmetic as above): where the seed was found from
+          float4 a = L.src[i & ~31];
+          if (apply) {
+            float ox, oy, oz;
+            transform_icp(T, a.x, a.y, a.z, ox, oy, oz);
+            a.x = ox;
+            a.y = oy;
+            a.z = oz;
+          }
+          // a patch that straddles the end of a row of the source grid holds points from two
+          // places: a seed from the other place would only blow the ball up
+          const float ax = p.x - a.x, ay = p.y - a.y, az = p.z - a.z;
+          if (ax * ax + ay * ay + az * az > L.seed_guard2 * L.grid.h * L.grid.h) j_seed = -1;
+          if (j_seed >= 0) best = grid_nn_seeded(L.grid, p.x, p.y, p.z, j_seed, a.x, a.y, a.z, L.stop_d2);
+        }
+        if (!(G == 1 && j_seed >= 0)) best = grid_nn<G>(L.grid, p.x, p.y, p.z, L.stop_d2);
         if (CERT && lane_in_group == 0) *sl = -1.0f;
       }
     }
@@ -556,6 +605,7 @@ namespace {
 int prepare_launch(peb_ctx* ctx, size_t H, const peb_icp_params* prm, IcpLaunch& L) {
   const int n = ctx->n_src_sorted;
   L.grid = ctx->tgt_grid.view;
+  L.seed_guard2 = ctx->seed_guard * ctx->seed_guard;
   L.src = ctx->src_grid.view.pts;
   L.n_src = n;
   const int max_bph = std::max(blocks_for(n, H, ctx->nn_group), blocks_for(n, H, 1));
@@ -629,6 +679,16 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
   IcpLaunch Lc = L, Lw = L;
   Lc.blocks_per_hyp = blocks_for(n, H, g_cold);
   Lc.warm = 0;
+  // (a single align has too few patches to fill the machine with anchor searches: their latency
+  //  would exceed what the seeds save; its cold launch keeps the plain ring search)
+  if (ctx->warm_start && ctx->anchor_seed && g_cold == 1 && n >= 64 && H * static_cast<size_t>(n) >= (1u << 20)) {
+    const int n_anchor = ceil_div(n, 32);
+    PEB_CUDA(ctx, ctx->anchors.ensure(H * static_cast<size_t>(n_anchor) * sizeof(int)));
+    Lc.n_anchor = n_anchor;
+    dim3 agrid(ceil_div(n_anchor, 128), static_cast<unsigned>(H));
+    PEB_LAUNCH(ctx, icp_anchor_kernel, agrid, 128, 0, Lc, ctx->anchors.as<int>());
+    Lc.anchors = ctx->anchors.as<int>();
+  }
   Lw.blocks_per_hyp = blocks_for(n, H, g_warm);
   Lw.warm = ctx->warm_start ? 1 : 0;
   ctx->prof_launches = 0;

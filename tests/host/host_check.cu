@@ -16,6 +16,7 @@ namespace {
 struct HostGrid {
   std::vector<float4> pts;
   std::vector<uint32_t> cell_start;
+
   GridView v{};
 };
 
@@ -152,6 +153,24 @@ HC_API void hc_grid_nn_warm(const float* tgt, size_t n, size_t tstride, const fl
     out_idx[i] = b.idx;
     out_d2[i] = b.d2;
     out_slack[i] = slack;
+  }
+}
+
+// seeded search: query i is seeded with the exact match of seed query s[i] (found by the ring search)
+HC_API void hc_grid_nn_seeded(const float* tgt, size_t n, size_t tstride, const float* q, const float* sq, size_t nq,
+                              float occupancy, float limit_d2, int32_t* out_idx, float* out_d2) {
+  HostGrid g;
+  build_grid(tgt, n, tstride / 4, occupancy, 0.0f, g);
+  for (size_t i = 0; i < nq; ++i) {
+    int rings;
+    NnBest sb = grid_nn_host(g.v, sq[3 * i], sq[3 * i + 1], sq[3 * i + 2], limit_d2, &rings);
+    NnBest b;
+    if (sb.j >= 0)
+      b = grid_nn_seeded(g.v, q[3 * i], q[3 * i + 1], q[3 * i + 2], sb.j, sq[3 * i], sq[3 * i + 1], sq[3 * i + 2], limit_d2);
+    else
+      b = grid_nn_host(g.v, q[3 * i], q[3 * i + 1], q[3 * i + 2], limit_d2, &rings);
+    out_idx[i] = b.idx;
+    out_d2[i] = b.d2;
   }
 }
 

@@ -22,6 +22,7 @@ def hc():
     vp, sz = C.c_void_p, C.c_size_t
     L.hc_grid_nn.argtypes = [vp, sz, sz, vp, sz, sz, C.c_float, C.c_float, C.c_float, vp, vp, vp]
     L.hc_grid_nn_warm.argtypes = [vp, sz, sz, vp, sz, sz, C.c_float, vp, C.c_float, C.c_float, vp, vp, vp]
+    L.hc_grid_nn_seeded.argtypes = [vp, sz, sz, vp, vp, sz, C.c_float, C.c_float, vp, vp]
     L.hc_umeyama_pairs.argtypes = [vp, vp, sz, vp]
     L.hc_lls_pairs.argtypes = [vp, vp, vp, sz, vp]
     L.hc_criteria_script.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]
@@ -139,6 +140,32 @@ def test_warm_started_search_is_exact_for_any_candidate(hc, oracle, occupancy):
     assert acc.any() and (~acc).any()
     assert np.array_equal(gd[acc], bd[acc]) and np.array_equal(gi[acc], bi[acc])
     assert (gd[~acc] > lim).all()
+
+
+@pytest.mark.parametrize("occupancy", [0.5, 2.0, 8.0])
+def test_seeded_and_large_ball_searches_are_exact(hc, oracle, occupancy):
+    """Far queries (balls spanning dozens of cells) seeded with the match of
+    a neighbouring query, and random far seeds through the plain warm search."""
+    rng = np.random.default_rng(19)
+    prob = synth.make_c1(6000, seed=20)
+    tgt = np.ascontiguousarray(prob.target[:, :3])
+    n = 1500
+    base = prob.source[:n, :3]
+    offsets = rng.normal(size=(n, 3)).astype(np.float32)
+    offsets *= (rng.uniform(0.0, 0.02, n) / np.linalg.norm(offsets, axis=1))[:, None].astype(np.float32)
+    q = np.ascontiguousarray(base + offsets)                                  # up to 20 mm off the surface
+    sq = np.ascontiguousarray(q + rng.normal(0, 1.5e-3, q.shape).astype(np.float32))   # the "anchor" of each query
+    bi, bd = oracle.nn_bruteforce(tgt, q)
+    idx = np.empty(n, np.int32)
+    d2 = np.empty(n, np.float32)
+    for limit in (np.inf, 4e-4):
+        hc.hc_grid_nn_seeded(tgt.ctypes.data, len(tgt), tgt.strides[0], q.ctypes.data, sq.ctypes.data, n, occupancy,
+                             limit, idx.ctypes.data, d2.ctypes.data)
+        acc = bd <= limit
+        assert np.array_equal(d2[acc], bd[acc]) and np.array_equal(idx[acc], bi[acc])
+        assert (d2[~acc] > limit).all()
+    gi, gd = grid_nn_warm(hc, tgt, q, rng.integers(0, len(tgt), n), occupancy)   # arbitrary seeds: huge balls
+    assert np.array_equal(gd, bd) and np.array_equal(gi, bi)
 
 
 @pytest.mark.parametrize("margin", [0.0, 2e-4, 1e-3])

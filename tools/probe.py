@@ -50,29 +50,19 @@ def main():
     rng = np.random.default_rng(0)
     guesses = np.stack([synth.perturb_pose(prob.gt_pose, rng, 6.0, 0.008) for _ in range(128)])
     icp.setInputSource(prob.source)
-    for socc in (0, 100, 250, 500, 1000):
-        ctx.set_int("cert_margin_x1000", socc)
-        for g in (1,):
-            ctx.set_int("nn_group", g)
-            icp.setMaxCorrespondenceDistance(1e9)
-            best = 1e9
-            for rep in range(5):
-                t0 = time.perf_counter()
-                icp.align(prob.guess, want_output=False)
-                best = min(best, time.perf_counter() - t0)
-            pr = profile(ctx)
-            print(f"margin {socc:4d} G={g}: single align wall {1e3 * best:.3f} ms | kernels {pr.sum():.3f} ms, first {pr[0] * 1e3:.1f} us "
-                  f"median {np.median(pr[:-1]) * 1e3:.1f} us, fitness {pr[-1] * 1e3:.1f} us | fit {icp.getFitnessScore():.4e}", flush=True)
-            icp.setMaxCorrespondenceDistance(0.02)
-            best = 1e9
-            for rep in range(3):
-                t0 = time.perf_counter()
-                res = icp.alignBatch(guesses)
-                best = min(best, time.perf_counter() - t0)
-            pr = profile(ctx)
-            fit = np.array([r.fitness for r in res])
-            print(f"margin {socc:4d} G={g}: batch H=128 iters(ms) {np.round(pr[:12], 2).tolist()} wall {1e3 * best:.2f} ms = {128 / best:.0f} hyp/s | "
-                  f"median {np.median(pr[:-1]):.3f} ms | fitness median {np.median(fit):.3e}", flush=True)
+    icp.setMaxCorrespondenceDistance(0.02)
+    for rows, guard in ((25, 40), (25, 60), (25, 100), (81, 60), (225, 60), (1000000, 60), (1000000, 100), (25, 0)):
+        ctx.set_int("ball_direct_rows", rows)
+        ctx.set_int("seed_guard_x10", guard)
+        best = 1e9
+        for rep in range(3):
+            t0 = time.perf_counter()
+            res = icp.alignBatch(guesses)
+            best = min(best, time.perf_counter() - t0)
+        pr = profile(ctx)
+        fit = np.array([r.fitness for r in res])
+        print(f"rows {rows:7d} guard {guard / 10}: batch H=128 iters(ms) {np.round(pr[:8], 2).tolist()} wall {1e3 * best:.2f} ms = {128 / best:.0f} hyp/s | "
+              f"median {np.median(pr[:-1]):.3f} ms | fitness median {np.median(fit):.3e}", flush=True)
     # normals
     ne = pcl.NormalEstimation(ctx)
     ne.setInputCloud(prob.target)
