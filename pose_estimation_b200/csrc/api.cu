@@ -158,7 +158,7 @@ PEB_API void peb_ctx_destroy(peb_ctx* ctx) {
   if (!ctx) return;
   DeviceGuard guard(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->d_small, &ctx->d_scratch, &ctx->d_stage, &ctx->tgt_raw, &ctx->tgt_nrm_raw, &ctx->src, &ctx->work, &ctx->slack, &ctx->anchors,
+  DevBuf* bufs[] = {&ctx->d_small, &ctx->d_scratch, &ctx->d_stage, &ctx->tgt_raw, &ctx->tgt_nrm_raw, &ctx->src, &ctx->work, &ctx->slack, &ctx->anchors, &ctx->dbg,
                     &ctx->corr_idx, &ctx->corr_d2, &ctx->partials, &ctx->state, &ctx->trace, &ctx->d_guesses,
                     &ctx->d_results, &ctx->d_aligned, &ctx->vg_in, &ctx->vg_out, &ctx->vg_flags, &ctx->vg_scan,
                     &ctx->vg_starts, &ctx->nrm_in, &ctx->nrm_out, &ctx->nn_q, &ctx->nn_idx, &ctx->nn_d2};
@@ -208,6 +208,14 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
   }
   if (!strcmp(key, "seed_guard_x10")) {
     ctx->seed_guard = value / 10.0f;
+    return PEB_OK;
+  }
+  if (!strcmp(key, "pdl")) {
+    ctx->use_pdl = value != 0;
+    return PEB_OK;
+  }
+  if (!strcmp(key, "debug_timers")) {
+    ctx->debug_timers = value != 0;
     return PEB_OK;
   }
   if (!strcmp(key, "anchor_seed")) {
@@ -487,6 +495,20 @@ PEB_API int peb_profile_read(peb_ctx* ctx, float* out_ms, size_t cap, size_t* ou
   *out_n = cnt;
   for (size_t i = 0; i < cnt && out_ms; ++i)
     PEB_CUDA(ctx, cudaEventElapsedTime(&out_ms[i], ctx->prof_events[2 * i], ctx->prof_events[2 * i + 1]));
+  return PEB_OK;
+}
+
+// development aid (not in the public header): copies the phase time stamps of the last align
+extern "C" PEB_API int peb_debug_timers_read(peb_ctx* ctx, unsigned long long* out, size_t cap_launches, size_t* out_n) {
+  if (!ctx || !out_n) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  size_t n = static_cast<size_t>(ctx->dbg_launches);
+  if (n > cap_launches) n = cap_launches;
+  *out_n = n;
+  if (n) {
+    PEB_CUDA(ctx, cudaMemcpyAsync(out, ctx->dbg.p, n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    PEB_TRY(sync(ctx));
+  }
   return PEB_OK;
 }
 

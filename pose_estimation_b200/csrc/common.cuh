@@ -102,6 +102,10 @@ struct peb_ctx {
   bool warm_start = true;       // iterations >= 1 seed the search with the previous match
   bool anchor_seed = true;      // iteration 0: one cold search per 32-point patch seeds the patch
   float seed_guard = 10.0f;     // seeds farther than this many cells from the query are not used
+  bool use_pdl = true;          // programmatic dependent launch between the ICP launches of an align
+  bool debug_timers = false;    // development: %globaltimer stamps of the phases of every iteration launch
+  peb::DevBuf dbg;
+  int dbg_launches = 0;
   peb::DevBuf anchors;          // H x ceil(n / 32) sorted positions
   float cert_margin = 0.0f;     // > 0: warm searches cover this fraction of a cell beyond the match, which
                                 // buys a certificate that lets later iterations skip the search while the
@@ -183,6 +187,25 @@ int fail(peb_ctx* ctx, int code, const char* fmt, ...);
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);           \
     (ctx)->launches++;                                                         \
     PEB_CUDA((ctx), cudaGetLastError());                                       \
+  } while (0)
+
+// Launch with programmatic dependent launch (PDL): the kernel may be scheduled while the previous
+// kernel of the stream is still draining; it must execute pdl_wait() before it touches anything the
+// previous kernel wrote.  Hides the ~3 us launch gap between the dependent ICP iteration launches.
+#define PEB_LAUNCH_PDL(ctx, kernel, grid_, block_, ...)                                   \
+  do {                                                                                    \
+    cudaLaunchConfig_t _cfg = {};                                                         \
+    _cfg.gridDim = (grid_);                                                               \
+    _cfg.blockDim = (block_);                                                             \
+    _cfg.dynamicSmemBytes = 0;                                                            \
+    _cfg.stream = (ctx)->stream;                                                          \
+    cudaLaunchAttribute _attr[1];                                                         \
+    _attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                     \
+    _attr[0].val.programmaticStreamSerializationAllowed = (ctx)->use_pdl ? 1 : 0;         \
+    _cfg.attrs = _attr;                                                                   \
+    _cfg.numAttrs = 1;                                                                    \
+    (ctx)->launches++;                                                                    \
+    PEB_CUDA((ctx), cudaLaunchKernelEx(&_cfg, kernel, __VA_ARGS__));                      \
   } while (0)
 
 static inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }

@@ -349,20 +349,25 @@ struct Rot2 {
   double c, s;
 };
 
-PEB_HD void rot_left(double* W, int p, int q, Rot2 j) {
+// All indices below are compile-time constants (templates, unrolled loops) so that W, U, V live
+// in registers: the solve runs in ONE thread at the end of every iteration launch and sits on the
+// critical path of a single align (measured 10 us per iteration with indexed local arrays).
+template <int P, int Q>
+PEB_HD void rot_left(double (&W)[9], Rot2 j) {
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    double xi = W[p * 3 + i], yi = W[q * 3 + i];
-    W[p * 3 + i] = j.c * xi + j.s * yi;
-    W[q * 3 + i] = -j.s * xi + j.c * yi;
+    const double xi = W[P * 3 + i], yi = W[Q * 3 + i];
+    W[P * 3 + i] = j.c * xi + j.s * yi;
+    W[Q * 3 + i] = -j.s * xi + j.c * yi;
   }
 }
-PEB_HD void rot_right(double* W, int p, int q, Rot2 j) {
+template <int P, int Q>
+PEB_HD void rot_right(double (&W)[9], Rot2 j) {
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    double xi = W[i * 3 + p], yi = W[i * 3 + q];
-    W[i * 3 + p] = j.c * xi - j.s * yi;
-    W[i * 3 + q] = j.s * xi + j.c * yi;
+    const double xi = W[i * 3 + P], yi = W[i * 3 + Q];
+    W[i * 3 + P] = j.c * xi - j.s * yi;
+    W[i * 3 + Q] = j.s * xi + j.c * yi;
   }
 }
 
@@ -370,13 +375,76 @@ PEB_HD double det3(const double* a) {
   return a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
 }
 
-// A (row-major) = U diag(sv) V^T, sv descending
-PEB_HD void svd3(const double* A, double* U, double* sv, double* V) {
+// one (p, q) step of a two-sided Jacobi sweep ([EIGEN] JacobiSVD + real_2x2_jacobi_svd)
+template <int P, int Q>
+PEB_HD void jacobi_pair(double (&W)[9], double (&U)[9], double (&V)[9], double& maxDiag, bool& finished) {
   const double precision = 2.0 * DBL_EPSILON;
+  const double thr = fmax(DBL_MIN, precision * maxDiag);
+  if (!(fabs(W[P * 3 + Q]) > thr || fabs(W[Q * 3 + P]) > thr)) return;
+  finished = false;
+  const double m00 = W[P * 3 + P], m01 = W[P * 3 + Q], m10 = W[Q * 3 + P], m11 = W[Q * 3 + Q];
+  // Same rotations as Eigen's real_2x2_jacobi_svd / makeJacobi, written with reciprocal square
+  // roots instead of their divide-sqrt-divide chains: the solve is one thread's serial dependency
+  // chain, and every double division or square root in it costs ~100 cycles of latency.
+  Rot2 r1;
+  const double t = m00 + m11, d = m10 - m01;
+  if (fabs(d) < DBL_MIN) {
+    r1.s = 0.0;
+    r1.c = 1.0;
+  } else {
+    // u = t / d;  s = 1 / sqrt(1 + u^2) = |d| / hypot(t, d);  c = u * s = t * sign(d) / hypot(t, d)
+    const double inv = rsqrt(t * t + d * d);
+    r1.s = fabs(d) * inv;
+    r1.c = copysign(t, t * d) * inv;
+  }
+  const double n00 = r1.c * m00 + r1.s * m10, n01 = r1.c * m01 + r1.s * m11, n11 = -r1.s * m01 + r1.c * m11;
+  Rot2 jr;
+  const double deno = 2.0 * fabs(n01);
+  if (deno < DBL_MIN) {
+    jr.c = 1.0;
+    jr.s = 0.0;
+  } else {
+    // tan(theta) = sign(tau) / (|tau| + sqrt(tau^2 + 1)),  tau = (n00 - n11) / (2 |n01|)
+    // multiply through by 2 |n01|:  tan(theta) = sign(a) * b / (|a| + hypot(a, b)),  a = n00 - n11, b = 2 |n01|
+    const double a = n00 - n11;
+    const double hyp = sqrt(a * a + deno * deno);
+    const double tt = copysign(deno, a > 0.0 ? 1.0 : -1.0) / (fabs(a) + hyp);
+    const double nn = rsqrt(tt * tt + 1.0);
+    jr.s = -copysign(fabs(tt) * nn, tt) * copysign(1.0, n01);
+    jr.c = nn;
+  }
+  const Rot2 jl{r1.c * jr.c + r1.s * jr.s, r1.s * jr.c - r1.c * jr.s};
+  rot_left<P, Q>(W, jl);
+  rot_right<P, Q>(U, Rot2{jl.c, -jl.s});
+  rot_right<P, Q>(W, jr);
+  rot_right<P, Q>(V, jr);
+  maxDiag = fmax(maxDiag, fmax(fabs(W[P * 3 + P]), fabs(W[Q * 3 + Q])));
+}
+
+template <int I, int J>
+PEB_HD void swap_columns(double (&sv)[3], double (&U)[9], double (&V)[9]) {
+  const double ts = sv[I];
+  sv[I] = sv[J];
+  sv[J] = ts;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const double tu = U[r * 3 + I];
+    U[r * 3 + I] = U[r * 3 + J];
+    U[r * 3 + J] = tu;
+    const double tv = V[r * 3 + I];
+    V[r * 3 + I] = V[r * 3 + J];
+    V[r * 3 + J] = tv;
+  }
+}
+
+// A (row-major) = U diag(sv) V^T, sv descending
+PEB_HD void svd3(const double (&A)[9], double (&U)[9], double (&sv)[3], double (&V)[9]) {
   double scale = 0.0;
+#pragma unroll
   for (int i = 0; i < 9; ++i) scale = fmax(scale, fabs(A[i]));
   if (scale == 0.0) scale = 1.0;
   double W[9];
+#pragma unroll
   for (int i = 0; i < 9; ++i) {
     W[i] = A[i] / scale;
     U[i] = V[i] = (i % 4 == 0) ? 1.0 : 0.0;
@@ -385,72 +453,98 @@ PEB_HD void svd3(const double* A, double* U, double* sv, double* V) {
   bool finished = false;
   for (int sweep = 0; sweep < 64 && !finished; ++sweep) {
     finished = true;
-    for (int p = 1; p < 3; ++p)
-      for (int q = 0; q < p; ++q) {
-        double thr = fmax(DBL_MIN, precision * maxDiag);
-        if (fabs(W[p * 3 + q]) > thr || fabs(W[q * 3 + p]) > thr) {
-          finished = false;
-          double m00 = W[p * 3 + p], m01 = W[p * 3 + q], m10 = W[q * 3 + p], m11 = W[q * 3 + q];
-          Rot2 r1;
-          double t = m00 + m11, d = m10 - m01;
-          if (fabs(d) < DBL_MIN) {
-            r1.s = 0.0;
-            r1.c = 1.0;
-          } else {
-            double u = t / d;
-            double tmp = sqrt(1.0 + u * u);
-            r1.s = 1.0 / tmp;
-            r1.c = u / tmp;
-          }
-          double n00 = r1.c * m00 + r1.s * m10, n01 = r1.c * m01 + r1.s * m11, n11 = -r1.s * m01 + r1.c * m11;
-          Rot2 jr;
-          double deno = 2.0 * fabs(n01);
-          if (deno < DBL_MIN) {
-            jr.c = 1.0;
-            jr.s = 0.0;
-          } else {
-            double tau = (n00 - n11) / deno;
-            double w = sqrt(tau * tau + 1.0);
-            double tt = (tau > 0.0) ? 1.0 / (tau + w) : 1.0 / (tau - w);
-            double sign_t = tt > 0.0 ? 1.0 : -1.0;
-            double nn = 1.0 / sqrt(tt * tt + 1.0);
-            jr.s = -sign_t * (n01 / fabs(n01)) * fabs(tt) * nn;
-            jr.c = nn;
-          }
-          Rot2 jl{r1.c * jr.c + r1.s * jr.s, r1.s * jr.c - r1.c * jr.s};
-          rot_left(W, p, q, jl);
-          rot_right(U, p, q, Rot2{jl.c, -jl.s});
-          rot_right(W, p, q, jr);
-          rot_right(V, p, q, jr);
-          maxDiag = fmax(maxDiag, fmax(fabs(W[p * 3 + p]), fabs(W[q * 3 + q])));
-        }
-      }
+    jacobi_pair<1, 0>(W, U, V, maxDiag, finished);  // (p, q) in JacobiSVD's order: (1,0) (2,0) (2,1)
+    jacobi_pair<2, 0>(W, U, V, maxDiag, finished);
+    jacobi_pair<2, 1>(W, U, V, maxDiag, finished);
   }
+#pragma unroll
   for (int i = 0; i < 3; ++i) {
-    double a = W[i * 3 + i];
+    const double a = W[i * 3 + i];
     sv[i] = fabs(a) * scale;
-    if (a < 0.0)
+    if (a < 0.0) {
+#pragma unroll
       for (int r = 0; r < 3; ++r) U[r * 3 + i] = -U[r * 3 + i];
-  }
-  for (int i = 0; i < 3; ++i) {
-    int pos = i;
-    for (int k = i + 1; k < 3; ++k)
-      if (sv[k] > sv[pos]) pos = k;
-    if (sv[pos] == 0.0) break;
-    if (pos != i) {
-      double ts = sv[i];
-      sv[i] = sv[pos];
-      sv[pos] = ts;
-      for (int r = 0; r < 3; ++r) {
-        double tu = U[r * 3 + i];
-        U[r * 3 + i] = U[r * 3 + pos];
-        U[r * 3 + pos] = tu;
-        double tv = V[r * 3 + i];
-        V[r * 3 + i] = V[r * 3 + pos];
-        V[r * 3 + pos] = tv;
-      }
     }
   }
+  // selection sort, descending, first maximum wins (Eigen's order of swaps), with constant indices
+  {
+    const bool one = sv[1] > sv[0];
+    const double m01 = one ? sv[1] : sv[0];
+    const bool two = sv[2] > m01;
+    if ((two ? sv[2] : m01) == 0.0) return;
+    if (two)
+      swap_columns<0, 2>(sv, U, V);
+    else if (one)
+      swap_columns<0, 1>(sv, U, V);
+    if (sv[2] > sv[1]) swap_columns<1, 2>(sv, U, V);
+  }
+}
+
+// Orthogonal polar factor of A by scaled Newton iterations, X <- (g X + X^-T / g) / 2 (Higham).
+// For det(A) > 0 it equals U V^T of the SVD — umeyama's rotation in the generic case — to double
+// precision, at a fraction of the latency of the Jacobi sweeps: ~7 iterations of mostly independent
+// multiplies with 3 dependent divide / square-root steps each, against ~12 plane rotations with 5.
+// Returns false (caller takes the SVD path) for reflections, rank deficiency or no convergence.
+PEB_HD bool polar_rotation3(const double (&A)[9], double (&R)[9]) {
+  double n2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) n2 += A[i] * A[i];
+  if (!(n2 > 0.0)) return false;
+  const double inv_norm = rsqrt(n2);
+  double X[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) X[i] = A[i] * inv_norm;
+  if (!(det3(X) > 1e-15)) return false;  // |X|_F = 1: det = s1 s2 s3 <= 0.2; tiny or negative -> SVD path
+  bool scaled = true;
+  for (int it = 0; it < 16; ++it) {
+    double Cf[9];  // cofactors: X^-T = Cf / det
+    Cf[0] = X[4] * X[8] - X[5] * X[7];
+    Cf[1] = X[5] * X[6] - X[3] * X[8];
+    Cf[2] = X[3] * X[7] - X[4] * X[6];
+    Cf[3] = X[2] * X[7] - X[1] * X[8];
+    Cf[4] = X[0] * X[8] - X[2] * X[6];
+    Cf[5] = X[1] * X[6] - X[0] * X[7];
+    Cf[6] = X[1] * X[5] - X[2] * X[4];
+    Cf[7] = X[2] * X[3] - X[0] * X[5];
+    Cf[8] = X[0] * X[4] - X[1] * X[3];
+    const double det = X[0] * Cf[0] + X[1] * Cf[1] + X[2] * Cf[2];
+    if (!(det > 0.0)) return false;
+    double a, b;  // X <- a X + b Cf
+    if (scaled) {
+      // Any positive scaling keeps the iteration on course; only its speed depends on g.  The
+      // scaled steps therefore take g, 1/g and 1/det from single-precision MUFU operations
+      // (~20 cycles each) instead of double divisions and square roots (~200 cycles each, in series).
+      float nx2 = 0.0f, nc2 = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        nx2 += static_cast<float>(X[i]) * static_cast<float>(X[i]);
+        nc2 += static_cast<float>(Cf[i]) * static_cast<float>(Cf[i]);
+      }
+      const float fdet = static_cast<float>(det);
+      // g^4 = |X^-T|_F^2 / |X|_F^2 = nc2 / (det^2 nx2)
+      const float g2 = sqrtf(nc2 / (fdet * fdet * nx2));
+      const float g = sqrtf(g2);
+      a = 0.5 * static_cast<double>(g);
+      b = static_cast<double>(0.5f / (g * fdet));
+    } else {
+      a = 0.5;
+      b = 0.5 / det;
+    }
+    double delta = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const double xn = a * X[i] + b * Cf[i];
+      delta = fmax(delta, fabs(xn - X[i]));
+      X[i] = xn;
+    }
+    if (delta < 1e-2) scaled = false;  // close to orthogonal: plain (exact) Newton converges quadratically
+    if (delta < 1e-15) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) R[i] = X[i];
+      return true;
+    }
+  }
+  return false;
 }
 
 // Accumulator layouts of the two estimators (doubles):
@@ -460,25 +554,15 @@ constexpr int kAccSvd = 17;
 constexpr int kAccLls = 29;
 constexpr int kAccMax = 32;
 
-// [PCL] common/impl/eigen.hpp : pcl::umeyama (no scaling) from the moment sums, in double.
-// PCL runs it in float on demeaned 3 x n matrices; sums of the raw moments in double carry
-// ~1e-13 relative error, far below PCL's own float noise (SURVEY.md H2b).
-PEB_HD Mat4 umeyama_from_sums(const double* acc) {
-  const double n = acc[0];
-  const double inv_n = 1.0 / n;
-  double sm[3], tm[3];
-  for (int i = 0; i < 3; ++i) {
-    sm[i] = acc[1 + i] * inv_n;
-    tm[i] = acc[4 + i] * inv_n;
-  }
-  double sigma[9];
-  for (int r = 0; r < 3; ++r)
-    for (int c = 0; c < 3; ++c) sigma[r * 3 + c] = acc[7 + r * 3 + c] * inv_n - tm[r] * sm[c];
+// umeyama's rotation through the SVD, with its reflection and rank-2 cases
+// ([PCL] common/impl/eigen.hpp : pcl::umeyama): the path for everything polar_rotation3 declines.
+PEB_HD void umeyama_rotation_svd(const double (&sigma)[9], double (&R)[9]) {
   double U[9], V[9], sv[3];
   svd3(sigma, U, sv, V);
   double S[3] = {1.0, 1.0, 1.0};
   if (det3(sigma) < 0.0) S[2] = -1.0;
   int rank = 0;
+#pragma unroll
   for (int i = 0; i < 3; ++i)
     if (!(fabs(sv[i]) <= fabs(sv[0]) * 1e-12)) ++rank;
   if (rank == 2) {
@@ -488,16 +572,24 @@ PEB_HD Mat4 umeyama_from_sums(const double* acc) {
       S[2] = -1.0;
     }
   }
-  double R[9];
+#pragma unroll
   for (int r = 0; r < 3; ++r)
+#pragma unroll
     for (int c = 0; c < 3; ++c) {
       double a = 0.0;
+#pragma unroll
       for (int k = 0; k < 3; ++k) a += U[r * 3 + k] * S[k] * V[c * 3 + k];
       R[r * 3 + c] = a;
     }
+}
+
+// T = [R | dst_mean - R src_mean], cast to float like umeyama's Matrix4f result
+PEB_HD Mat4 umeyama_pack(const double (&R)[9], const double (&sm)[3], const double (&tm)[3]) {
   Mat4 T = mat4_identity();
+#pragma unroll
   for (int r = 0; r < 3; ++r) {
     double a = 0.0;
+#pragma unroll
     for (int c = 0; c < 3; ++c) {
       T.m[c * 4 + r] = static_cast<float>(R[r * 3 + c]);
       a += R[r * 3 + c] * sm[c];
@@ -505,6 +597,28 @@ PEB_HD Mat4 umeyama_from_sums(const double* acc) {
     T.m[12 + r] = static_cast<float>(tm[r] - a);
   }
   return T;
+}
+
+// [PCL] common/impl/eigen.hpp : pcl::umeyama (no scaling) from the moment sums, in double.
+// PCL runs it in float on demeaned 3 x n matrices; sums of the raw moments in double carry
+// ~1e-13 relative error, far below PCL's own float noise (SURVEY.md H2b).
+PEB_HD Mat4 umeyama_from_sums(const double* acc) {
+  const double n = acc[0];
+  const double inv_n = 1.0 / n;
+  double sm[3], tm[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    sm[i] = acc[1 + i] * inv_n;
+    tm[i] = acc[4 + i] * inv_n;
+  }
+  double sigma[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sigma[r * 3 + c] = acc[7 + r * 3 + c] * inv_n - tm[r] * sm[c];
+  double R[9];
+  if (!polar_rotation3(sigma, R)) umeyama_rotation_svd(sigma, R);
+  return umeyama_pack(R, sm, tm);
 }
 
 // x = ATA^-1 ATb by LU with partial pivoting ([EIGEN] fixed 6x6 inverse() goes through

@@ -44,6 +44,8 @@ struct IcpLaunch {
   const int* anchors;    // nullable, H x n_anchor: match (sorted position) of the first point of every 32-point patch
   int n_anchor;
   float seed_guard2;     // (cells)^2: an anchor farther than this from the query is not used as a seed
+  unsigned long long* dbg;  // nullable: 8 timestamps (ns, %globaltimer) per launch, written by the last block
+  int launch_idx;
   IcpState* states;      // H
   double* partials;      // H x blocks_per_hyp x kAccMax
   int32_t* corr_idx;     // nullable, indexed by ORIGINAL source index (single align only)
@@ -122,18 +124,18 @@ __device__ __forceinline__ void reduce_partials(const double* __restrict__ part,
   constexpr int kW = kIcpThreads / 32;
   double v = 0.0;
   if (lane < NACC) {
-    // warp w owns the contiguous block range [b0, b1); eight independent loads in flight per lane
+    // warp w owns the contiguous block range [b0, b1); sixteen independent loads in flight per lane
     // (the L2 round trip, not the adds, is what this loop waits for); the order of the adds is fixed
     const int per = (n_blocks + kW - 1) / kW;
     const int b0 = warp * per, b1 = min(b0 + per, n_blocks);
     const double* p = part + lane;
     int b = b0;
-    for (; b + 8 <= b1; b += 8) {
-      double t[8];
+    for (; b + 16 <= b1; b += 16) {
+      double t[16];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) t[k] = __ldcg(p + static_cast<size_t>(b + k) * kAccMax);
+      for (int k = 0; k < 16; ++k) t[k] = __ldcg(p + static_cast<size_t>(b + k) * kAccMax);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v += t[k];
+      for (int k = 0; k < 16; ++k) v += t[k];
     }
     for (; b < b1; ++b) v += __ldcg(p + static_cast<size_t>(b) * kAccMax);
     sm[warp][lane] = v;
@@ -176,20 +178,42 @@ __global__ void __launch_bounds__(128) icp_anchor_kernel(const IcpLaunch L, int*
   anchors[static_cast<size_t>(h) * L.n_anchor + a] = best.j;
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // The solve runs once per launch in one thread; keeping it out of line keeps its registers and
 // local arrays out of the per-query loop's allocation.
+// (templated on the register cap of the calling kernel so that the single-align copy is not
+//  squeezed into the batched kernels' 64 registers)
+template <int MB>
 __device__ __noinline__ void finish_iteration(IcpState* st, const IcpCriteria* cr, const double* acc, Mat4* trace,
-                                              int trace_cap) {
+                                              int trace_cap, unsigned long long* dbg) {
+  if (dbg) dbg[5] = global_ns();
   IcpState s = *st;
+  if (dbg) dbg[6] = global_ns() + (s.iterations < -5 ? 1 : 0);
   icp_finish_iteration(s, *cr, acc);
+  if (dbg) dbg[7] = global_ns() + (s.iterations < -5 ? 1 : 0);
   s.ticket = 0;
   if (trace && s.state != PEB_NO_CORRESPONDENCES && s.iterations >= 1 && s.iterations <= trace_cap)
     trace[s.iterations - 1] = s.inc;
   *st = s;
 }
 
+// PDL (common.cuh : PEB_LAUNCH_PDL): let the next launch of the stream be scheduled now, then wait
+// until everything the previous launch wrote is complete and visible.
+__device__ __forceinline__ void pdl_trigger_and_wait() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 template <int G, int EST, int MB, bool CERT>
 __global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_kernel(const IcpLaunch L) {
+  pdl_trigger_and_wait();
+  unsigned long long t_dbg[5];
+  if (L.dbg) t_dbg[0] = global_ns();
   constexpr int NACC = (EST == PEB_ESTIMATOR_SVD) ? kAccSvd : kAccLls;
   __shared__ double sm[kIcpThreads / 32][kAccMax];
   __shared__ double sm_tot[kAccMax];
@@ -375,6 +399,7 @@ __global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_kernel(const Ic
     }
   }
 
+  if (L.dbg) t_dbg[1] = global_ns();
   const double r = block_reduce_acc<NACC>(acc, sm);
   double* part = L.partials + (static_cast<size_t>(h) * L.blocks_per_hyp) * kAccMax;
   if (threadIdx.x < NACC) __stcg(part + static_cast<size_t>(blockIdx.x) * kAccMax + threadIdx.x, r);
@@ -388,8 +413,16 @@ __global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_kernel(const Ic
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  if (L.dbg) t_dbg[2] = global_ns();
   reduce_partials<NACC>(part, L.blocks_per_hyp, sm, sm_tot);
-  if (threadIdx.x == 0) finish_iteration(st, &L.crit, sm_tot, L.trace, L.trace_cap);
+  if (L.dbg) t_dbg[3] = global_ns();
+  if (threadIdx.x == 0) {
+    finish_iteration<MB>(st, &L.crit, sm_tot, L.trace, L.trace_cap, (L.dbg && h == 0) ? L.dbg + 8 * L.launch_idx : nullptr);
+    if (L.dbg && h == 0) {
+      t_dbg[4] = global_ns();
+      for (int k = 0; k < 5; ++k) L.dbg[8 * L.launch_idx + k] = t_dbg[k];
+    }
+  }
 }
 
 // [PCL] registration/impl/registration.hpp : getFitnessScore(max_range) with the final transform
@@ -398,6 +431,7 @@ template <int G>
 __global__ void __launch_bounds__(kIcpThreads) icp_fitness_kernel(const IcpLaunch L) {
   __shared__ double sm[kIcpThreads / 32][kAccMax];
   __shared__ double sm_tot[kAccMax];
+  pdl_trigger_and_wait();
   const int h = blockIdx.y;
   IcpState* st = L.states + h;
   float T[16];
@@ -549,7 +583,7 @@ int launch_one_iteration(peb_ctx* ctx, const IcpLaunch& L, size_t H, int estimat
   constexpr int S = PEB_ESTIMATOR_SVD, P = PEB_ESTIMATOR_POINT_TO_PLANE_LLS;
   const bool cert = G == 1 && L.margin > 0.0f;
   const bool svd = estimator == PEB_ESTIMATOR_SVD;
-#define PEB_ICP_LAUNCH(EST, MB, CERT) PEB_LAUNCH(ctx, (icp_iteration_kernel<G, EST, MB, CERT>), grid, kIcpThreads, 0, L)
+#define PEB_ICP_LAUNCH(EST, MB, CERT) PEB_LAUNCH_PDL(ctx, (icp_iteration_kernel<G, EST, MB, CERT>), grid, dim3(kIcpThreads), L)
   if (H == 1) {
     if (cert) { if (svd) PEB_ICP_LAUNCH(S, kMinBlocksSingle, (G == 1)); else PEB_ICP_LAUNCH(P, kMinBlocksSingle, (G == 1)); }
     else      { if (svd) PEB_ICP_LAUNCH(S, kMinBlocksSingle, false);    else PEB_ICP_LAUNCH(P, kMinBlocksSingle, false); }
@@ -575,11 +609,11 @@ int launch_one_iteration_g(peb_ctx* ctx, int G, const IcpLaunch& L, size_t H, in
 int launch_fitness_g(peb_ctx* ctx, int G, const IcpLaunch& L, size_t H) {
   dim3 grid(L.blocks_per_hyp, static_cast<unsigned>(H));
   switch (G) {
-    case 1: PEB_LAUNCH(ctx, icp_fitness_kernel<1>, grid, kIcpThreads, 0, L); break;
-    case 2: PEB_LAUNCH(ctx, icp_fitness_kernel<2>, grid, kIcpThreads, 0, L); break;
-    case 4: PEB_LAUNCH(ctx, icp_fitness_kernel<4>, grid, kIcpThreads, 0, L); break;
-    case 8: PEB_LAUNCH(ctx, icp_fitness_kernel<8>, grid, kIcpThreads, 0, L); break;
-    default: PEB_LAUNCH(ctx, icp_fitness_kernel<16>, grid, kIcpThreads, 0, L); break;
+    case 1: PEB_LAUNCH_PDL(ctx, icp_fitness_kernel<1>, grid, dim3(kIcpThreads), L); break;
+    case 2: PEB_LAUNCH_PDL(ctx, icp_fitness_kernel<2>, grid, dim3(kIcpThreads), L); break;
+    case 4: PEB_LAUNCH_PDL(ctx, icp_fitness_kernel<4>, grid, dim3(kIcpThreads), L); break;
+    case 8: PEB_LAUNCH_PDL(ctx, icp_fitness_kernel<8>, grid, dim3(kIcpThreads), L); break;
+    default: PEB_LAUNCH_PDL(ctx, icp_fitness_kernel<16>, grid, dim3(kIcpThreads), L); break;
   }
   return PEB_OK;
 }
@@ -692,8 +726,15 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
   Lw.blocks_per_hyp = blocks_for(n, H, g_warm);
   Lw.warm = ctx->warm_start ? 1 : 0;
   ctx->prof_launches = 0;
+  if (ctx->debug_timers) {
+    PEB_CUDA(ctx, ctx->dbg.ensure(static_cast<size_t>(launches) * 8 * sizeof(unsigned long long)));
+    PEB_CUDA(ctx, cudaMemsetAsync(ctx->dbg.p, 0, static_cast<size_t>(launches) * 8 * sizeof(unsigned long long), ctx->stream));
+    Lc.dbg = Lw.dbg = ctx->dbg.as<unsigned long long>();
+    ctx->dbg_launches = launches;
+  }
   for (int it = 0; it < launches; ++it) {
     PEB_TRY(prof_mark(ctx, 2 * it));
+    Lc.launch_idx = Lw.launch_idx = it;
     if (it == 0)
       PEB_TRY(launch_one_iteration_g(ctx, g_cold, Lc, H, prm->estimator));
     else

@@ -266,3 +266,18 @@ HC_API void hc_mat4_mul(const float* A, const float* B, float* Cm) {
   memcpy(Cm, c.m, 64);
 }
 }
+
+extern "C" {
+// rotation of umeyama from a 3x3 sigma: polar Newton path vs the Jacobi SVD path (returns 1 if polar converged)
+__attribute__((visibility("default"))) int hc_rotation_paths(const double* sigma9, double* R_polar, double* R_svd) {
+  double A[9], Rp[9], Rs[9];
+  for (int i = 0; i < 9; ++i) A[i] = sigma9[i];
+  const bool ok = polar_rotation3(A, Rp);
+  umeyama_rotation_svd(A, Rs);
+  for (int i = 0; i < 9; ++i) {
+    R_polar[i] = ok ? Rp[i] : 0.0;
+    R_svd[i] = Rs[i];
+  }
+  return ok ? 1 : 0;
+}
+}

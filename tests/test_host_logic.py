@@ -23,6 +23,7 @@ def hc():
     L.hc_grid_nn.argtypes = [vp, sz, sz, vp, sz, sz, C.c_float, C.c_float, C.c_float, vp, vp, vp]
     L.hc_grid_nn_warm.argtypes = [vp, sz, sz, vp, sz, sz, C.c_float, vp, C.c_float, C.c_float, vp, vp, vp]
     L.hc_grid_nn_seeded.argtypes = [vp, sz, sz, vp, vp, sz, C.c_float, C.c_float, vp, vp]
+    L.hc_rotation_paths.argtypes = [vp, vp, vp]
     L.hc_umeyama_pairs.argtypes = [vp, vp, sz, vp]
     L.hc_lls_pairs.argtypes = [vp, vp, vp, sz, vp]
     L.hc_criteria_script.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]
@@ -219,6 +220,43 @@ def test_umeyama_from_sums_matches_oracle(hc, oracle):
     t2 = (s2 * np.array([1, 1, 1], np.float32)) + np.float32(0.1)
     hc.hc_umeyama_pairs(s2.ctypes.data, t2.ctypes.data, len(s2), T.ctypes.data)
     assert abs(np.linalg.det(T.reshape(4, 4).T[:3, :3].astype(np.float64)) - 1) < 1e-5
+
+
+def test_polar_rotation_equals_svd_rotation(hc):
+    """The fast path of the solve (scaled Newton polar decomposition) must give umeyama's U V^T to double
+    precision whenever it accepts the matrix, and must decline reflections / rank-deficient matrices."""
+    rng = np.random.default_rng(23)
+    Rp = np.zeros(9)
+    Rs = np.zeros(9)
+    accepted = 0
+    worst = 0.0
+    for k in range(400):
+        U, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        V, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        if np.linalg.det(U) * np.linalg.det(V) < 0:
+            V[:, 0] *= -1
+        sv = np.sort(10.0 ** rng.uniform(-6, 0, 3))[::-1] * 10.0 ** rng.uniform(-8, 2)   # cond up to 1e6, any scale
+        A = np.ascontiguousarray(U @ np.diag(sv) @ V.T)
+        ok = hc.hc_rotation_paths(A.ctypes.data, Rp.ctypes.data, Rs.ctypes.data)
+        ref = (U @ V.T).reshape(-1)
+        assert np.abs(Rs - ref).max() < 1e-9
+        if ok:
+            accepted += 1
+            worst = max(worst, np.abs(Rp - Rs).max())
+            assert np.abs(Rp.reshape(3, 3) @ Rp.reshape(3, 3).T - np.eye(3)).max() < 1e-14
+    assert accepted > 380 and worst < 1e-10 * 1e3   # agreement limited by conditioning: 1e-16 * cond
+    # ICP-like covariances (well conditioned): agreement at the 1e-15 level
+    for k in range(200):
+        p = rng.normal(size=(500, 3)) * [0.05, 0.03, 0.004]
+        Rt = synth.rotation_about(synth.random_unit(rng), rng.uniform(0, 0.3))
+        q = p @ Rt.T + rng.normal(0, 1e-3, p.shape)
+        A = np.ascontiguousarray((q - q.mean(0)).T @ (p - p.mean(0)) / len(p))
+        assert hc.hc_rotation_paths(A.ctypes.data, Rp.ctypes.data, Rs.ctypes.data) == 1
+        assert np.abs(Rp - Rs).max() < 5e-14
+    # reflection (det < 0), rank 2 and zero matrices are declined
+    for A in (np.diag([1.0, 1.0, -1.0]), np.diag([1.0, 0.5, 0.0]), np.zeros((3, 3)), np.diag([1.0, 1e-9, 1e-9])):
+        A = np.ascontiguousarray(A)
+        assert hc.hc_rotation_paths(A.ctypes.data, Rp.ctypes.data, Rs.ctypes.data) == 0
 
 
 def test_lls_from_sums_matches_oracle_bitwise(hc, oracle):
