@@ -266,7 +266,7 @@ def run_ours(args):
             h_out.copy_(d_all, non_blocking=True)
             stream.synchronize()
 
-    def timed(fn, steps, profile=False):
+    def timed(fn, steps, profile=0):
         """-> (total ms of `steps` steps, per-launch iteration-kernel ms)"""
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         kernel_ms: list[float] = []
@@ -277,9 +277,12 @@ def run_ours(args):
             a.record(stream)
             fn()
             b.record(stream)
-            if profile:
+            if profile == 1:    # one value: the span of this step's ITERATIONS iteration launches
                 chk(lib.peb_profile_read(ctx.handle, buf.ctypes.data, len(buf), C.byref(cnt)))
-                kernel_ms.extend(float(x) for x in buf[: max(cnt.value - 1, 0)])  # last entry = fitness launch
+                kernel_ms.extend(float(x) for x in buf[: cnt.value])
+            elif profile == 2:  # per launch (last entry = fitness launch)
+                chk(lib.peb_profile_read(ctx.handle, buf.ctypes.data, len(buf), C.byref(cnt)))
+                kernel_ms.extend(float(x) for x in buf[: max(cnt.value - 1, 0)])
         stream.synchronize()
         return sum(a.elapsed_time(b) for a, b in ev), kernel_ms
 
@@ -304,11 +307,15 @@ def run_ours(args):
         launches0 = ctx.launch_count
         if rank == 0:
             sampler.start()
-        total_ms, kernel_ms = timed(step_device, args.steps, profile=True)
+        total_ms, span_ms = timed(step_device, args.steps, profile=1)
         barrier()
         clocks = sampler.stop() if rank == 0 else None
         launches = ctx.launch_count - launches0
+        # per-iteration detail from one extra, untimed step (events between the launches serialise them)
+        ctx.set_int("profile", 2)
+        _, kernel_ms = timed(step_device, 1, profile=2)
         ctx.set_int("profile", 0)
+        ms_per_step_local = total_ms / args.steps
         total_ms = max_over_ranks(total_ms)
         # ---- end-to-end leg through the host-buffer C ABI ---------------------------------
         timed(step_e2e, max(1, min(args.warmup, 3)))
@@ -329,7 +336,7 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     alg_bytes = h_local * len(c4.source) * ALG_BYTES_PER_QUERY
-    avg_kernel_ms = sum(kernel_ms) / max(len(kernel_ms), 1)
+    avg_kernel_ms = sum(span_ms) / max(len(span_ms) * ITERATIONS, 1)  # live, inside the timed steps
     achieved = alg_bytes / (avg_kernel_ms * 1e-3) / 1e9 if avg_kernel_ms > 0 else 0.0
     traffic = None
     tf = ROOT / "profiles" / "roofline_traffic.json"
@@ -340,11 +347,11 @@ def run_ours(args):
             traffic = None
     roofline = {"bound": "hbm", "kernel": "icp_iteration_kernel (batched, one launch = one ICP iteration of this rank's hypotheses)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_kernel_ms, "launches_timed": len(kernel_ms),
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_kernel_ms,
+                "launches_timed": len(span_ms) * ITERATIONS,
                 "peak_source": peak_src,
-                "launch_ms_by_iteration": [round(float(np.mean(kernel_ms[i::ITERATIONS])), 3) for i in range(ITERATIONS)]
-                if len(kernel_ms) == ITERATIONS * args.steps else None,
-                "share_of_step": (sum(kernel_ms) / args.steps) / (total_ms / args.steps) if total_ms > 0 else None}
+                "launch_ms_by_iteration": [round(float(x), 3) for x in kernel_ms] if len(kernel_ms) == ITERATIONS else None,
+                "share_of_step": (sum(span_ms) / args.steps) / ms_per_step_local if ms_per_step_local > 0 else None}
 
     line = {
         "metric": "icp_hypotheses_per_s", "value": value, "unit": "hypotheses/s", "n_gpus": world, "steps": args.steps,

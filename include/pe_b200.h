@@ -189,8 +189,10 @@ typedef struct peb_grid_info {
   int64_t n_cells;
 } peb_grid_info;
 PEB_API int peb_target_grid_info(peb_ctx* ctx, peb_grid_info* out);
-/* with peb_ctx_set_int(ctx, "profile", 1): device time (ms, CUDA events on the context's stream)
- * of every ICP kernel launch of the last align — the iteration launches, then the fitness launch */
+/* with peb_ctx_set_int(ctx, "profile", 2): device time (ms, CUDA events on the context's stream)
+ * of every ICP kernel launch of the last align — the iteration launches, then the fitness launch.
+ * With "profile" = 1: ONE value, the span from the first to the last iteration launch (no events
+ * between the launches, so their overlap is not disturbed). */
 PEB_API int peb_profile_read(peb_ctx* ctx, float* out_ms, size_t cap, size_t* out_n);
 /* per-iteration increments of the last peb_icp_align (column-major 4x4 each);
  * copies min(cap, iterations) matrices, returns the count via *out_n */

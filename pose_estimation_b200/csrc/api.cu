@@ -210,6 +210,11 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
     ctx->seed_guard = value / 10.0f;
     return PEB_OK;
   }
+  if (!strcmp(key, "blocks_factor")) {
+    if (value < 1 || value > 4096) return fail(ctx, PEB_E_INVALID_ARG, "blocks_factor out of [1, 4096]");
+    ctx->blocks_factor = value;
+    return PEB_OK;
+  }
   if (!strcmp(key, "pdl")) {
     ctx->use_pdl = value != 0;
     return PEB_OK;
@@ -228,6 +233,7 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
   }
   if (!strcmp(key, "profile")) {
     ctx->profile = value != 0;
+    ctx->profile_level = value;
     ctx->prof_launches = 0;
     return PEB_OK;
   }

@@ -102,6 +102,7 @@ struct peb_ctx {
   bool warm_start = true;       // iterations >= 1 seed the search with the previous match
   bool anchor_seed = true;      // iteration 0: one cold search per 32-point patch seeds the patch
   float seed_guard = 10.0f;     // seeds farther than this many cells from the query are not used
+  int blocks_factor = 32;       // batched aligns: ~this many blocks per SM and launch in total
   bool use_pdl = true;          // programmatic dependent launch between the ICP launches of an align
   bool debug_timers = false;    // development: %globaltimer stamps of the phases of every iteration launch
   peb::DevBuf dbg;
@@ -153,6 +154,8 @@ struct peb_ctx {
   bool profile = false;
   std::vector<cudaEvent_t> prof_events;
   int prof_launches = 0;
+  int profile_level = 0;        // 1: one event pair around all iteration launches, 2: one per launch
+  int prof_span_launches = 0;
   peb::DevBuf nn_q, nn_idx, nn_d2;   // peb_nn_search staging
 
   // voxel grid / normals scratch

@@ -621,13 +621,13 @@ int launch_fitness_g(peb_ctx* ctx, int G, const IcpLaunch& L, size_t H) {
 // blocks per hypothesis for a group width: one block handles kIcpThreads / G queries per pass;
 // a single align spreads over the whole chip, batched aligns give every hypothesis a few blocks
 // and let grid.y fill the machine
-int blocks_for(int n, size_t H, int G) {
+int blocks_for(int n, size_t H, int G, int factor) {
   const int want = ceil_div(std::max(n, 1), kIcpThreads / G);
   int bph;
   if (H == 1)
     bph = std::min(want, kSmCount * 8);
   else
-    bph = std::min(want, std::max(1, static_cast<int>((kSmCount * 32 + H - 1) / H)));
+    bph = std::min(want, std::max(1, static_cast<int>((static_cast<size_t>(kSmCount) * factor + H - 1) / H)));
   return std::max(bph, 1);
 }
 
@@ -642,7 +642,7 @@ int prepare_launch(peb_ctx* ctx, size_t H, const peb_icp_params* prm, IcpLaunch&
   L.seed_guard2 = ctx->seed_guard * ctx->seed_guard;
   L.src = ctx->src_grid.view.pts;
   L.n_src = n;
-  const int max_bph = std::max(blocks_for(n, H, ctx->nn_group), blocks_for(n, H, 1));
+  const int max_bph = std::max(blocks_for(n, H, ctx->nn_group, ctx->blocks_factor), blocks_for(n, H, 1, ctx->blocks_factor));
   PEB_CUDA(ctx, ctx->work.ensure(std::max<size_t>(H * static_cast<size_t>(n), 1) * sizeof(float4)));
   PEB_CUDA(ctx, ctx->slack.ensure(std::max<size_t>(H * static_cast<size_t>(n), 1) * sizeof(float)));
   PEB_CUDA(ctx, ctx->state.ensure(H * sizeof(IcpState)));
@@ -711,7 +711,7 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
   const int g_cold = ctx->nn_group;
   const int g_warm = ctx->warm_start ? 1 : g_cold;
   IcpLaunch Lc = L, Lw = L;
-  Lc.blocks_per_hyp = blocks_for(n, H, g_cold);
+  Lc.blocks_per_hyp = blocks_for(n, H, g_cold, ctx->blocks_factor);
   Lc.warm = 0;
   // (a single align has too few patches to fill the machine with anchor searches: their latency
   //  would exceed what the seeds save; its cold launch keeps the plain ring search)
@@ -723,7 +723,7 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
     PEB_LAUNCH(ctx, icp_anchor_kernel, agrid, 128, 0, Lc, ctx->anchors.as<int>());
     Lc.anchors = ctx->anchors.as<int>();
   }
-  Lw.blocks_per_hyp = blocks_for(n, H, g_warm);
+  Lw.blocks_per_hyp = blocks_for(n, H, g_warm, ctx->blocks_factor);
   Lw.warm = ctx->warm_start ? 1 : 0;
   ctx->prof_launches = 0;
   if (ctx->debug_timers) {
@@ -732,19 +732,32 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
     Lc.dbg = Lw.dbg = ctx->dbg.as<unsigned long long>();
     ctx->dbg_launches = launches;
   }
+  // profile 1: one event pair around the whole run of iteration launches (nothing between the
+  // launches, so PDL overlap is what the bench measures); profile 2: a pair around every launch
+  const bool per_launch = ctx->profile_level >= 2;
+  if (!per_launch) PEB_TRY(prof_mark(ctx, 0));
   for (int it = 0; it < launches; ++it) {
-    PEB_TRY(prof_mark(ctx, 2 * it));
+    if (per_launch) PEB_TRY(prof_mark(ctx, 2 * it));
     Lc.launch_idx = Lw.launch_idx = it;
     if (it == 0)
       PEB_TRY(launch_one_iteration_g(ctx, g_cold, Lc, H, prm->estimator));
     else
       PEB_TRY(launch_one_iteration_g(ctx, g_warm, Lw, H, prm->estimator));
-    PEB_TRY(prof_mark(ctx, 2 * it + 1));
+    if (per_launch) PEB_TRY(prof_mark(ctx, 2 * it + 1));
   }
-  PEB_TRY(prof_mark(ctx, 2 * launches));
-  PEB_TRY(launch_fitness_g(ctx, g_warm, Lw, H));
-  PEB_TRY(prof_mark(ctx, 2 * launches + 1));
-  if (ctx->profile) ctx->prof_launches = launches + 1;
+  if (per_launch) {
+    PEB_TRY(prof_mark(ctx, 2 * launches));
+    PEB_TRY(launch_fitness_g(ctx, g_warm, Lw, H));
+    PEB_TRY(prof_mark(ctx, 2 * launches + 1));
+    if (ctx->profile) ctx->prof_launches = launches + 1;
+  } else {
+    PEB_TRY(prof_mark(ctx, 1));
+    PEB_TRY(launch_fitness_g(ctx, g_warm, Lw, H));
+    if (ctx->profile) {
+      ctx->prof_launches = 1;        // one record: the span of all iteration launches
+      ctx->prof_span_launches = launches;
+    }
+  }
   return PEB_OK;
 }
 
@@ -759,7 +772,7 @@ int fitness_device(peb_ctx* ctx, const float* d_T, double max_range, peb_icp_res
   L.results = d_result;
   L.fitness_only = 1;
   L.warm = 0;  // an arbitrary transform: nothing to seed the search with
-  L.blocks_per_hyp = blocks_for(ctx->n_src_sorted, 1, ctx->nn_group);
+  L.blocks_per_hyp = blocks_for(ctx->n_src_sorted, 1, ctx->nn_group, ctx->blocks_factor);
   PEB_LAUNCH(ctx, icp_init_kernel, 1, 128, 0, L.states, d_T, 1);
   return launch_fitness_g(ctx, ctx->nn_group, L, 1);
 }

@@ -45,7 +45,7 @@ def main():
     icp = pcl.IterativeClosestPoint(ctx)
     icp.setMaximumIterations(30)
     icp.getConvergeCriteria().setAbsoluteMSE(-1.0)
-    ctx.set_int("profile", 1)
+    ctx.set_int("profile", 2)
     icp.setInputTarget(prob.target)
     rng = np.random.default_rng(0)
     guesses = np.stack([synth.perturb_pose(prob.gt_pose, rng, 6.0, 0.008) for _ in range(128)])
