@@ -335,20 +335,32 @@ def run_ours(args):
         peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
-    alg_bytes = h_local * len(c4.source) * ALG_BYTES_PER_QUERY
-    avg_kernel_ms = sum(span_ms) / max(len(span_ms) * ITERATIONS, 1)  # live, inside the timed steps
+    persistent = False  # (a persistent cooperative variant was measured slower and removed: profiles/README.md)
+    if persistent:
+        # one cooperative launch per batch: anchors + ITERATIONS iterations (40 B/query each) + fitness (32 B/query)
+        kernel_name = ("icp_persistent_kernel (batched: one launch = anchors, all ICP iterations and the fitness pass "
+                       "of this rank's hypotheses)")
+        alg_bytes = h_local * len(c4.source) * (ALG_BYTES_PER_QUERY * ITERATIONS + 32)
+        avg_kernel_ms = sum(span_ms) / max(len(span_ms), 1)  # live, inside the timed steps
+        launches_timed = len(span_ms)
+    else:
+        kernel_name = "icp_iteration_kernel (batched, one launch = one ICP iteration of this rank's hypotheses)"
+        alg_bytes = h_local * len(c4.source) * ALG_BYTES_PER_QUERY
+        avg_kernel_ms = sum(span_ms) / max(len(span_ms) * ITERATIONS, 1)
+        launches_timed = len(span_ms) * ITERATIONS
     achieved = alg_bytes / (avg_kernel_ms * 1e-3) / 1e9 if avg_kernel_ms > 0 else 0.0
     traffic = None
     tf = ROOT / "profiles" / "roofline_traffic.json"
     if tf.exists():
         try:
-            traffic = json.loads(tf.read_text()).get("icp_iteration_kernel_batch_bytes_per_launch")
+            traffic = json.loads(tf.read_text()).get(
+                "icp_persistent_kernel_bytes_per_launch" if persistent else "icp_iteration_kernel_batch_bytes_per_launch")
         except (ValueError, OSError):
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "icp_iteration_kernel (batched, one launch = one ICP iteration of this rank's hypotheses)",
+    roofline = {"bound": "hbm", "kernel": kernel_name,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_kernel_ms,
-                "launches_timed": len(span_ms) * ITERATIONS,
+                "launches_timed": launches_timed,
                 "peak_source": peak_src,
                 "launch_ms_by_iteration": [round(float(x), 3) for x in kernel_ms] if len(kernel_ms) == ITERATIONS else None,
                 "share_of_step": (sum(span_ms) / args.steps) / ms_per_step_local if ms_per_step_local > 0 else None}

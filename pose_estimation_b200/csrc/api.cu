@@ -173,6 +173,9 @@ PEB_API void peb_ctx_destroy(peb_ctx* ctx) {
     g->vals_tmp.release();
   }
   for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->join_events) cudaEventDestroy(e);
+  for (cudaStream_t st : ctx->sub_streams) cudaStreamDestroy(st);
+  if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
   ctx->h_stage.release();
   ctx->h_small.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -210,8 +213,13 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
     ctx->seed_guard = value / 10.0f;
     return PEB_OK;
   }
+  if (!strcmp(key, "batch_streams")) {
+    if (value < 0 || value > 32) return fail(ctx, PEB_E_INVALID_ARG, "batch_streams out of [0, 32]");
+    ctx->batch_streams = value;
+    return PEB_OK;
+  }
   if (!strcmp(key, "blocks_factor")) {
-    if (value < 1 || value > 4096) return fail(ctx, PEB_E_INVALID_ARG, "blocks_factor out of [1, 4096]");
+    if (value < 0 || value > 4096) return fail(ctx, PEB_E_INVALID_ARG, "blocks_factor out of [0, 4096]");
     ctx->blocks_factor = value;
     return PEB_OK;
   }

@@ -102,7 +102,11 @@ struct peb_ctx {
   bool warm_start = true;       // iterations >= 1 seed the search with the previous match
   bool anchor_seed = true;      // iteration 0: one cold search per 32-point patch seeds the patch
   float seed_guard = 10.0f;     // seeds farther than this many cells from the query are not used
-  int blocks_factor = 32;       // batched aligns: ~this many blocks per SM and launch in total
+  int batch_streams = 0;        // batched aligns: independent chains of launches (see icp.cu); 0 = auto
+  std::vector<cudaStream_t> sub_streams;
+  std::vector<cudaEvent_t> join_events;
+  cudaEvent_t fork_event = nullptr;
+  int blocks_factor = 0;        // batched aligns: ~this many blocks per SM and launch in total; 0 = auto
   bool use_pdl = true;          // programmatic dependent launch between the ICP launches of an align
   bool debug_timers = false;    // development: %globaltimer stamps of the phases of every iteration launch
   peb::DevBuf dbg;

@@ -209,6 +209,103 @@ __device__ __forceinline__ void pdl_trigger_and_wait() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// adds one accepted correspondence (working point p, match best) to the estimator's moment sums
+template <int EST, int NACC>
+__device__ __forceinline__ void accumulate_pair_impl(const GridView& g, const float4& p, const NnBest& best,
+                                                     double (&acc)[NACC]) {
+  const float4 t = g.pts[best.j];
+  if (EST == PEB_ESTIMATOR_SVD) {
+    const double sx = p.x, sy = p.y, sz = p.z, tx = t.x, ty = t.y, tz = t.z;
+    acc[0] += 1.0;
+    acc[1] += sx;
+    acc[2] += sy;
+    acc[3] += sz;
+    acc[4] += tx;
+    acc[5] += ty;
+    acc[6] += tz;
+    acc[7] += tx * sx;
+    acc[8] += tx * sy;
+    acc[9] += tx * sz;
+    acc[10] += ty * sx;
+    acc[11] += ty * sy;
+    acc[12] += ty * sz;
+    acc[13] += tz * sx;
+    acc[14] += tz * sy;
+    acc[15] += tz * sz;
+    acc[16] += static_cast<double>(best.d2);
+  } else {
+    acc[0] += 1.0;
+    acc[NACC - 1] += static_cast<double>(best.d2);
+    const float4 nr = g.normals[best.j];
+    // [PCL] transformation_estimation_point_to_plane_lls.hpp: pairs with a non-finite
+    // member are left out of the normal equations (they still count as correspondences)
+    if (finite3(t.x, t.y, t.z) && finite3(nr.x, nr.y, nr.z)) {
+      const float sx = p.x, sy = p.y, sz = p.z, dx = t.x, dy = t.y, dz = t.z;
+      const float nx = nr.x, ny = nr.y, nz = nr.z;
+      const double a = nz * sy - ny * sz;  // float expressions, widened afterwards
+      const double b = nx * sz - nz * sx;
+      const double c = ny * sx - nx * sy;
+      acc[1] += a * a;
+      acc[2] += a * b;
+      acc[3] += a * c;
+      acc[4] += a * nx;
+      acc[5] += a * ny;
+      acc[6] += a * nz;
+      acc[7] += b * b;
+      acc[8] += b * c;
+      acc[9] += b * nx;
+      acc[10] += b * ny;
+      acc[11] += b * nz;
+      acc[12] += c * c;
+      acc[13] += c * nx;
+      acc[14] += c * ny;
+      acc[15] += c * nz;
+      acc[16] += nx * nx;  // float products
+      acc[17] += nx * ny;
+      acc[18] += nx * nz;
+      acc[19] += ny * ny;
+      acc[20] += ny * nz;
+      acc[21] += nz * nz;
+      const double d = nx * dx + ny * dy + nz * dz - nx * sx - ny * sy - nz * sz;
+      acc[22] += a * d;
+      acc[23] += b * d;
+      acc[24] += c * d;
+      acc[25] += nx * d;
+      acc[26] += ny * d;
+      acc[27] += nz * d;
+    }
+  }
+}
+template <int EST, int NACC>
+__device__ __forceinline__ void accumulate_pair(const GridView& g, const float4& p, const NnBest& best,
+                                                double (&acc)[NACC]) {
+  static_assert((EST == PEB_ESTIMATOR_SVD && NACC == kAccSvd) || (EST != PEB_ESTIMATOR_SVD && NACC == kAccLls), "layout");
+  accumulate_pair_impl<EST, NACC>(g, p, best, acc);
+}
+
+// first-iteration search of query p seeded by its patch's anchor (icp_anchor_kernel), or cold
+__device__ __forceinline__ NnBest first_iteration_search(const IcpLaunch& L, int h, int i, const float4& p,
+                                                         const float* T, bool apply, const int* anchors) {
+  int j_seed = anchors ? __ldcg(anchors + static_cast<size_t>(h) * L.n_anchor + (i >> 5)) : -1;
+  if (j_seed >= 0) {
+    // the patch's anchor query, recomputed (same arithmetic as the caller's): where the seed was found from
+    float4 a = L.src[i & ~31];
+    if (apply) {
+      float ox, oy, oz;
+      transform_icp(T, a.x, a.y, a.z, ox, oy, oz);
+      a.x = ox;
+      a.y = oy;
+      a.z = oz;
+    }
+    // a patch that straddles the end of a row of the source grid holds points from two places:
+    // a seed from the other place would only blow the ball up
+    const float ax = p.x - a.x, ay = p.y - a.y, az = p.z - a.z;
+    if (ax * ax + ay * ay + az * az > L.seed_guard2 * L.grid.h * L.grid.h) j_seed = -1;
+    if (j_seed >= 0) return grid_nn_seeded(L.grid, p.x, p.y, p.z, j_seed, a.x, a.y, a.z, L.stop_d2);
+  }
+  return grid_nn<1>(L.grid, p.x, p.y, p.z, L.stop_d2);
+}
+
 template <int G, int EST, int MB, bool CERT>
 __global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_kernel(const IcpLaunch L) {
   pdl_trigger_and_wait();
@@ -299,25 +396,10 @@ __global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_kernel(const Ic
           best = grid_nn_warm(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2);
         }
       } else {
-        int j_seed = -1;
-        if (G == 1 && first && L.anchors) j_seed = L.anchors[static_cast<size_t>(h) * L.n_anchor + (i >> 5)];
-        if (G == 1 && j_seed >= 0) {
-          // the patch's anchor query, recomputed (same arithmetic as above): where the seed was found from
-          float4 a = L.src[i & ~31];
-          if (apply) {
-            float ox, oy, oz;
-            transform_icp(T, a.x, a.y, a.z, ox, oy, oz);
-            a.x = ox;
-            a.y = oy;
-            a.z = oz;
-          }
-          // a patch that straddles the end of a row of the source grid holds points from two
-          // places: a seed from the other place would only blow the ball up
-          const float ax = p.x - a.x, ay = p.y - a.y, az = p.z - a.z;
-          if (ax * ax + ay * ay + az * az > L.seed_guard2 * L.grid.h * L.grid.h) j_seed = -1;
-          if (j_seed >= 0) best = grid_nn_seeded(L.grid, p.x, p.y, p.z, j_seed, a.x, a.y, a.z, L.stop_d2);
-        }
-        if (!(G == 1 && j_seed >= 0)) best = grid_nn<G>(L.grid, p.x, p.y, p.z, L.stop_d2);
+        if (G == 1 && first && L.anchors)
+          best = first_iteration_search(L, h, i, p, T, apply, L.anchors);
+        else
+          best = grid_nn<G>(L.grid, p.x, p.y, p.z, L.stop_d2);
         if (CERT && lane_in_group == 0) *sl = -1.0f;
       }
     }
@@ -333,70 +415,7 @@ __global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_kernel(const Ic
       L.corr_idx[orig] = keep ? best.idx : -1;
       L.corr_d2[orig] = keep ? best.d2 : 0.0f;
     }
-    if (keep && lane_in_group == 0) {
-      const float4 t = L.grid.pts[best.j];
-      if (EST == PEB_ESTIMATOR_SVD) {
-        const double sx = p.x, sy = p.y, sz = p.z, tx = t.x, ty = t.y, tz = t.z;
-        acc[0] += 1.0;
-        acc[1] += sx;
-        acc[2] += sy;
-        acc[3] += sz;
-        acc[4] += tx;
-        acc[5] += ty;
-        acc[6] += tz;
-        acc[7] += tx * sx;
-        acc[8] += tx * sy;
-        acc[9] += tx * sz;
-        acc[10] += ty * sx;
-        acc[11] += ty * sy;
-        acc[12] += ty * sz;
-        acc[13] += tz * sx;
-        acc[14] += tz * sy;
-        acc[15] += tz * sz;
-        acc[16] += static_cast<double>(best.d2);
-      } else {
-        acc[0] += 1.0;
-        acc[28] += static_cast<double>(best.d2);
-        const float4 nr = L.grid.normals[best.j];
-        // [PCL] transformation_estimation_point_to_plane_lls.hpp: pairs with a non-finite
-        // member are left out of the normal equations (they still count as correspondences)
-        if (finite3(t.x, t.y, t.z) && finite3(nr.x, nr.y, nr.z)) {
-          const float sx = p.x, sy = p.y, sz = p.z, dx = t.x, dy = t.y, dz = t.z;
-          const float nx = nr.x, ny = nr.y, nz = nr.z;
-          const double a = nz * sy - ny * sz;  // float expressions, widened afterwards
-          const double b = nx * sz - nz * sx;
-          const double c = ny * sx - nx * sy;
-          acc[1] += a * a;
-          acc[2] += a * b;
-          acc[3] += a * c;
-          acc[4] += a * nx;
-          acc[5] += a * ny;
-          acc[6] += a * nz;
-          acc[7] += b * b;
-          acc[8] += b * c;
-          acc[9] += b * nx;
-          acc[10] += b * ny;
-          acc[11] += b * nz;
-          acc[12] += c * c;
-          acc[13] += c * nx;
-          acc[14] += c * ny;
-          acc[15] += c * nz;
-          acc[16] += nx * nx;  // float products
-          acc[17] += nx * ny;
-          acc[18] += nx * nz;
-          acc[19] += ny * ny;
-          acc[20] += ny * nz;
-          acc[21] += nz * nz;
-          const double d = nx * dx + ny * dy + nz * dz - nx * sx - ny * sy - nz * sz;
-          acc[22] += a * d;
-          acc[23] += b * d;
-          acc[24] += c * d;
-          acc[25] += nx * d;
-          acc[26] += ny * d;
-          acc[27] += nz * d;
-        }
-      }
-    }
+    if (keep && lane_in_group == 0) accumulate_pair<EST>(L.grid, p, best, acc);
   }
 
   if (L.dbg) t_dbg[1] = global_ns();
@@ -621,7 +640,11 @@ int launch_fitness_g(peb_ctx* ctx, int G, const IcpLaunch& L, size_t H) {
 // blocks per hypothesis for a group width: one block handles kIcpThreads / G queries per pass;
 // a single align spreads over the whole chip, batched aligns give every hypothesis a few blocks
 // and let grid.y fill the machine
+// factor = blocks per SM and launch, summed over all hypotheses.  0 = measured defaults (B200, C4):
+// large batches like many small blocks (their cold launch is uneven), small batches pay the fixed
+// cost of a block (state load, 17-value reduction, ticket) per ~10 queries a thread and like fewer
 int blocks_for(int n, size_t H, int G, int factor) {
+  if (factor <= 0) factor = H >= 512 ? 64 : (H >= 256 ? 32 : 16);
   const int want = ceil_div(std::max(n, 1), kIcpThreads / G);
   int bph;
   if (H == 1)
@@ -671,6 +694,21 @@ int prepare_launch(peb_ctx* ctx, size_t H, const peb_icp_params* prm, IcpLaunch&
   return PEB_OK;
 }
 
+}  // namespace
+
+namespace {
+int ensure_sub_streams(peb_ctx* ctx, int S) {
+  while (static_cast<int>(ctx->sub_streams.size()) < S) {
+    cudaStream_t st;
+    cudaEvent_t ev;
+    PEB_CUDA(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    PEB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    ctx->sub_streams.push_back(st);
+    ctx->join_events.push_back(ev);
+  }
+  if (!ctx->fork_event) PEB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+  return PEB_OK;
+}
 }  // namespace
 
 int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_icp_params* prm,
@@ -735,6 +773,63 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
   // profile 1: one event pair around the whole run of iteration launches (nothing between the
   // launches, so PDL overlap is what the bench measures); profile 2: a pair around every launch
   const bool per_launch = ctx->profile_level >= 2;
+
+  // Batched aligns run as S independent chains of launches on S streams, each over a contiguous
+  // share of the hypotheses: while one chain drains the tail of a launch (its last blocks, the
+  // per-hypothesis solves) the other chains' blocks fill the idle SMs.  Hypotheses never interact,
+  // so the chains need no synchronisation between the fork and the join.
+  int S = 1;
+  if (!single_mode && !per_launch && !ctx->debug_timers) {
+    const size_t want = ctx->batch_streams > 0 ? ctx->batch_streams : (H >= 512 ? 4 : 2);  // measured, B200 C4
+    S = static_cast<int>(std::min<size_t>(want, H / 16));
+  }
+  if (S > 1) {
+    PEB_TRY(ensure_sub_streams(ctx, S));
+    PEB_TRY(prof_mark(ctx, 0));
+    PEB_CUDA(ctx, cudaEventRecord(ctx->fork_event, ctx->stream));
+    const size_t per = (H + S - 1) / S;
+    struct StreamSwap {  // the launch macros use ctx->stream
+      peb_ctx* c;
+      cudaStream_t keep;
+      StreamSwap(peb_ctx* c_, cudaStream_t s) : c(c_), keep(c_->stream) { c->stream = s; }
+      ~StreamSwap() { c->stream = keep; }
+    };
+    auto chunk_of = [&](const IcpLaunch& base, size_t h0) {
+      IcpLaunch C = base;
+      C.states += h0;
+      C.work += h0 * static_cast<size_t>(n);
+      C.slack += h0 * static_cast<size_t>(n);
+      C.partials += h0 * static_cast<size_t>(base.blocks_per_hyp) * kAccMax;
+      C.results += h0;
+      if (C.anchors) C.anchors += h0 * static_cast<size_t>(C.n_anchor);
+      return C;
+    };
+    // the anchor launch above ran on the main stream for all hypotheses: the fork event orders it
+    for (int c = 0; c < S; ++c) PEB_CUDA(ctx, cudaStreamWaitEvent(ctx->sub_streams[c], ctx->fork_event, 0));
+    for (int it = 0; it <= launches; ++it) {
+      for (int c = 0; c < S; ++c) {
+        const size_t h0 = c * per, h1 = std::min(H, h0 + per);
+        if (h0 >= h1) continue;
+        StreamSwap swap(ctx, ctx->sub_streams[c]);
+        if (it == 0) {
+          PEB_TRY(launch_one_iteration_g(ctx, g_cold, chunk_of(Lc, h0), h1 - h0, prm->estimator));
+        } else if (it < launches) {
+          PEB_TRY(launch_one_iteration_g(ctx, g_warm, chunk_of(Lw, h0), h1 - h0, prm->estimator));
+        } else {
+          PEB_TRY(launch_fitness_g(ctx, g_warm, chunk_of(Lw, h0), h1 - h0));
+          PEB_CUDA(ctx, cudaEventRecord(ctx->join_events[c], ctx->stream));
+        }
+      }
+    }
+    for (int c = 0; c < S; ++c) PEB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->join_events[c], 0));
+    PEB_TRY(prof_mark(ctx, 1));
+    if (ctx->profile) {
+      ctx->prof_launches = 1;  // one record: the span of all chains (iterations + fitness)
+      ctx->prof_span_launches = launches;
+    }
+    return PEB_OK;
+  }
+
   if (!per_launch) PEB_TRY(prof_mark(ctx, 0));
   for (int it = 0; it < launches; ++it) {
     if (per_launch) PEB_TRY(prof_mark(ctx, 2 * it));

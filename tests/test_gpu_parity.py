@@ -349,7 +349,7 @@ def test_icp_batch_equals_single_and_oracle(pcl, ctx, oracle, scene_small):
 
 
 @pytest.mark.parametrize("option,value", [("warm_start", 0), ("cert_margin_x1000", 300), ("nn_group", 8), ("anchor_seed", 0),
-                                          ("pdl", 0)])
+                                          ("pdl", 0), ("batch_streams", 1)])
 def test_speed_options_never_change_results(pcl, oracle, scene_small, option, value):
     """warm start, search-skipping certificates and the cold lane-group width are exactness-preserving:
     every combination must give the bit-identical answer."""
