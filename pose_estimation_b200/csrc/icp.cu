@@ -753,7 +753,7 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
   Lc.warm = 0;
   // (a single align has too few patches to fill the machine with anchor searches: their latency
   //  would exceed what the seeds save; its cold launch keeps the plain ring search)
-  if (ctx->warm_start && ctx->anchor_seed && g_cold == 1 && n >= 64 && H * static_cast<size_t>(n) >= (1u << 20)) {
+  if (ctx->warm_start && ctx->anchor_seed && g_cold == 1 && n >= 64 && H * static_cast<size_t>(n) >= (1u << 20) && H <= 65535) {
     const int n_anchor = ceil_div(n, 32);
     PEB_CUDA(ctx, ctx->anchors.ensure(H * static_cast<size_t>(n_anchor) * sizeof(int)));
     Lc.n_anchor = n_anchor;
@@ -782,7 +782,12 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
   if (!single_mode && !per_launch && !ctx->debug_timers) {
     const size_t want = ctx->batch_streams > 0 ? ctx->batch_streams : (H >= 512 ? 4 : 2);  // measured, B200 C4
     S = static_cast<int>(std::min<size_t>(want, H / 16));
+    // gridDim.y carries the hypothesis index: very large batches are split into more chains
+    S = std::max<int>(S, static_cast<int>((H + 32767) / 32768));
   }
+  if (S <= 1 && H > 65535)
+    return fail(ctx, PEB_E_UNSUPPORTED, "align_batch: %zu hypotheses in one launch (profile level 2 / debug timers "
+                "allow at most 65535)", H);
   if (S > 1) {
     PEB_TRY(ensure_sub_streams(ctx, S));
     PEB_TRY(prof_mark(ctx, 0));
