@@ -121,6 +121,30 @@ PEB_API int peb_voxel_grid(peb_ctx* ctx, const void* pts, size_t n, size_t strid
                            float leaf_x, float leaf_y, float leaf_z, unsigned min_pts,
                            float* out_xyz4, size_t* out_n);
 
+/* ---- scene pre-filter: the deterministic part of PoseEstimation::create_surface_match_pc -------- */
+/* (the step right before the path)
+ *   pcl::removeNaNFromPointCloud                      pose_estimation/src/pose_estimation.cpp:246-248
+ *   PoseEstimation::filter_points (sphere filter)     pose_estimation/src/pose_estimation.cpp:347-372
+ *   the 5 mm band removal of remove_planes            pose_estimation/src/pose_estimation.cpp:309-333
+ * applied in that order, in one fused pass; survivors keep their original order (the reference's
+ * own order depends on OpenMP scheduling).  The RANSAC fit that produces the plane coefficients
+ * (pcl::SACSegmentation, random sampling) is not part of this call: coefficients are inputs. */
+enum { PEB_PREFILTER_MAX_PLANES = 8 };
+typedef struct peb_prefilter_params {
+  int32_t use_sphere;          /* filter_points() is applied                                   */
+  int32_t remove_inliers;      /* filter_out == "inliers": drop the points INSIDE the sphere     */
+  float sphere_center[3];      /* filter_pose_[0..2]                                             */
+  float sphere_radius;         /* filter_radius_                                                 */
+  int32_t n_planes;            /* plane coefficient sets applied one after the other             */
+  float plane_band;            /* 0.005 in the reference                                         */
+  float planes[4 * PEB_PREFILTER_MAX_PLANES]; /* a b c d of ax + by + cz + d = 0                 */
+} peb_prefilter_params;
+/* out_xyz4 must hold n x 4 floats; records are x y z 1 */
+PEB_API int peb_scene_prefilter(peb_ctx* ctx, const void* pts, size_t n, size_t stride,
+                                const peb_prefilter_params* params, float* out_xyz4, size_t* out_n);
+PEB_API int peb_scene_prefilter_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, const peb_prefilter_params* params,
+                                    void* d_out_xyz4, size_t* out_n);
+
 /* ---- pcl::NormalEstimation<PointXYZ,Normal>::compute  [PCL] features/.../impl/normal_3d.hpp */
 /* out_normal8: n x 8 floats = pcl::Normal memory image (nx ny nz 0 | curvature 0 0 0). */
 PEB_API int peb_normals_knn(peb_ctx* ctx, const void* pts, size_t n, size_t stride, int k,

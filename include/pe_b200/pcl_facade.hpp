@@ -59,6 +59,40 @@ class Context {
   peb_ctx* ctx_ = nullptr;
 };
 
+// NaN removal + sphere filter + plane-band removal in front of VoxelGrid: the deterministic part of
+// PoseEstimation::create_surface_match_pc (pose_estimation/src/pose_estimation.cpp:246-261, 309-333, 347-372)
+class ScenePrefilter {
+ public:
+  explicit ScenePrefilter(Context& c) : c_(c) {
+    std::memset(&p_, 0, sizeof(p_));
+    p_.plane_band = 0.005f;
+  }
+  void setInputCloud(const void* pts, size_t n, size_t stride = 16) { in_ = {pts, n, stride}; }
+  // filter_out == "inliers" drops the points inside the sphere, anything else keeps only them
+  void setSphereFilter(const float center[3], float radius, const std::string& filter_out) {
+    p_.use_sphere = radius > 0.0f ? 1 : 0;
+    p_.remove_inliers = filter_out == "inliers" ? 1 : 0;
+    for (int i = 0; i < 3; ++i) p_.sphere_center[i] = center[i];
+    p_.sphere_radius = radius;
+  }
+  void addPlane(float a, float b, float c, float d) {
+    if (p_.n_planes >= PEB_PREFILTER_MAX_PLANES) throw Error(PEB_E_INVALID_ARG, "ScenePrefilter: too many planes");
+    float* v = p_.planes + 4 * p_.n_planes++;
+    v[0] = a, v[1] = b, v[2] = c, v[3] = d;
+  }
+  void filter(std::vector<float>& out_xyz4) {
+    out_xyz4.resize(4 * (in_.size ? in_.size : 1));
+    size_t m = 0;
+    c_.check(peb_scene_prefilter(c_.get(), in_.data, in_.size, in_.stride, &p_, out_xyz4.data(), &m));
+    out_xyz4.resize(4 * m);
+  }
+
+ private:
+  Context& c_;
+  CloudView in_;
+  peb_prefilter_params p_;
+};
+
 class VoxelGrid {
  public:
   explicit VoxelGrid(Context& c) : c_(c) {}

@@ -51,6 +51,37 @@ class IcpResult(C.Structure):
         return np.array(self.T, dtype=np.float32).reshape(4, 4).T.copy()
 
 
+class PrefilterParams(C.Structure):
+    """peb_prefilter_params (include/pe_b200.h)."""
+
+    _fields_ = [
+        ("use_sphere", C.c_int32),
+        ("remove_inliers", C.c_int32),
+        ("sphere_center", C.c_float * 3),
+        ("sphere_radius", C.c_float),
+        ("n_planes", C.c_int32),
+        ("plane_band", C.c_float),
+        ("planes", C.c_float * 32),
+    ]
+
+
+def prefilter_params(sphere=None, remove_inliers=False, planes=(), band=0.005) -> PrefilterParams:
+    """sphere = (cx, cy, cz, radius) or None; planes = iterable of (a, b, c, d)."""
+    f = PrefilterParams()
+    if sphere is not None:
+        f.use_sphere = 1
+        f.remove_inliers = int(bool(remove_inliers))
+        f.sphere_center[:] = [float(v) for v in sphere[:3]]
+        f.sphere_radius = float(sphere[3])
+    planes = list(planes)
+    f.n_planes = len(planes)
+    f.plane_band = float(band)
+    for k, pl in enumerate(planes):
+        for j in range(4):
+            f.planes[4 * k + j] = float(pl[j])
+    return f
+
+
 DBL_MAX = float(np.finfo(np.float64).max)
 
 
@@ -144,6 +175,8 @@ class Oracle:
         L.orc_point_to_plane_lls.argtypes = [_vp, _vp, _vp, _sz, _vp]
         L.orc_criteria_script.argtypes = [_vp, _vp, _vp, _sz, _vp, _vp]
         L.orc_max_threads.restype = C.c_int
+        L.orc_scene_prefilter.restype = _sz
+        L.orc_scene_prefilter.argtypes = [_vp, _sz, _sz, _vp, _vp]
 
     # ---- nearest neighbours ------------------------------------------------------------
     def knn(self, target: np.ndarray, queries: np.ndarray, k: int = 1):
@@ -176,6 +209,13 @@ class Oracle:
         m = self.L.orc_voxel_grid(p.ctypes.data, p.shape[0], p.strides[0], leaf[0], leaf[1], leaf[2], min_pts,
                                   out.ctypes.data, C.byref(unchanged))
         return out[:m].copy(), bool(unchanged.value)
+
+    # ---- scene pre-filter (restates the reference's own code) ----------------------------------
+    def scene_prefilter(self, pts: np.ndarray, params: "PrefilterParams") -> np.ndarray:
+        p = _as_f32(pts)
+        out = np.empty((max(p.shape[0], 1), 4), np.float32)
+        m = self.L.orc_scene_prefilter(p.ctypes.data, p.shape[0], p.strides[0], C.byref(params), out.ctypes.data)
+        return out[:m].copy()
 
     # ---- NormalEstimation ----------------------------------------------------------------
     def normals(self, pts: np.ndarray, k: int, viewpoint=(0.0, 0.0, 0.0), threads: int = 1, want_nn: bool = False):

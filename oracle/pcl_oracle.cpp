@@ -1387,6 +1387,45 @@ ORC_API void orc_criteria_script(const peb_icp_params* prm, const float* incs, c
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Scene pre-filter: restates the reference's OWN code (verified in /root/reference), in order:
+//   pcl::removeNaNFromPointCloud          pose_estimation/src/pose_estimation.cpp:246-248
+//   PoseEstimation::filter_points         pose_estimation/src/pose_estimation.cpp:347-372
+//   the band test of remove_planes        pose_estimation/src/pose_estimation.cpp:309-333
+// Survivors are kept in original order (the reference's order depends on OpenMP scheduling of its
+// push_back under `omp critical`; ExtractIndices with setNegative(true) restores index order).
+// ------------------------------------------------------------------------------------------
+ORC_API size_t orc_scene_prefilter(const void* pts, size_t n, size_t stride, const peb_prefilter_params* f,
+                                   float* out_xyz4) {
+  size_t m = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const float* p = orc::rec(pts, i, stride);
+    const float x = p[0], y = p[1], z = p[2];
+    if (!std::isfinite(x) || !std::isfinite(y) || !std::isfinite(z)) continue;
+    if (f->use_sphere) {
+      float dx = f->sphere_center[0] - x;
+      float dy = f->sphere_center[1] - y;
+      float dz = f->sphere_center[2] - z;
+      float d = std::sqrt(dx * dx + dy * dy + dz * dz);
+      bool inside = d <= f->sphere_radius;
+      if (f->remove_inliers ? inside : !inside) continue;
+    }
+    bool near_plane = false;
+    for (int k = 0; k < f->n_planes && !near_plane; ++k) {
+      const float* c = f->planes + 4 * k;
+      float d = (x * c[0] + y * c[1] + z * c[2] + c[3]) / std::sqrt(x * x + y * y + z * z);
+      if (std::abs(d) <= f->plane_band) near_plane = true;
+    }
+    if (near_plane) continue;
+    out_xyz4[4 * m] = x;
+    out_xyz4[4 * m + 1] = y;
+    out_xyz4[4 * m + 2] = z;
+    out_xyz4[4 * m + 3] = 1.0f;
+    ++m;
+  }
+  return m;
+}
+
 ORC_API int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

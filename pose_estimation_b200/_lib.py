@@ -71,6 +71,20 @@ class IcpResult(C.Structure):
     ]
 
 
+class PrefilterParams(C.Structure):
+    """peb_prefilter_params."""
+
+    _fields_ = [
+        ("use_sphere", C.c_int32),
+        ("remove_inliers", C.c_int32),
+        ("sphere_center", C.c_float * 3),
+        ("sphere_radius", C.c_float),
+        ("n_planes", C.c_int32),
+        ("plane_band", C.c_float),
+        ("planes", C.c_float * 32),
+    ]
+
+
 class GridInfo(C.Structure):
     _fields_ = [
         ("origin", C.c_float * 3),
@@ -94,6 +108,8 @@ SYMBOLS = {
     "peb_ctx_launch_count": (C.c_uint64, [_vp]),
     "peb_ctx_set_int": (_i, [_vp, C.c_char_p, _i]),
     "peb_voxel_grid": (_i, [_vp, _vp, _sz, _sz, _f, _f, _f, C.c_uint, _vp, _pp(_sz)]),
+    "peb_scene_prefilter": (_i, [_vp, _vp, _sz, _sz, _pp(PrefilterParams), _vp, _pp(_sz)]),
+    "peb_scene_prefilter_dev": (_i, [_vp, _vp, _sz, _pp(PrefilterParams), _vp, _pp(_sz)]),
     "peb_normals_knn": (_i, [_vp, _vp, _sz, _sz, _i, _vp, _vp]),
     "peb_normals_knn_ex": (_i, [_vp, _vp, _sz, _sz, _i, _vp, _vp, _vp]),
     "peb_nn_search": (_i, [_vp, _vp, _sz, _sz, _vp, _vp]),

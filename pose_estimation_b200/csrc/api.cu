@@ -285,6 +285,36 @@ PEB_API int peb_voxel_grid(peb_ctx* ctx, const void* pts, size_t n, size_t strid
   return PEB_OK;
 }
 
+// ---- scene pre-filter ----------------------------------------------------------------------------
+PEB_API int peb_scene_prefilter_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, const peb_prefilter_params* params,
+                                    void* d_out_xyz4, size_t* out_n) {
+  if (!ctx || !params || !out_n) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  if (n > 0 && (!d_xyz4 || !d_out_xyz4)) return fail(ctx, PEB_E_INVALID_ARG, "scene_prefilter_dev: null device pointer");
+  if (n > static_cast<size_t>(INT32_MAX) / 2) return fail(ctx, PEB_E_INVALID_ARG, "scene_prefilter: too many points");
+  return scene_prefilter_device(ctx, static_cast<const float4*>(d_xyz4), static_cast<int>(n), params,
+                                static_cast<float4*>(d_out_xyz4), out_n);
+}
+
+PEB_API int peb_scene_prefilter(peb_ctx* ctx, const void* pts, size_t n, size_t stride, const peb_prefilter_params* params,
+                                float* out_xyz4, size_t* out_n) {
+  if (!ctx || !params || !out_n) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  *out_n = 0;
+  PEB_TRY(check_cloud(ctx, "scene_prefilter", pts, n, stride));
+  if (n > 0 && !out_xyz4) return fail(ctx, PEB_E_INVALID_ARG, "scene_prefilter: null output");
+  PEB_CUDA(ctx, ctx->vg_in.ensure(n * sizeof(float4)));
+  PEB_CUDA(ctx, ctx->vg_out.ensure(n * sizeof(float4)));
+  PEB_TRY(upload_cloud(ctx, pts, n, stride, 1.0f, ctx->vg_in.as<float4>()));
+  size_t m = 0;
+  PEB_TRY(scene_prefilter_device(ctx, ctx->vg_in.as<float4>(), static_cast<int>(n), params, ctx->vg_out.as<float4>(), &m));
+  if (m > 0)
+    PEB_CUDA(ctx, cudaMemcpyAsync(out_xyz4, ctx->vg_out.p, m * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  PEB_TRY(sync(ctx));
+  *out_n = m;
+  return PEB_OK;
+}
+
 // ---- NormalEstimation ---------------------------------------------------------------------------
 PEB_API int peb_normals_knn_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, int k, const float viewpoint[3],
                                 void* d_out_normal8) {

@@ -237,6 +237,9 @@ int nn_bruteforce_device(peb_ctx* ctx, const float4* d_q, int nq, int32_t* d_idx
 // voxel.cu
 int voxel_grid_device(peb_ctx* ctx, const float4* d_in, int n, float lx, float ly, float lz, unsigned min_pts,
                       float4* d_out, size_t* out_n);
+// prefilter.cu
+int scene_prefilter_device(peb_ctx* ctx, const float4* d_in, int n, const peb_prefilter_params* prm, float4* d_out,
+                           size_t* out_n);
 // normals.cu
 int normals_knn_device(peb_ctx* ctx, const float4* d_in, int n, int k, const float vp[3], float* d_out8,
                        int32_t* d_out_nn /*nullable, n x k original indices*/);

@@ -17,7 +17,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import IcpParams, IcpResult, GridInfo, lib
+from ._lib import IcpParams, IcpResult, GridInfo, PrefilterParams, lib
 
 DBL_MAX = float(np.finfo(np.float64).max)
 
@@ -143,6 +143,51 @@ def default_context() -> Context:
     if _default_ctx is None:
         _default_ctx = Context(0)
     return _default_ctx
+
+
+class ScenePrefilter:
+    """The deterministic part of PoseEstimation::create_surface_match_pc
+    (pose_estimation/src/pose_estimation.cpp:246-261): NaN removal, the optional sphere filter around the
+    last pose (filter_points, :347-372) and the 5 mm band removal of remove_planes (:309-333) for plane
+    coefficients the caller supplies (the RANSAC fit is not part of this path)."""
+
+    def __init__(self, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self._input = None
+        self.params = PrefilterParams()
+        self.params.plane_band = 0.005
+
+    def setInputCloud(self, cloud):
+        self._input = _cloud(cloud)
+
+    def setSphereFilter(self, center, radius: float, filter_out: str = "outliers"):
+        """filter_out == "inliers" removes the points inside the sphere, anything else keeps only them
+        (EstimatePose.srv: filter_out / filter_radius)."""
+        self.params.use_sphere = 1 if radius > 0 else 0
+        self.params.remove_inliers = 1 if filter_out == "inliers" else 0
+        self.params.sphere_center[:] = [float(v) for v in center[:3]]
+        self.params.sphere_radius = float(radius)
+
+    def addPlane(self, a: float, b: float, c: float, d: float):
+        k = self.params.n_planes
+        if k >= 8:
+            raise PebError(-1, "ScenePrefilter: at most 8 planes")
+        for j, v in enumerate((a, b, c, d)):
+            self.params.planes[4 * k + j] = float(v)
+        self.params.n_planes = k + 1
+
+    def setPlaneBand(self, band: float):
+        self.params.plane_band = float(band)
+
+    def filter(self) -> np.ndarray:
+        if self._input is None:
+            raise ValueError("ScenePrefilter.filter: no input cloud (setInputCloud)")
+        p = self._input
+        out = np.empty((max(p.shape[0], 1), 4), np.float32)
+        m = C.c_size_t(0)
+        self.ctx.check(lib.peb_scene_prefilter(self.ctx.handle, p.ctypes.data, p.shape[0], _stride(p), C.byref(self.params),
+                                               out.ctypes.data, C.byref(m)))
+        return out[: m.value].copy()
 
 
 class VoxelGrid:

@@ -530,3 +530,44 @@ def test_normals_edge_cases(pcl, ctx, oracle):
     with pytest.raises(pcl.PebError) as e:
         ne.compute()
     assert e.value.code == -6
+
+
+# ---- scene pre-filter ----------------------------------------------------------
+def test_scene_prefilter_bit_exact(pcl, ctx, oracle):
+    from oracle import prefilter_params
+
+    rng = np.random.default_rng(31)
+    surf = synth.Surface(31)
+    scene = synth.render_scene(surf, synth.default_gt_pose(rng), rng, 486, 300)
+    scene[5, :3] = 0.0
+    plane = (0.0, -0.0872, 0.9962, -0.747)
+    for sphere, remove_inliers, planes in ((None, False, []), ((0.0, 0.0, 0.7, 0.08), False, []),
+                                           ((0.0, 0.0, 0.7, 0.08), True, [plane]), (None, False, [plane, (1.0, 0.0, 0.0, 0.1)])):
+        pf = pcl.ScenePrefilter(ctx)
+        pf.setInputCloud(scene)
+        if sphere is not None:
+            pf.setSphereFilter(sphere[:3], sphere[3], "inliers" if remove_inliers else "outliers")
+        for pl in planes:
+            pf.addPlane(*pl)
+        out = pf.filter()
+        ref = oracle.scene_prefilter(scene, prefilter_params(sphere, remove_inliers, planes, 0.005))
+        assert out.shape == ref.shape and len(out) > 0
+        assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))  # same survivors, original order, same bits
+    # edge cases: empty, all NaN, everything filtered out; 12-byte records
+    pf = pcl.ScenePrefilter(ctx)
+    pf.setInputCloud(np.empty((0, 4), np.float32))
+    assert pf.filter().shape == (0, 4)
+    pf.setInputCloud(np.full((9, 4), np.nan, np.float32))
+    assert pf.filter().shape == (0, 4)
+    pf.setSphereFilter((10.0, 10.0, 10.0), 0.01)
+    pf.setInputCloud(scene)
+    assert pf.filter().shape == (0, 4)
+    pf3 = pcl.ScenePrefilter(ctx)
+    pf3.setInputCloud(np.ascontiguousarray(scene[:, :3]))
+    assert np.array_equal(pf3.filter(), oracle.scene_prefilter(scene, prefilter_params()))
+    # the chain the node would run: prefilter -> VoxelGrid
+    vg = pcl.VoxelGrid(ctx)
+    vg.setInputCloud(pf3.filter())
+    vg.setLeafSize(0.003)
+    ref_ds, _ = oracle.voxel_grid(oracle.scene_prefilter(scene, prefilter_params()), 0.003)
+    assert np.array_equal(vg.filter().view(np.uint32), ref_ds.view(np.uint32))
