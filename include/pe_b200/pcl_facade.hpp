@@ -231,6 +231,71 @@ class IterativeClosestPoint {
   size_t n_src_ = 0;
 };
 
+// ---- the step right after the path: host-side, no device work ----------------
+// Which refined hypothesis the node returns: pose_estimation/src/opencv_surface_match.cpp:100-124.
+// Most votes wins; but if the matcher produced more than 5 results in total, the lowest residual among
+// the refined poses with more than 400 votes overrides it (the loop keeps the LAST assignment, so a later
+// pose with more votes still takes over — reproduced as written).
+inline size_t select_best_pose(const int* num_votes, const double* residual, size_t n_subset, size_t n_results_total) {
+  int max_votes = 0;
+  float min_res = 10000.0f;
+  size_t best_idx = 0;
+  for (size_t i = 0; i < n_subset; ++i) {
+    if (num_votes[i] > max_votes) {
+      max_votes = num_votes[i];
+      best_idx = i;
+    }
+    if (n_results_total > 5) {
+      if (residual[i] < min_res && num_votes[i] > 400) {
+        min_res = static_cast<float>(residual[i]);
+        best_idx = i;
+      }
+    }
+  }
+  return best_idx;
+}
+
+// rotation part of a column-major 4x4 -> unit quaternion (w, x, y, z), w >= 0
+inline void rotation_to_quat(const float* T16, double q[4]) {
+  const double m00 = T16[0], m10 = T16[1], m20 = T16[2], m01 = T16[4], m11 = T16[5], m21 = T16[6], m02 = T16[8],
+               m12 = T16[9], m22 = T16[10];
+  const double tr = m00 + m11 + m22;
+  if (tr > 0.0) {
+    const double s = std::sqrt(tr + 1.0) * 2.0;
+    q[0] = 0.25 * s, q[1] = (m21 - m12) / s, q[2] = (m02 - m20) / s, q[3] = (m10 - m01) / s;
+  } else if (m00 > m11 && m00 > m22) {
+    const double s = std::sqrt(1.0 + m00 - m11 - m22) * 2.0;
+    q[0] = (m21 - m12) / s, q[1] = 0.25 * s, q[2] = (m01 + m10) / s, q[3] = (m02 + m20) / s;
+  } else if (m11 > m22) {
+    const double s = std::sqrt(1.0 + m11 - m00 - m22) * 2.0;
+    q[0] = (m02 - m20) / s, q[1] = (m01 + m10) / s, q[2] = 0.25 * s, q[3] = (m12 + m21) / s;
+  } else {
+    const double s = std::sqrt(1.0 + m22 - m00 - m11) * 2.0;
+    q[0] = (m10 - m01) / s, q[1] = (m02 + m20) / s, q[2] = (m12 + m21) / s, q[3] = 0.25 * s;
+  }
+  if (q[0] < 0.0)
+    for (int i = 0; i < 4; ++i) q[i] = -q[i];
+}
+
+// The 7 floats the node publishes, {x, y, z, qx, qy, qz, qw} (pose_estimation/include/pose_estimation.hpp:83-88).
+// reference_layout = true reproduces opencv_surface_match.cpp:133-142 literally: pose[5] (qz) is never
+// written and pose[6] receives q[3] and is then overwritten with q[0] — so qz is lost and left 0.
+inline void pack_pose(const float* T16, float pose7[7], bool reference_layout = false) {
+  double q[4];
+  rotation_to_quat(T16, q);
+  for (int i = 0; i < 3; ++i) pose7[i] = T16[12 + i];
+  pose7[3] = static_cast<float>(q[1]);
+  pose7[4] = static_cast<float>(q[2]);
+  if (reference_layout) {
+    pose7[5] = 0.0f;
+    pose7[6] = static_cast<float>(q[3]);
+    pose7[6] = static_cast<float>(q[0]);
+  } else {
+    pose7[5] = static_cast<float>(q[3]);
+    pose7[6] = static_cast<float>(q[0]);
+  }
+}
+
 class IterativeClosestPointWithNormals : public IterativeClosestPoint {
  public:
   explicit IterativeClosestPointWithNormals(Context& c) : IterativeClosestPoint(c, PEB_ESTIMATOR_POINT_TO_PLANE_LLS) {}

@@ -1,0 +1,74 @@
+"""Selection and packing of the refined pose: the Python mirror against scipy and
+against the C++ functions of the facade (compiled with plain g++, no GPU)."""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+from scipy.spatial.transform import Rotation
+
+from pose_estimation_b200 import poses
+from pose_estimation_b200.testing import synth
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_quaternion_packing_matches_scipy():
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        R = Rotation.random(random_state=rng.integers(1 << 31)).as_matrix()
+        T = synth.make_pose(R, rng.normal(size=3))
+        p = poses.pack_pose(T)
+        q = Rotation.from_matrix(R).as_quat()  # x y z w
+        q = -q if q[3] < 0 else q
+        assert np.allclose(p[3:], q, atol=1e-6) and np.allclose(p[:3], T[:3, 3], atol=1e-6)
+        ref = poses.pack_pose(T, reference_layout=True)
+        assert ref[5] == 0.0 and np.allclose(ref[[0, 1, 2, 3, 4, 6]], p[[0, 1, 2, 3, 4, 6]])  # the reference loses qz
+
+
+def test_selection_rule_of_the_reference():
+    # most votes wins when the matcher returned <= 5 results
+    assert poses.select_best_pose([100, 900, 500], [0.3, 0.2, 0.1], 3) == 1
+    # > 5 results: lowest residual among > 400 votes overrides ...
+    assert poses.select_best_pose([100, 900, 500, 50, 40, 30], [0.3, 0.2, 0.1, 0.0, 0.0, 0.0], 8) == 2
+    # ... but a later pose with more votes takes over again (last assignment wins, as written)
+    assert poses.select_best_pose([500, 900], [0.1, 0.2], 8) == 1
+    assert poses.select_best_pose([], [], 0) == 0
+
+
+def test_cpp_functions_agree_with_the_python_mirror(tmp_path):
+    src = tmp_path / "poses_check.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include "pe_b200/pcl_facade.hpp"
+int main() {
+  const int votes[6] = {100, 900, 500, 50, 40, 30};
+  const double res[6] = {0.3, 0.2, 0.1, 0.0, 0.0, 0.0};
+  std::printf("%zu %zu\n", pe_b200::select_best_pose(votes, res, 3, 3), pe_b200::select_best_pose(votes, res, 6, 8));
+  float T[16];
+  while (std::scanf("%f %f %f %f %f %f %f %f %f %f %f %f %f %f %f %f", T, T+1, T+2, T+3, T+4, T+5, T+6, T+7, T+8, T+9, T+10,
+                    T+11, T+12, T+13, T+14, T+15) == 16) {
+    float a[7], b[7];
+    pe_b200::pack_pose(T, a, false);
+    pe_b200::pack_pose(T, b, true);
+    for (int i = 0; i < 7; ++i) std::printf("%.9g ", a[i]);
+    for (int i = 0; i < 7; ++i) std::printf("%.9g ", b[i]);
+    std::printf("\n");
+  }
+}
+''')
+    exe = tmp_path / "poses_check"
+    r = subprocess.run(["g++", "-std=c++17", "-I", str(ROOT / "include"), str(src), "-o", str(exe), "-L",
+                        str(ROOT / "pose_estimation_b200"), "-lpe_b200", f"-Wl,-rpath,{ROOT / 'pose_estimation_b200'}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rng = np.random.default_rng(1)
+    Ts = [synth.make_pose(Rotation.random(random_state=int(rng.integers(1 << 31))).as_matrix(), rng.normal(size=3))
+          for _ in range(50)]
+    inp = "\n".join(" ".join(f"{v:.9g}" for v in np.asarray(T, np.float32).T.reshape(-1)) for T in Ts)
+    out = subprocess.run([str(exe)], input=inp, capture_output=True, text=True).stdout.strip().splitlines()
+    assert out[0].split() == ["1", "2"]
+    for T, line in zip(Ts, out[1:]):
+        vals = np.array([float(v) for v in line.split()], np.float32)
+        T32 = np.asarray(T, np.float32)
+        assert np.allclose(vals[:7], poses.pack_pose(T32), atol=1e-6)
+        assert np.allclose(vals[7:], poses.pack_pose(T32, reference_layout=True), atol=1e-6)
