@@ -223,6 +223,11 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
     ctx->blocks_factor = value;
     return PEB_OK;
   }
+  if (!strcmp(key, "coop_max_rows")) {
+    if (value < 0 || value > (1 << 20)) return fail(ctx, PEB_E_INVALID_ARG, "coop_max_rows out of [0, 2^20]");
+    ctx->coop_max_rows = value;
+    return PEB_OK;
+  }
   if (!strcmp(key, "pdl")) {
     ctx->use_pdl = value != 0;
     return PEB_OK;

@@ -101,6 +101,7 @@ struct peb_ctx {
   float grid_occupancy = 2.0f;  // wanted mean points per occupied cell of the target grid
   bool warm_start = true;       // iterations >= 1 seed the search with the previous match
   bool anchor_seed = true;      // iteration 0: one cold search per 32-point patch seeds the patch
+  int coop_max_rows = 1024;     // first iteration of a batch: a patch verifies its 32 candidates together (nn_search.cuh) up to this many grid rows
   float seed_guard = 10.0f;     // seeds farther than this many cells from the query are not used
   int batch_streams = 0;        // batched aligns: independent chains of launches (see icp.cu); 0 = auto
   std::vector<cudaStream_t> sub_streams;

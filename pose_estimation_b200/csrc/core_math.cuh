@@ -253,6 +253,21 @@ PEB_HD NnBest grid_nn_seeded(const GridView& g, float qx, float qy, float qz, in
   return best;
 }
 
+// The first half of grid_nn_seeded: the candidate only (an upper bound that still has to be verified
+// by a ball search — the caller's own, or the warp-cooperative one of nn_search.cuh).
+PEB_HD NnBest grid_nn_seed_probe(const GridView& g, float qx, float qy, float qz, int j_seed, float sx, float sy, float sz) {
+  NnBest best;
+  const float4 t = g.pts[j_seed];
+  best.d2 = l2_simple(qx, qy, qz, t.x, t.y, t.z);
+  best.idx = point_index(t);
+  best.j = j_seed;
+  const int cx = grid_coord(t.x + (qx - sx), g.ox, g.inv_h, g.dx);
+  const int cy = grid_coord(t.y + (qy - sy), g.oy, g.inv_h, g.dy);
+  const int cz = grid_coord(t.z + (qz - sz), g.oz, g.inv_h, g.dz);
+  grid_scan_ring(g, qx, qy, qz, cx, cy, cz, 1, true, 0, 1, best);
+  return best;
+}
+
 // The same search with a certificate.
 // Certificate: the ball is grown by `margin`, and the search also tracks the runner-up distance.
 // On return *slack_out is a lower bound on (distance of any OTHER target point) - (distance of the

@@ -44,6 +44,7 @@ struct IcpLaunch {
   const int* anchors;    // nullable, H x n_anchor: match (sorted position) of the first point of every 32-point patch
   int n_anchor;
   float seed_guard2;     // (cells)^2: an anchor farther than this from the query is not used as a seed
+  int coop_max_rows;     // first iteration: patches verify their candidates together while the common region has at most this many grid rows (0: never)
   unsigned long long* dbg;  // nullable: 8 timestamps (ns, %globaltimer) per launch, written by the last block
   int launch_idx;
   IcpState* states;      // H
@@ -283,32 +284,146 @@ __device__ __forceinline__ void accumulate_pair(const GridView& g, const float4&
   accumulate_pair_impl<EST, NACC>(g, p, best, acc);
 }
 
-// first-iteration search of query p seeded by its patch's anchor (icp_anchor_kernel), or cold
-__device__ __forceinline__ NnBest first_iteration_search(const IcpLaunch& L, int h, int i, const float4& p,
-                                                         const float* T, bool apply, const int* anchors) {
-  int j_seed = anchors ? __ldcg(anchors + static_cast<size_t>(h) * L.n_anchor + (i >> 5)) : -1;
-  if (j_seed >= 0) {
-    // the patch's anchor query, recomputed (same arithmetic as the caller's): where the seed was found from
-    float4 a = L.src[i & ~31];
-    if (apply) {
-      float ox, oy, oz;
-      transform_icp(T, a.x, a.y, a.z, ox, oy, oz);
-      a.x = ox;
-      a.y = oy;
-      a.z = oz;
+// First-iteration search of the 32 queries of a warp (one source patch), all lanes together.  A query
+// gets its candidate from its patch's anchor (icp_anchor_kernel); the candidates are then verified by
+// the warp as a whole (nn_search.cuh : grid_nn_coop_verify) or, for spread-out patches, one by one.
+// Queries without a usable seed search cold.
+__device__ __forceinline__ NnBest first_iteration_search(const IcpLaunch& L, int h, int i, bool valid, const float4& p,
+                                                         const float* T, bool apply, CoopTile* tile) {
+  NnBest best;
+  best.d2 = pos_inf();
+  best.idx = -1;
+  best.j = -1;
+  bool need = false;  // holds a candidate that is not verified yet
+  int group = 0;      // 0: seeded by the own anchor, 1: by the next patch's (the two places are verified separately)
+  if (valid) {
+    // Seed: the match of this patch's anchor (its first point).  A patch is 32 consecutive points of
+    // the cell-sorted source, so it may hold points from two places (the end of one run of cells and
+    // the start of the next); the tail of such a patch continues into the NEXT patch, whose anchor is
+    // then the nearby one.  A seed farther than seed_guard cells would only blow the ball up.
+    int j_seed = -1;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    group = 0;
+    const int patch = i >> 5;
+#pragma unroll 1
+    for (int k = 0; k < 2 && j_seed < 0; ++k) {
+      const int pa = patch + k;
+      if (pa >= L.n_anchor) break;
+      const int js = __ldcg(L.anchors + static_cast<size_t>(h) * L.n_anchor + pa);
+      if (js < 0) continue;
+      // the anchor query, recomputed (same arithmetic as the caller's): where the seed was found from
+      a = L.src[32 * pa];
+      if (apply) {
+        float ox, oy, oz;
+        transform_icp(T, a.x, a.y, a.z, ox, oy, oz);
+        a.x = ox;
+        a.y = oy;
+        a.z = oz;
+      }
+      const float ax = p.x - a.x, ay = p.y - a.y, az = p.z - a.z;
+      if (ax * ax + ay * ay + az * az <= L.seed_guard2 * L.grid.h * L.grid.h) {
+        j_seed = js;
+        group = k;
+      }
     }
-    // a patch that straddles the end of a row of the source grid holds points from two places:
-    // a seed from the other place would only blow the ball up
-    const float ax = p.x - a.x, ay = p.y - a.y, az = p.z - a.z;
-    if (ax * ax + ay * ay + az * az > L.seed_guard2 * L.grid.h * L.grid.h) j_seed = -1;
-    if (j_seed >= 0) return grid_nn_seeded(L.grid, p.x, p.y, p.z, j_seed, a.x, a.y, a.z, L.stop_d2);
+    if (j_seed >= 0) {
+      best = grid_nn_seed_probe(L.grid, p.x, p.y, p.z, j_seed, a.x, a.y, a.z);
+      need = true;
+    } else {
+      best = grid_nn<1>(L.grid, p.x, p.y, p.z, L.stop_d2);
+      PEB_COOP_COUNT_LANE(6);
+    }
   }
-  return grid_nn<1>(L.grid, p.x, p.y, p.z, L.stop_d2);
+  PEB_COOP_COUNT(7, __any_sync(0xFFFFFFFFu, valid && !need) ? 1 : 0);
+#pragma unroll 1
+  for (int k = 0; k < 2; ++k) {
+    const bool mine = need && group == k;
+    bool done = false;
+    if (L.coop_max_rows > 0) done = grid_nn_coop_verify(L.grid, tile, mine, p.x, p.y, p.z, L.stop_d2, L.coop_max_rows, best);
+    if (!done && mine) grid_ball_search(L.grid, p.x, p.y, p.z, L.stop_d2, best);
+  }
+  return best;
 }
 
-template <int G, int EST, int MB, bool CERT>
-__global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_kernel(const IcpLaunch L) {
-  pdl_trigger_and_wait();
+// One query of one ICP iteration: working point i of hypothesis h is moved by T (the previous
+// increment, or the guess in the first iteration), its exact nearest neighbour is searched (seeded
+// by its previous match when there is one), the correspondence is thresholded and added to the
+// estimator's moment sums.  Shared by the per-iteration kernel and the work-queue kernel.
+template <int G, int EST, bool CERT, int NACC>
+__device__ __forceinline__ void icp_query(const IcpLaunch& L, const int h, float4* __restrict__ work, const int i,
+                                          const bool first, const bool apply, const float* T, CoopTile* tile,
+                                          double (&acc)[NACC]) {
+  const int lane_in_group = threadIdx.x & (G - 1);
+  const bool in = i < L.n_src;
+  float4 p = make_float4(0.f, 0.f, 0.f, 1.f);
+  if (in) p = first ? L.src[i] : work[i];
+  const int j_prev = first ? -1 : __float_as_int(p.w);  // last iteration's match (sorted position)
+  const bool valid = in && finite3(p.x, p.y, p.z);
+  float moved = 0.0f;
+  if (valid && apply) {
+    float ox, oy, oz;
+    transform_icp(T, p.x, p.y, p.z, ox, oy, oz);
+    if (CERT) {
+      const float mx = ox - p.x, my = oy - p.y, mz = oz - p.z;
+      moved = sqrtf(mx * mx + my * my + mz * mz);
+    }
+    p.x = ox;
+    p.y = oy;
+    p.z = oz;
+  }
+  // queries of a group run the search together; invalid ones idle through it
+  NnBest best;
+  best.d2 = pos_inf();
+  best.idx = -1;
+  best.j = -1;
+  float slack = -1.0f;
+  if (G == 1 && first && L.anchors) {
+    // (uniform branch: every lane of the warp takes part, valid or not)
+    best = first_iteration_search(L, h, i, valid, p, T, apply, tile);
+    if (CERT && valid) L.slack[static_cast<size_t>(h) * L.n_src + i] = -1.0f;
+  } else if (valid) {
+    float* sl = L.slack + static_cast<size_t>(h) * L.n_src + i;
+    if (G == 1 && L.warm && j_prev >= 0 && j_prev < L.grid.n) {
+      if (CERT) {
+        // certificate of the previous search (core_math.cuh : grid_nn_warm_cert): every other
+        // target point was at least `slack` farther than the match; the point has moved by `moved`
+        slack = *sl - 2.000002f * moved - 1e-5f * L.grid.h;
+        if (slack > 0.0f) {
+          const float4 t = L.grid.pts[j_prev];
+          best.d2 = l2_simple(p.x, p.y, p.z, t.x, t.y, t.z);
+          best.idx = __float_as_int(t.w);
+          best.j = j_prev;
+        } else {
+          best = grid_nn_warm_cert(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2, L.margin, &slack);
+        }
+        *sl = slack;
+      } else {
+        best = grid_nn_warm(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2);
+      }
+    } else {
+      best = grid_nn<G>(L.grid, p.x, p.y, p.z, L.stop_d2);
+      if (CERT && lane_in_group == 0) *sl = -1.0f;
+    }
+  }
+  if (in && lane_in_group == 0 && (first || valid)) {
+    p.w = __int_as_float(best.j);
+    work[i] = p;
+  }
+  bool keep = valid && best.idx >= 0;
+  if (keep && static_cast<double>(best.d2) > L.max_dist_sqr) keep = false;
+  if (keep && L.use_rejector && !(best.d2 < L.rej_max2)) keep = false;
+  if (in && lane_in_group == 0 && L.corr_idx) {
+    const int orig = __float_as_int(L.src[i].w);
+    L.corr_idx[orig] = keep ? best.idx : -1;
+    L.corr_d2[orig] = keep ? best.d2 : 0.0f;
+  }
+  if (keep && lane_in_group == 0) accumulate_pair<EST>(L.grid, p, best, acc);
+}
+
+// One block's share of one ICP iteration of hypothesis h: chunk `blk` of L.blocks_per_hyp.  Shared by
+// the per-iteration kernel (blk = blockIdx.x, h = blockIdx.y) and the work-queue kernel below.
+template <int G, int EST, int MB, bool CERT, bool FIRST>
+__device__ __forceinline__ void icp_iteration_body(const IcpLaunch& L, const int h, const int blk) {
   unsigned long long t_dbg[5];
   if (L.dbg) t_dbg[0] = global_ns();
   constexpr int NACC = (EST == PEB_ESTIMATOR_SVD) ? kAccSvd : kAccLls;
@@ -316,12 +431,13 @@ __global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_kernel(const Ic
   __shared__ double sm_tot[kAccMax];
   __shared__ float s_inc[16];
   __shared__ int s_flags[3];  // active, first iteration, apply transform
-  const int h = blockIdx.y;
+  __shared__ CoopTile s_tile[kIcpThreads / 32];  // first iteration of a batch: one staging tile per warp
   IcpState* st = L.states + h;
-  if (threadIdx.x < 16) s_inc[threadIdx.x] = __ldcg(&st->inc.m[threadIdx.x]);
+  // the transform every query of this launch is moved by: the guess in launch 0, else the last increment
+  if (threadIdx.x < 16) s_inc[threadIdx.x] = FIRST ? __ldcg(&st->final_t.m[threadIdx.x]) : __ldcg(&st->inc.m[threadIdx.x]);
   if (threadIdx.x == 32) {
     const int active = __ldcg(&st->active);
-    const int first = __ldcg(&st->iterations) == 0;
+    const int first = FIRST ? 1 : 0;
     int apply = 1;
     if (first) {
       // [PCL] icp.hpp: the guess is applied only if it differs from the identity
@@ -337,91 +453,25 @@ __global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_kernel(const Ic
   }
   __syncthreads();
   if (!s_flags[0]) return;
-  const bool first = s_flags[1] != 0;
+  constexpr bool first = FIRST;
   const bool apply = s_flags[2] != 0;
-  float T[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) T[i] = first ? __ldcg(&st->final_t.m[i]) : s_inc[i];
+  // (read from shared memory where it is used: 16 registers less in the search loop)
+  const float* T = s_inc;
 
   double acc[NACC];
 #pragma unroll
   for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
 
   float4* work = L.work + static_cast<size_t>(h) * L.n_src;
-  const int lane_in_group = threadIdx.x & (G - 1);
   constexpr int kQ = kIcpThreads / G;  // queries per block per pass
   const int q_local = threadIdx.x / G;
-  for (int base = blockIdx.x * kQ; base < L.n_src; base += L.blocks_per_hyp * kQ) {
-    const int i = base + q_local;
-    const bool in = i < L.n_src;
-    float4 p = make_float4(0.f, 0.f, 0.f, 1.f);
-    if (in) p = first ? L.src[i] : work[i];
-    const int j_prev = first ? -1 : __float_as_int(p.w);  // last iteration's match (sorted position)
-    const bool valid = in && finite3(p.x, p.y, p.z);
-    float moved = 0.0f;
-    if (valid && apply) {
-      float ox, oy, oz;
-      transform_icp(T, p.x, p.y, p.z, ox, oy, oz);
-      if (CERT) {
-        const float mx = ox - p.x, my = oy - p.y, mz = oz - p.z;
-        moved = sqrtf(mx * mx + my * my + mz * mz);
-      }
-      p.x = ox;
-      p.y = oy;
-      p.z = oz;
-    }
-    // queries of a group run the search together; invalid ones idle through it
-    NnBest best;
-    best.d2 = pos_inf();
-    best.idx = -1;
-    best.j = -1;
-    float slack = -1.0f;
-    if (valid) {
-      float* sl = L.slack + static_cast<size_t>(h) * L.n_src + i;
-      if (G == 1 && L.warm && j_prev >= 0 && j_prev < L.grid.n) {
-        if (CERT) {
-          // certificate of the previous search (core_math.cuh : grid_nn_warm_cert): every other
-          // target point was at least `slack` farther than the match; the point has moved by `moved`
-          slack = *sl - 2.000002f * moved - 1e-5f * L.grid.h;
-          if (slack > 0.0f) {
-            const float4 t = L.grid.pts[j_prev];
-            best.d2 = l2_simple(p.x, p.y, p.z, t.x, t.y, t.z);
-            best.idx = __float_as_int(t.w);
-            best.j = j_prev;
-          } else {
-            best = grid_nn_warm_cert(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2, L.margin, &slack);
-          }
-          *sl = slack;
-        } else {
-          best = grid_nn_warm(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2);
-        }
-      } else {
-        if (G == 1 && first && L.anchors)
-          best = first_iteration_search(L, h, i, p, T, apply, L.anchors);
-        else
-          best = grid_nn<G>(L.grid, p.x, p.y, p.z, L.stop_d2);
-        if (CERT && lane_in_group == 0) *sl = -1.0f;
-      }
-    }
-    if (in && lane_in_group == 0 && (first || valid)) {
-      p.w = __int_as_float(best.j);
-      work[i] = p;
-    }
-    bool keep = valid && best.idx >= 0;
-    if (keep && static_cast<double>(best.d2) > L.max_dist_sqr) keep = false;
-    if (keep && L.use_rejector && !(best.d2 < L.rej_max2)) keep = false;
-    if (in && lane_in_group == 0 && L.corr_idx) {
-      const int orig = __float_as_int(L.src[i].w);
-      L.corr_idx[orig] = keep ? best.idx : -1;
-      L.corr_d2[orig] = keep ? best.d2 : 0.0f;
-    }
-    if (keep && lane_in_group == 0) accumulate_pair<EST>(L.grid, p, best, acc);
-  }
+  for (int base = blk * kQ; base < L.n_src; base += L.blocks_per_hyp * kQ)
+    icp_query<G, EST, CERT>(L, h, work, base + q_local, first, apply, T, &s_tile[threadIdx.x >> 5], acc);
 
   if (L.dbg) t_dbg[1] = global_ns();
   const double r = block_reduce_acc<NACC>(acc, sm);
   double* part = L.partials + (static_cast<size_t>(h) * L.blocks_per_hyp) * kAccMax;
-  if (threadIdx.x < NACC) __stcg(part + static_cast<size_t>(blockIdx.x) * kAccMax + threadIdx.x, r);
+  if (threadIdx.x < NACC) __stcg(part + static_cast<size_t>(blk) * kAccMax + threadIdx.x, r);
   __threadfence();
   __syncthreads();
   __shared__ int s_last;
@@ -442,6 +492,14 @@ __global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_kernel(const Ic
       for (int k = 0; k < 5; ++k) L.dbg[8 * L.launch_idx + k] = t_dbg[k];
     }
   }
+}
+
+// FIRST: launch 0 of an align (the state's iteration counter is 0 exactly then) — a compile-time
+// property so that the first iteration's search code stays out of the warm kernels' register budget.
+template <int G, int EST, int MB, bool CERT, bool FIRST>
+__global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_kernel(const IcpLaunch L) {
+  pdl_trigger_and_wait();
+  icp_iteration_body<G, EST, MB, CERT, FIRST>(L, blockIdx.y, blockIdx.x);
 }
 
 // [PCL] registration/impl/registration.hpp : getFitnessScore(max_range) with the final transform
@@ -596,13 +654,14 @@ int prof_mark(peb_ctx* ctx, int slot) {
   return PEB_OK;
 }
 
-template <int G>
+template <int G, bool FIRST>
 int launch_one_iteration(peb_ctx* ctx, const IcpLaunch& L, size_t H, int estimator) {
   dim3 grid(L.blocks_per_hyp, static_cast<unsigned>(H));
   constexpr int S = PEB_ESTIMATOR_SVD, P = PEB_ESTIMATOR_POINT_TO_PLANE_LLS;
   const bool cert = G == 1 && L.margin > 0.0f;
   const bool svd = estimator == PEB_ESTIMATOR_SVD;
-#define PEB_ICP_LAUNCH(EST, MB, CERT) PEB_LAUNCH_PDL(ctx, (icp_iteration_kernel<G, EST, MB, CERT>), grid, dim3(kIcpThreads), L)
+#define PEB_ICP_LAUNCH(EST, MB, CERT) \
+  PEB_LAUNCH_PDL(ctx, (icp_iteration_kernel<G, EST, MB, CERT, FIRST>), grid, dim3(kIcpThreads), L)
   if (H == 1) {
     if (cert) { if (svd) PEB_ICP_LAUNCH(S, kMinBlocksSingle, (G == 1)); else PEB_ICP_LAUNCH(P, kMinBlocksSingle, (G == 1)); }
     else      { if (svd) PEB_ICP_LAUNCH(S, kMinBlocksSingle, false);    else PEB_ICP_LAUNCH(P, kMinBlocksSingle, false); }
@@ -614,15 +673,18 @@ int launch_one_iteration(peb_ctx* ctx, const IcpLaunch& L, size_t H, int estimat
   return PEB_OK;
 }
 
-int launch_one_iteration_g(peb_ctx* ctx, int G, const IcpLaunch& L, size_t H, int estimator) {
+// first: launch 0 of the align
+int launch_one_iteration_g(peb_ctx* ctx, int G, bool first, const IcpLaunch& L, size_t H, int estimator) {
+#define PEB_ICP_G(GG) return first ? launch_one_iteration<GG, true>(ctx, L, H, estimator) : launch_one_iteration<GG, false>(ctx, L, H, estimator)
   switch (G) {
-    case 1: return launch_one_iteration<1>(ctx, L, H, estimator);
-    case 2: return launch_one_iteration<2>(ctx, L, H, estimator);
-    case 4: return launch_one_iteration<4>(ctx, L, H, estimator);
-    case 8: return launch_one_iteration<8>(ctx, L, H, estimator);
-    case 16: return launch_one_iteration<16>(ctx, L, H, estimator);
+    case 1: PEB_ICP_G(1);
+    case 2: PEB_ICP_G(2);
+    case 4: PEB_ICP_G(4);
+    case 8: PEB_ICP_G(8);
+    case 16: PEB_ICP_G(16);
     default: return fail(ctx, PEB_E_INVALID_ARG, "nn group width %d is not one of 1,2,4,8,16", G);
   }
+#undef PEB_ICP_G
 }
 
 int launch_fitness_g(peb_ctx* ctx, int G, const IcpLaunch& L, size_t H) {
@@ -663,6 +725,7 @@ int prepare_launch(peb_ctx* ctx, size_t H, const peb_icp_params* prm, IcpLaunch&
   const int n = ctx->n_src_sorted;
   L.grid = ctx->tgt_grid.view;
   L.seed_guard2 = ctx->seed_guard * ctx->seed_guard;
+  L.coop_max_rows = ctx->coop_max_rows;
   L.src = ctx->src_grid.view.pts;
   L.n_src = n;
   const int max_bph = std::max(blocks_for(n, H, ctx->nn_group, ctx->blocks_factor), blocks_for(n, H, 1, ctx->blocks_factor));
@@ -740,14 +803,14 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
     L.trace_cap = cap;
     ctx->last_trace_cap = cap;
   }
+  const int g_cold = ctx->nn_group;
+  const int g_warm = ctx->warm_start ? 1 : g_cold;
+  const bool per_launch = ctx->profile_level >= 2;
+  const int launches = std::max(prm->max_iterations, 1);  // PCL runs the loop body at least once (do ... while)
   PEB_LAUNCH(ctx, icp_init_kernel, ceil_div(static_cast<long long>(H), 128), 128, 0, L.states, d_guesses,
              static_cast<int>(H));
   if (L.margin > 0.0f)  // no certificate yet (all-ones = NaN: never > 0)
     PEB_CUDA(ctx, cudaMemsetAsync(L.slack, 0xFF, std::max<size_t>(H * static_cast<size_t>(n), 1) * sizeof(float), ctx->stream));
-  // PCL runs the loop body at least once (do ... while), also for max_iterations <= 1
-  const int launches = std::max(prm->max_iterations, 1);
-  const int g_cold = ctx->nn_group;
-  const int g_warm = ctx->warm_start ? 1 : g_cold;
   IcpLaunch Lc = L, Lw = L;
   Lc.blocks_per_hyp = blocks_for(n, H, g_cold, ctx->blocks_factor);
   Lc.warm = 0;
@@ -772,7 +835,6 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
   }
   // profile 1: one event pair around the whole run of iteration launches (nothing between the
   // launches, so PDL overlap is what the bench measures); profile 2: a pair around every launch
-  const bool per_launch = ctx->profile_level >= 2;
 
   // Batched aligns run as S independent chains of launches on S streams, each over a contiguous
   // share of the hypotheses: while one chain drains the tail of a launch (its last blocks, the
@@ -817,9 +879,9 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
         if (h0 >= h1) continue;
         StreamSwap swap(ctx, ctx->sub_streams[c]);
         if (it == 0) {
-          PEB_TRY(launch_one_iteration_g(ctx, g_cold, chunk_of(Lc, h0), h1 - h0, prm->estimator));
+          PEB_TRY(launch_one_iteration_g(ctx, g_cold, true, chunk_of(Lc, h0), h1 - h0, prm->estimator));
         } else if (it < launches) {
-          PEB_TRY(launch_one_iteration_g(ctx, g_warm, chunk_of(Lw, h0), h1 - h0, prm->estimator));
+          PEB_TRY(launch_one_iteration_g(ctx, g_warm, false, chunk_of(Lw, h0), h1 - h0, prm->estimator));
         } else {
           PEB_TRY(launch_fitness_g(ctx, g_warm, chunk_of(Lw, h0), h1 - h0));
           PEB_CUDA(ctx, cudaEventRecord(ctx->join_events[c], ctx->stream));
@@ -840,9 +902,9 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
     if (per_launch) PEB_TRY(prof_mark(ctx, 2 * it));
     Lc.launch_idx = Lw.launch_idx = it;
     if (it == 0)
-      PEB_TRY(launch_one_iteration_g(ctx, g_cold, Lc, H, prm->estimator));
+      PEB_TRY(launch_one_iteration_g(ctx, g_cold, true, Lc, H, prm->estimator));
     else
-      PEB_TRY(launch_one_iteration_g(ctx, g_warm, Lw, H, prm->estimator));
+      PEB_TRY(launch_one_iteration_g(ctx, g_warm, false, Lw, H, prm->estimator));
     if (per_launch) PEB_TRY(prof_mark(ctx, 2 * it + 1));
   }
   if (per_launch) {
@@ -860,6 +922,17 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
   }
   return PEB_OK;
 }
+
+#ifdef PEB_COOP_STATS
+extern "C" __attribute__((visibility("default"))) int peb_debug_coop_stats(unsigned long long* out8, int reset) {
+  if (cudaMemcpyFromSymbol(out8, g_coop_stats, 8 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[8] = {};
+    cudaMemcpyToSymbol(g_coop_stats, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 int fitness_device(peb_ctx* ctx, const float* d_T, double max_range, peb_icp_result* d_result) {
   if (!ctx->tgt_grid.valid) return fail(ctx, PEB_E_NO_TARGET, "fitness_score: no target set (peb_target_set)");

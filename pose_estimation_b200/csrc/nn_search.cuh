@@ -71,4 +71,139 @@ __device__ __forceinline__ NnBest grid_nn(const GridView& g, float qx, float qy,
   return best;
 }
 
+// ---- warp-cooperative verification of 32 nearby queries (first ICP iteration of a batch) ---------
+// In the first iteration the queries are millimetres away from the target surface: each one has a
+// candidate (from its patch's anchor, core_math.cuh : grid_nn_seed_probe) and must verify that the
+// ball of the candidate's distance holds nothing closer — hundreds of grid rows per query, and the
+// 32 balls of a 32-point patch overlap almost entirely.  Here the warp walks the rows of ONE region
+// that contains all 32 balls (the bounding ball of their union) with one row per lane, stages the
+// points found in a shared-memory tile (coalesced copies), and every lane scans the tile: each row is
+// looked up once per warp instead of once per lane, with uniform control flow.  The result is the same
+// as 32 independent ball searches (same distance arithmetic, same tie rule, which does not depend on
+// the order of examination).
+constexpr int kCoopTile = 128;
+#ifdef PEB_COOP_STATS
+// development build only (make EXTRA=-DPEB_COOP_STATS): patches, fallbacks, rows, non-empty rows, staged points
+__device__ unsigned long long g_coop_stats[8];
+#define PEB_COOP_COUNT(k, v) do { const unsigned long long v_ = static_cast<unsigned long long>(v); if ((threadIdx.x & 31) == 0) atomicAdd(&g_coop_stats[k], v_); } while (0)
+#define PEB_COOP_COUNT_LANE(k) atomicAdd(&g_coop_stats[k], 1ull)
+#else
+#define PEB_COOP_COUNT(k, v) do { } while (0)
+#define PEB_COOP_COUNT_LANE(k) do { } while (0)
+#endif
+struct CoopTile {
+  float4 pts[kCoopTile];
+  int pos[kCoopTile];  // sorted position of the staged point
+};
+
+__device__ __forceinline__ float warp_min_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+  return v;
+}
+
+// Must be called by all 32 lanes.  `need`: this lane holds a finite query and a candidate in `best`
+// that still has to be verified.  Returns false (nothing done) if the region is larger than max_rows
+// grid rows or unbounded; the caller then verifies every lane on its own (grid_ball_search).
+__device__ __forceinline__ bool grid_nn_coop_verify(const GridView& g, CoopTile* __restrict__ tile, bool need, float qx,
+                                                    float qy, float qz, float limit_d2, int max_rows, NnBest& best) {
+  constexpr unsigned kFull = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  if (__ballot_sync(kFull, need) == 0u) return true;
+  const float big = 3.0e38f;
+  const float lox = warp_min_f(need ? qx : big), hix = warp_max_f(need ? qx : -big);
+  const float loy = warp_min_f(need ? qy : big), hiy = warp_max_f(need ? qy : -big);
+  const float loz = warp_min_f(need ? qz : big), hiz = warp_max_f(need ? qz : -big);
+  const float cx = 0.5f * (lox + hix), cy = 0.5f * (loy + hiy), cz = 0.5f * (loz + hiz);
+  const float pad = 0.001f * g.h;  // >> one ulp of any coordinate (h >= 1e-4 * max |coordinate|)
+  float reach = 0.0f;
+  if (need) {
+    const float r = sqrtf(fminf(best.d2, limit_d2)) * 1.0001f + pad;          // this lane's ball (grid_ball_search)
+    reach = sqrtf(l2_simple(qx, qy, qz, cx, cy, cz)) * 1.0001f + pad + r;     // triangle inequality, rounded up
+  }
+  const float Ru = warp_max_f(reach);
+  PEB_COOP_COUNT(0, 1);
+  if (!(Ru < big)) return false;
+  const int y0 = grid_coord(cy - Ru, g.oy, g.inv_h, g.dy), y1 = grid_coord(cy + Ru, g.oy, g.inv_h, g.dy);
+  const int z0 = grid_coord(cz - Ru, g.oz, g.inv_h, g.dz), z1 = grid_coord(cz + Ru, g.oz, g.inv_h, g.dz);
+  const int ny = y1 - y0 + 1;
+  const int nrows = ny * (z1 - z0 + 1);
+  if (nrows > max_rows) {
+    PEB_COOP_COUNT(1, 1);
+    return false;
+  }
+  PEB_COOP_COUNT(2, nrows);
+  PEB_COOP_COUNT(5, __popc(__ballot_sync(kFull, need)));
+  const float Ru2 = Ru * Ru;
+  // lanes with nothing to verify scan along, but can never accept a point
+  const NnBest own = best;
+  if (!need) {
+    qx = cx;
+    qy = cy;
+    qz = cz;
+    best.d2 = -1.0f;
+  }
+  int fill = 0;   // points staged in the tile (uniform)
+  int slot = -1;  // tile slot of this lane's current winner, if it came from the tile being scanned
+  auto flush = [&]() {
+    __syncwarp();
+    for (int j = 0; j < fill; ++j) {
+      const float4 p = tile->pts[j];
+      const float d2 = l2_simple(qx, qy, qz, p.x, p.y, p.z);
+      const int id = __float_as_int(p.w);
+      if (d2 < best.d2 || (d2 == best.d2 && id < best.idx)) {
+        best.d2 = d2;
+        best.idx = id;
+        slot = j;
+      }
+    }
+    if (slot >= 0) best.j = tile->pos[slot];
+    slot = -1;
+    fill = 0;
+    __syncwarp();
+  };
+  for (int row0 = 0; row0 < nrows; row0 += 32) {
+    const int row = row0 + lane;
+    uint32_t s = 0, e = 0;
+    if (row < nrows) {
+      const int zi = row / ny;
+      const int y = y0 + (row - zi * ny), z = z0 + zi;
+      const float dy = grid_slab_dist(cy, g.oy, g.h, y), dz = grid_slab_dist(cz, g.oz, g.h, z);
+      const float dyz2 = dy * dy + dz * dz;
+      if (dyz2 <= Ru2) {
+        const float rx = sqrtf(Ru2 - dyz2) * 1.0001f + pad;
+        const int x0 = grid_coord(cx - rx, g.ox, g.inv_h, g.dx), x1 = grid_coord(cx + rx, g.ox, g.inv_h, g.dx);
+        const int base = (z * g.dy + y) * g.dx;
+        s = g.cell_start[base + x0];
+        e = g.cell_start[base + x1 + 1];
+      }
+    }
+    unsigned live = __ballot_sync(kFull, e > s);
+    PEB_COOP_COUNT(3, __popc(live));
+    while (live) {
+      const int src_lane = __ffs(live) - 1;
+      live &= live - 1;
+      const uint32_t rs = __shfl_sync(kFull, s, src_lane), re = __shfl_sync(kFull, e, src_lane);
+      for (uint32_t j0 = rs; j0 < re; j0 += 32) {
+        if (fill + 32 > kCoopTile) flush();
+        const uint32_t j = j0 + lane;
+        if (j < re) {
+          tile->pts[fill + lane] = g.pts[j];
+          tile->pos[fill + lane] = static_cast<int>(j);
+        }
+        fill += static_cast<int>(min(32u, re - j0));
+        PEB_COOP_COUNT(4, min(32u, re - j0));
+      }
+    }
+  }
+  flush();
+  if (!need) best = own;
+  return true;
+}
+
 }  // namespace peb
