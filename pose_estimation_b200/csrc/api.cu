@@ -228,6 +228,11 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
     ctx->coop_max_rows = value;
     return PEB_OK;
   }
+  if (!strcmp(key, "blocks_factor_cold")) {
+    if (value < 0 || value > 4096) return fail(ctx, PEB_E_INVALID_ARG, "blocks_factor_cold out of [0, 4096]");
+    ctx->blocks_factor_cold = value;
+    return PEB_OK;
+  }
   if (!strcmp(key, "pdl")) {
     ctx->use_pdl = value != 0;
     return PEB_OK;

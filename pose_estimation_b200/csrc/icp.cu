@@ -23,6 +23,8 @@
 // Later launches of an align that has already converged return at once (state.active == 0).
 // The batched mode is the same code with H > 1: one working cloud per hypothesis so that PCL's
 // incremental float update is reproduced exactly for every hypothesis.
+#include <algorithm>
+
 #include "nn_search.cuh"
 
 namespace peb {
@@ -728,7 +730,8 @@ int prepare_launch(peb_ctx* ctx, size_t H, const peb_icp_params* prm, IcpLaunch&
   L.coop_max_rows = ctx->coop_max_rows;
   L.src = ctx->src_grid.view.pts;
   L.n_src = n;
-  const int max_bph = std::max(blocks_for(n, H, ctx->nn_group, ctx->blocks_factor), blocks_for(n, H, 1, ctx->blocks_factor));
+  const int max_bph = std::max({blocks_for(n, H, ctx->nn_group, ctx->blocks_factor), blocks_for(n, H, 1, ctx->blocks_factor),
+                                blocks_for(n, H, ctx->nn_group, ctx->blocks_factor_cold), blocks_for(n, H, 1, ctx->blocks_factor_cold)});
   PEB_CUDA(ctx, ctx->work.ensure(std::max<size_t>(H * static_cast<size_t>(n), 1) * sizeof(float4)));
   PEB_CUDA(ctx, ctx->slack.ensure(std::max<size_t>(H * static_cast<size_t>(n), 1) * sizeof(float)));
   PEB_CUDA(ctx, ctx->state.ensure(H * sizeof(IcpState)));
@@ -812,7 +815,8 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
   if (L.margin > 0.0f)  // no certificate yet (all-ones = NaN: never > 0)
     PEB_CUDA(ctx, cudaMemsetAsync(L.slack, 0xFF, std::max<size_t>(H * static_cast<size_t>(n), 1) * sizeof(float), ctx->stream));
   IcpLaunch Lc = L, Lw = L;
-  Lc.blocks_per_hyp = blocks_for(n, H, g_cold, ctx->blocks_factor);
+  // launch 0 costs several warm launches and its blocks differ a lot: finer blocks keep the machine even
+  Lc.blocks_per_hyp = blocks_for(n, H, g_cold, ctx->blocks_factor_cold > 0 ? ctx->blocks_factor_cold : ctx->blocks_factor);
   Lc.warm = 0;
   // (a single align has too few patches to fill the machine with anchor searches: their latency
   //  would exceed what the seeds save; its cold launch keeps the plain ring search)

@@ -91,10 +91,36 @@ __device__ unsigned long long g_coop_stats[8];
 #define PEB_COOP_COUNT(k, v) do { } while (0)
 #define PEB_COOP_COUNT_LANE(k) do { } while (0)
 #endif
-struct CoopTile {
-  float4 pts[kCoopTile];
-  int pos[kCoopTile];  // sorted position of the staged point
+struct alignas(16) CoopTile {
+  float xs[kCoopTile], ys[kCoopTile], zs[kCoopTile];  // structure of arrays: two points per packed f32x2 instruction
+  int ids[kCoopTile];                                 // original index
+  int pos[kCoopTile];                                 // sorted position of the staged point
 };
+
+// Packed single precision (sm_100: FADD2 / FMUL2 / FFMA2 work on two floats in a 64-bit register pair with
+// one issue slot).  ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 even under --fmad=false, so the packed
+// distance below is NOT PCL's arithmetic: it is used as a filter only (see CoopTile scan), and every candidate
+// that passes is re-evaluated with l2_simple.
+__device__ __forceinline__ unsigned long long f32x2_splat(float v) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f32x2_sub(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f32x2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 
 __device__ __forceinline__ float warp_min_f(float v) {
 #pragma unroll
@@ -150,16 +176,50 @@ __device__ __forceinline__ bool grid_nn_coop_verify(const GridView& g, CoopTile*
   }
   int fill = 0;   // points staged in the tile (uniform)
   int slot = -1;  // tile slot of this lane's current winner, if it came from the tile being scanned
+  // Scan of the staged points, two per iteration in packed arithmetic.  The packed squared distance uses
+  // fused multiply-adds, so it may differ from l2_simple by a few ulps (each is within 2 ulps of the exact
+  // value): it only FILTERS — a pair that comes within 1e-6 relative of the lane's best is re-evaluated with
+  // l2_simple and goes through the usual comparison (smaller distance, then lower index).
+  const unsigned long long qx2 = f32x2_splat(qx), qy2 = f32x2_splat(qy), qz2 = f32x2_splat(qz);
   auto flush = [&]() {
+    if (lane < ((4 - (fill & 3)) & 3)) {  // pad to a multiple of four with copies of the last point (a copy never wins a comparison)
+      tile->xs[fill + lane] = tile->xs[fill - 1];
+      tile->ys[fill + lane] = tile->ys[fill - 1];
+      tile->zs[fill + lane] = tile->zs[fill - 1];
+      tile->ids[fill + lane] = tile->ids[fill - 1];
+      tile->pos[fill + lane] = tile->pos[fill - 1];
+    }
     __syncwarp();
-    for (int j = 0; j < fill; ++j) {
-      const float4 p = tile->pts[j];
-      const float d2 = l2_simple(qx, qy, qz, p.x, p.y, p.z);
-      const int id = __float_as_int(p.w);
-      if (d2 < best.d2 || (d2 == best.d2 && id < best.idx)) {
-        best.d2 = d2;
-        best.idx = id;
-        slot = j;
+    float thresh = best.d2 * 1.000001f + 1e-37f;
+    for (int j = 0; j < fill; j += 4) {
+      // four points per trip: two independent packed chains (one LDS.128 per coordinate)
+      const ulonglong2 x4 = *reinterpret_cast<const ulonglong2*>(tile->xs + j);
+      const ulonglong2 y4 = *reinterpret_cast<const ulonglong2*>(tile->ys + j);
+      const ulonglong2 z4 = *reinterpret_cast<const ulonglong2*>(tile->zs + j);
+      const unsigned long long dxa = f32x2_sub(qx2, x4.x), dxb = f32x2_sub(qx2, x4.y);
+      const unsigned long long dya = f32x2_sub(qy2, y4.x), dyb = f32x2_sub(qy2, y4.y);
+      const unsigned long long dza = f32x2_sub(qz2, z4.x), dzb = f32x2_sub(qz2, z4.y);
+      const unsigned long long da = f32x2_fma(dza, dza, f32x2_fma(dya, dya, f32x2_mul(dxa, dxa)));
+      const unsigned long long db = f32x2_fma(dzb, dzb, f32x2_fma(dyb, dyb, f32x2_mul(dxb, dxb)));
+      float d0, d1, d2_, d3;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(da));
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(d2_), "=f"(d3) : "l"(db));
+      if (fminf(fminf(d0, d1), fminf(d2_, d3)) <= thresh) {
+        // rare per lane, but some lane of the warp passes on most trips: only the elements that pass are re-evaluated
+        const float dk[4] = {d0, d1, d2_, d3};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (dk[k] <= thresh) {
+            const float d2 = l2_simple(qx, qy, qz, tile->xs[j + k], tile->ys[j + k], tile->zs[j + k]);
+            const int id = tile->ids[j + k];
+            if (d2 < best.d2 || (d2 == best.d2 && id < best.idx)) {
+              best.d2 = d2;
+              best.idx = id;
+              slot = j + k;
+              thresh = d2 * 1.000001f + 1e-37f;
+            }
+          }
+        }
       }
     }
     if (slot >= 0) best.j = tile->pos[slot];
@@ -183,6 +243,7 @@ __device__ __forceinline__ bool grid_nn_coop_verify(const GridView& g, CoopTile*
         e = g.cell_start[base + x1 + 1];
       }
     }
+    // the non-empty rows are staged one after the other, 32 points per step (coalesced)
     unsigned live = __ballot_sync(kFull, e > s);
     PEB_COOP_COUNT(3, __popc(live));
     while (live) {
@@ -190,10 +251,14 @@ __device__ __forceinline__ bool grid_nn_coop_verify(const GridView& g, CoopTile*
       live &= live - 1;
       const uint32_t rs = __shfl_sync(kFull, s, src_lane), re = __shfl_sync(kFull, e, src_lane);
       for (uint32_t j0 = rs; j0 < re; j0 += 32) {
-        if (fill + 32 > kCoopTile) flush();
+        if (fill + 32 > kCoopTile - 4) flush();  // (the scan pads to a multiple of four)
         const uint32_t j = j0 + lane;
         if (j < re) {
-          tile->pts[fill + lane] = g.pts[j];
+          const float4 pt = g.pts[j];
+          tile->xs[fill + lane] = pt.x;
+          tile->ys[fill + lane] = pt.y;
+          tile->zs[fill + lane] = pt.z;
+          tile->ids[fill + lane] = __float_as_int(pt.w);
           tile->pos[fill + lane] = static_cast<int>(j);
         }
         fill += static_cast<int>(min(32u, re - j0));

@@ -39,7 +39,6 @@ def main():
     icp.setInputTarget(prob.target)
     icp.setInputSource(prob.source)
     icp.setMaxCorrespondenceDistance(0.02)
-    ctx.set_int("work_queue", 0)
 
     def wall(H, reps=4):
         best = 1e9
@@ -49,18 +48,20 @@ def main():
             best = min(best, time.perf_counter() - t0)
         return 1e3 * best
 
-    for H in (1024, 128):
+    for H in (128, 1024):
         ctx.set_int("profile", 2)
         wall(H, 2)
         pr = profile(ctx)
         ctx.set_int("profile", 0)
         print(f"H={H} single chain per-launch ms: first {np.round(pr[:4], 3).tolist()} last {np.round(pr[-4:], 3).tolist()} "
               f"sum {pr.sum():.2f} (iterations {pr[:-1].sum():.2f}, fitness {pr[-1]:.3f})", flush=True)
-        for streams in (1, 2, 4, 8):
-            for factor in (8, 16, 32, 64):
+        for streams in (2,):
+            for factor, cold in ((16, 0), (15, 0), (15, 32), (15, 64), (15, 128), (16, 64), (7, 64), (31, 64)):
                 ctx.set_int("batch_streams", streams)
                 ctx.set_int("blocks_factor", factor)
-                print(f"H={H} chains {streams} blocks_factor {factor:3d}: wall {wall(H):7.2f} ms", flush=True)
+                ctx.set_int("blocks_factor_cold", cold)
+                print(f"H={H} chains {streams} blocks_factor {factor:3d} cold {cold:3d}: wall {wall(H):7.2f} ms", flush=True)
+        ctx.set_int("blocks_factor_cold", 0)
         ctx.set_int("batch_streams", 0)
         ctx.set_int("blocks_factor", 0)
         print(f"H={H} defaults: wall {wall(H):7.2f} ms", flush=True)
