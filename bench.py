@@ -59,15 +59,53 @@ def col_major(guesses: np.ndarray) -> np.ndarray:
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU, sampled DURING the timed region: NVML in a thread (a sample
+    every ~5 ms, so that even an 80 ms 8-GPU run is covered); `nvidia-smi -lms` if NVML is not importable."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
         self.index = index
         self.proc = None
         self.lines: list[str] = []
+        self.nvml = None
+        self.samples: list[tuple[int, int]] = []
+        self.max_mhz = None
+        self.stop_flag = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:  # CUDA_VISIBLE_DEVICES re-numbers CUDA devices, not NVML's: go by UUID
+                import torch
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                try:
+                    why = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    why = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((int(mhz), int(why)))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
@@ -82,6 +120,17 @@ class ClockSampler:
             self.lines.append(ln.strip())
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            sm = [m for m, _ in self.samples]
+            reasons = set()
+            for _, why in self.samples:
+                for bit, nm in self.NVML_REASONS.items():
+                    if why & bit:
+                        reasons.add(nm)
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
+                    "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -104,7 +153,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -316,6 +365,12 @@ def run_ours(args):
         _, kernel_ms = timed(step_device, 1, profile=2)
         ctx.set_int("profile", 0)
         ms_per_step_local = total_ms / args.steps
+        per_rank_ms = [ms_per_step_local]
+        if world > 1:  # diagnostics: how uneven the ranks are (the all_gather of every step waits for the slowest)
+            t = torch.tensor([ms_per_step_local], dtype=torch.float64, device=dev)
+            allt = torch.zeros(world, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allt, t)
+            per_rank_ms = [round(float(x), 3) for x in allt.cpu()]
         total_ms = max_over_ranks(total_ms)
         # ---- end-to-end leg through the host-buffer C ABI ---------------------------------
         timed(step_e2e, max(1, min(args.warmup, 3)))
@@ -374,6 +429,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(H * rec if world == 1 else world * world * per * rec),
                 "what": "peb_target_set + peb_source_set + peb_icp_align_batch from pinned host buffers, results back on the host"},
         "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
+        "per_rank_ms_per_step": per_rank_ms,
         "nn_queries_per_s": H * len(c4.source) * ITERATIONS / (ms_per_step * 1e-3),
     }
 
