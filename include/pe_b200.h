@@ -128,7 +128,7 @@ PEB_API int peb_voxel_grid(peb_ctx* ctx, const void* pts, size_t n, size_t strid
  *   the 5 mm band removal of remove_planes            pose_estimation/src/pose_estimation.cpp:309-333
  * applied in that order, in one fused pass; survivors keep their original order (the reference's
  * own order depends on OpenMP scheduling).  The RANSAC fit that produces the plane coefficients
- * (pcl::SACSegmentation, random sampling) is not part of this call: coefficients are inputs. */
+ * (pcl::SACSegmentation) is peb_sac_plane below: its coefficients are inputs of this call. */
 enum { PEB_PREFILTER_MAX_PLANES = 8 };
 typedef struct peb_prefilter_params {
   int32_t use_sphere;          /* filter_points() is applied                                   */
@@ -144,6 +144,37 @@ PEB_API int peb_scene_prefilter(peb_ctx* ctx, const void* pts, size_t n, size_t 
                                 const peb_prefilter_params* params, float* out_xyz4, size_t* out_n);
 PEB_API int peb_scene_prefilter_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, const peb_prefilter_params* params,
                                     void* d_out_xyz4, size_t* out_n);
+
+/* ---- pcl::SACSegmentation<pcl::PointXYZ>::segment, SACMODEL_PLANE + SAC_RANSAC ----------------
+ * The plane fit of the reference's remove_planes (pose_estimation/src/pose_estimation.cpp:285-297:
+ * distance threshold 0.0001, 100 iterations, optimised coefficients), the one step of the scene
+ * preparation that peb_scene_prefilter takes as an input.
+ * [PCL] segmentation/impl/sac_segmentation.hpp (segment), sample_consensus/impl/ransac.hpp
+ * (computeModel: adaptive iteration count k = log(1 - p) / log(1 - w^3), skipped samples),
+ * sample_consensus/sac_model.h (drawIndexSample: boost::mt19937 seeded with 12345 when the model is
+ * not "random", uniform_int<>(0, INT_MAX), partial Fisher-Yates on the persistent index shuffle),
+ * sample_consensus/impl/sac_model_plane.hpp (isSampleGood, computeModelCoefficients,
+ * countWithinDistance, selectWithinDistance, optimizeModelCoefficients = PCA of the inliers).
+ * The sample sequence does not depend on the data, so all candidate planes of a run are drawn on
+ * the host first, their inliers are counted in ONE pass over the cloud on the device, and the
+ * sequential loop (best-so-far, adaptive k) is replayed on the counts: same decisions as PCL's loop.
+ * The inlier moments are accumulated in double (PCL 1.10: float, single pass — see DESIGN.md). */
+typedef struct peb_sac_params {
+  double distance_threshold;     /* setDistanceThreshold                      (PCL default 0)     */
+  double probability;            /* setProbability                            (PCL default 0.99)  */
+  int32_t max_iterations;        /* setMaxIterations                          (PCL default 50)    */
+  int32_t optimize_coefficients; /* setOptimizeCoefficients                   (PCL default true)  */
+  uint32_t seed;                 /* 12345: SampleConsensusModel(random = false)                   */
+  int32_t reserved;
+} peb_sac_params;
+PEB_API void peb_sac_params_default(peb_sac_params* p);
+/* out_coeff: a b c d of ax + by + cz + d = 0 (all 0 when no model was found);
+ * out_inliers (nullable): up to n indices, ascending; out_iterations (nullable): RANSAC iterations run */
+PEB_API int peb_sac_plane(peb_ctx* ctx, const void* pts, size_t n, size_t stride, const peb_sac_params* params,
+                          float out_coeff[4], int32_t* out_inliers, size_t* out_n_inliers, int32_t* out_iterations);
+/* d_out_inliers: nullable DEVICE buffer of n int32 */
+PEB_API int peb_sac_plane_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, const peb_sac_params* params,
+                              float out_coeff[4], int32_t* d_out_inliers, size_t* out_n_inliers, int32_t* out_iterations);
 
 /* ---- pcl::NormalEstimation<PointXYZ,Normal>::compute  [PCL] features/.../impl/normal_3d.hpp */
 /* out_normal8: n x 8 floats = pcl::Normal memory image (nx ny nz 0 | curvature 0 0 0). */

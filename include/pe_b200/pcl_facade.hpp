@@ -93,6 +93,49 @@ class ScenePrefilter {
   peb_prefilter_params p_;
 };
 
+// pcl::SACSegmentation<pcl::PointXYZ> for SACMODEL_PLANE + SAC_RANSAC: the plane fit of remove_planes
+// (pose_estimation/src/pose_estimation.cpp:285-297).  Same setters and defaults as
+// [PCL] segmentation/include/pcl/segmentation/sac_segmentation.h; other model / method types throw
+// PEB_E_UNSUPPORTED (no CPU fallback).
+class SACSegmentation {
+ public:
+  enum { SACMODEL_PLANE = 0, SAC_RANSAC = 0 };  // pcl::SacModel / pcl::SAC_RANSAC values
+  explicit SACSegmentation(Context& c) : c_(c) { peb_sac_params_default(&p_); }
+  void setInputCloud(const void* pts, size_t n, size_t stride = 16) { in_ = {pts, n, stride}; }
+  void setModelType(int model) {
+    if (model != SACMODEL_PLANE) throw Error(PEB_E_UNSUPPORTED, "SACSegmentation: only SACMODEL_PLANE has a CUDA implementation");
+    have_model_ = true;
+  }
+  void setMethodType(int method) {
+    if (method != SAC_RANSAC) throw Error(PEB_E_UNSUPPORTED, "SACSegmentation: only SAC_RANSAC has a CUDA implementation");
+  }
+  void setOptimizeCoefficients(bool on) { p_.optimize_coefficients = on ? 1 : 0; }
+  void setDistanceThreshold(double t) { p_.distance_threshold = t; }
+  void setMaxIterations(int n) { p_.max_iterations = n; }
+  void setProbability(double p) { p_.probability = p; }
+  // inliers: ascending indices; coefficients: a b c d, or empty when no model was found (as PCL clears them)
+  void segment(std::vector<int32_t>& inliers, std::vector<float>& coefficients) {
+    if (!have_model_) throw Error(PEB_E_INVALID_ARG, "SACSegmentation::segment: no model type given (setModelType)");
+    inliers.resize(in_.size ? in_.size : 1);
+    coefficients.assign(4, 0.0f);
+    size_t m = 0;
+    int32_t its = 0;
+    c_.check(peb_sac_plane(c_.get(), in_.data, in_.size, in_.stride, &p_, coefficients.data(), inliers.data(), &m, &its));
+    inliers.resize(m);
+    iterations_ = its;
+    if (m == 0 && coefficients[0] == 0.0f && coefficients[1] == 0.0f && coefficients[2] == 0.0f && coefficients[3] == 0.0f)
+      coefficients.clear();
+  }
+  int iterations() const { return iterations_; }
+
+ private:
+  Context& c_;
+  CloudView in_;
+  peb_sac_params p_;
+  bool have_model_ = false;
+  int iterations_ = 0;
+};
+
 class VoxelGrid {
  public:
   explicit VoxelGrid(Context& c) : c_(c) {}

@@ -82,6 +82,24 @@ def prefilter_params(sphere=None, remove_inliers=False, planes=(), band=0.005) -
     return f
 
 
+class SacParams(C.Structure):
+    """peb_sac_params (include/pe_b200.h)."""
+
+    _fields_ = [
+        ("distance_threshold", C.c_double),
+        ("probability", C.c_double),
+        ("max_iterations", C.c_int32),
+        ("optimize_coefficients", C.c_int32),
+        ("seed", C.c_uint32),
+        ("reserved", C.c_int32),
+    ]
+
+
+def sac_params(distance_threshold=0.0, max_iterations=50, probability=0.99, optimize=True, seed=12345) -> SacParams:
+    """PCL 1.10 SACSegmentation defaults."""
+    return SacParams(float(distance_threshold), float(probability), int(max_iterations), int(bool(optimize)), int(seed), 0)
+
+
 DBL_MAX = float(np.finfo(np.float64).max)
 
 
@@ -177,6 +195,10 @@ class Oracle:
         L.orc_max_threads.restype = C.c_int
         L.orc_scene_prefilter.restype = _sz
         L.orc_scene_prefilter.argtypes = [_vp, _sz, _sz, _vp, _vp]
+        L.orc_sac_plane.restype = C.c_int
+        L.orc_sac_plane.argtypes = [_vp, _sz, _sz, _vp, C.c_int, _vp, _vp, _vp, _vp]
+        L.orc_mt19937_nth.restype = C.c_uint32
+        L.orc_mt19937_nth.argtypes = [C.c_uint32, C.c_uint32]
 
     # ---- nearest neighbours ------------------------------------------------------------
     def knn(self, target: np.ndarray, queries: np.ndarray, k: int = 1):
@@ -216,6 +238,21 @@ class Oracle:
         out = np.empty((max(p.shape[0], 1), 4), np.float32)
         m = self.L.orc_scene_prefilter(p.ctypes.data, p.shape[0], p.strides[0], C.byref(params), out.ctypes.data)
         return out[:m].copy()
+
+    # ---- SACSegmentation, plane + RANSAC -------------------------------------------------------
+    def sac_plane(self, pts: np.ndarray, params: "SacParams", wide_accum: bool = True):
+        """-> (found, coefficients float32[4], inlier indices int32, iterations)"""
+        p = _as_f32(pts)
+        coeff = np.zeros(4, np.float32)
+        inl = np.empty(max(p.shape[0], 1), np.int32)
+        m = C.c_size_t(0)
+        it = C.c_int32(0)
+        found = self.L.orc_sac_plane(p.ctypes.data, p.shape[0], p.strides[0], C.byref(params), int(wide_accum),
+                                     coeff.ctypes.data, inl.ctypes.data, C.byref(m), C.byref(it))
+        return bool(found), coeff, inl[: m.value].copy(), it.value
+
+    def mt19937_nth(self, seed: int, nth: int) -> int:
+        return int(self.L.orc_mt19937_nth(seed, nth))
 
     # ---- NormalEstimation ----------------------------------------------------------------
     def normals(self, pts: np.ndarray, k: int, viewpoint=(0.0, 0.0, 0.0), threads: int = 1, want_nn: bool = False):

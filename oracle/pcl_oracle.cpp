@@ -1426,6 +1426,204 @@ ORC_API size_t orc_scene_prefilter(const void* pts, size_t n, size_t stride, con
   return m;
 }
 
+// ------------------------------------------------------------------------------------------
+// pcl::SACSegmentation<PointXYZ>::segment with SACMODEL_PLANE / SAC_RANSAC, as PCL 1.10 runs it
+// (the reference: pose_estimation/src/pose_estimation.cpp:285-297).
+// [PCL] sample_consensus/impl/ransac.hpp : RandomSampleConsensus::computeModel
+// [PCL] sample_consensus/sac_model.h : getSamples, drawIndexSample, rnd()
+//       (boost::mt19937 seeded with 12345, boost::uniform_int<>(0, INT_MAX) == mt() >> 1)
+// [PCL] sample_consensus/impl/sac_model_plane.hpp : isSampleGood, computeModelCoefficients,
+//       countWithinDistance, selectWithinDistance, optimizeModelCoefficients
+// [PCL] segmentation/impl/sac_segmentation.hpp : segment (optimise, then re-select the inliers)
+// Written as the sequential loop PCL runs (the product draws all samples first and counts in one
+// pass).  The 4-term dot product is summed left to right (Eigen's packet reduction order depends on
+// the SSE level PCL was built with).  wide = 1: inlier moments in double (the product's choice);
+// wide = 0: PCL 1.10's single-pass float sums in index order.
+// ------------------------------------------------------------------------------------------
+}  // extern "C"  (helpers below are C++)
+
+namespace orc {
+
+struct Mt19937 {  // boost::mt19937 == std::mt19937; restated so that the oracle pins the stream itself
+  uint32_t mt[624];
+  int idx;
+  explicit Mt19937(uint32_t seed) {
+    mt[0] = seed;
+    for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + static_cast<uint32_t>(i);
+    idx = 624;
+  }
+  uint32_t next() {
+    if (idx >= 624) {
+      for (int i = 0; i < 624; ++i) {
+        uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+        mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      idx = 0;
+    }
+    uint32_t y = mt[idx++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+  }
+};
+
+static bool plane_sample_collinear(const float* p0, const float* p1, const float* p2) {
+  // Eigen::Array4f dy1dy2 = (p1 - p0) / (p2 - p0); the 4th lanes (w = 1 - 1 = 0 -> 0/0) are not looked at
+  float r[3];
+  for (int i = 0; i < 3; ++i) r[i] = (p1[i] - p0[i]) / (p2[i] - p0[i]);
+  return (r[0] == r[1]) && (r[2] == r[1]);
+}
+
+static float plane_dot(const float* mc, const float* p) { return ((mc[0] * p[0] + mc[1] * p[1]) + mc[2] * p[2]) + mc[3] * 1.0f; }
+
+static bool plane_from_sample(const float* p0, const float* p1, const float* p2, float* mc) {
+  if (plane_sample_collinear(p0, p1, p2)) return false;
+  float a[3], b[3];
+  for (int i = 0; i < 3; ++i) {
+    a[i] = p1[i] - p0[i];
+    b[i] = p2[i] - p0[i];
+  }
+  mc[0] = a[1] * b[2] - a[2] * b[1];
+  mc[1] = a[2] * b[0] - a[0] * b[2];
+  mc[2] = a[0] * b[1] - a[1] * b[0];
+  mc[3] = 0.0f;
+  // Eigen normalize(): v /= sqrt(squaredNorm)
+  float nn = std::sqrt(((mc[0] * mc[0] + mc[1] * mc[1]) + mc[2] * mc[2]) + mc[3] * mc[3]);
+  for (int i = 0; i < 4; ++i) mc[i] /= nn;
+  mc[3] = -1.0f * (((mc[0] * p0[0] + mc[1] * p0[1]) + mc[2] * p0[2]) + mc[3] * 1.0f);
+  return true;
+}
+
+}  // namespace orc
+
+extern "C" {
+
+// returns 1 if a model was found; coeff[4]; inliers (nullable) ascending indices; iterations run
+ORC_API int orc_sac_plane(const void* pts, size_t n, size_t stride, const peb_sac_params* prm, int wide, float* coeff,
+                          int32_t* inliers, size_t* n_inliers, int32_t* iterations_out) {
+  using namespace orc;
+  for (int i = 0; i < 4; ++i) coeff[i] = 0.0f;
+  *n_inliers = 0;
+  if (iterations_out) *iterations_out = 0;
+  if (n < 3) return 0;
+  std::vector<int> shuffled(n);
+  for (size_t i = 0; i < n; ++i) shuffled[i] = static_cast<int>(i);
+  Mt19937 rng(prm->seed);
+  auto rnd = [&]() { return static_cast<int>(rng.next() >> 1); };  // uniform_int<>(0, INT_MAX) over a 32-bit engine
+  const double threshold = prm->distance_threshold;
+  int iterations = 0;
+  int n_best = -std::numeric_limits<int>::max();
+  double k = 1.0;
+  const double log_probability = std::log(1.0 - prm->probability);
+  const double one_over_indices = 1.0 / static_cast<double>(n);
+  unsigned skipped = 0;
+  const unsigned max_skip = static_cast<unsigned>(prm->max_iterations) * 10u;
+  float best[4] = {0, 0, 0, 0};
+  bool have = false;
+  int sel[3];
+  while (iterations < k && skipped < max_skip) {
+    // getSamples: up to 1000 draws until isSampleGood
+    bool good = false;
+    for (unsigned it = 0; it < 1000 && !good; ++it) {
+      for (size_t i = 0; i < 3; ++i) std::swap(shuffled[i], shuffled[i + (rnd() % (n - i))]);
+      for (int i = 0; i < 3; ++i) sel[i] = shuffled[i];
+      good = !plane_sample_collinear(rec(pts, sel[0], stride), rec(pts, sel[1], stride), rec(pts, sel[2], stride));
+    }
+    if (!good) break;  // "No samples could be selected!"
+    float mc[4];
+    if (!plane_from_sample(rec(pts, sel[0], stride), rec(pts, sel[1], stride), rec(pts, sel[2], stride), mc)) {
+      ++skipped;
+      continue;
+    }
+    int cnt = 0;
+    for (size_t i = 0; i < n; ++i)
+      if (static_cast<double>(std::abs(plane_dot(mc, rec(pts, i, stride)))) < threshold) ++cnt;
+    if (cnt > n_best) {
+      n_best = cnt;
+      have = true;
+      for (int i = 0; i < 4; ++i) best[i] = mc[i];
+      double w = static_cast<double>(n_best) * one_over_indices;
+      double p_no_outliers = 1.0 - std::pow(w, 3.0);
+      p_no_outliers = std::max(std::numeric_limits<double>::epsilon(), p_no_outliers);
+      p_no_outliers = std::min(1.0 - std::numeric_limits<double>::epsilon(), p_no_outliers);
+      k = log_probability / std::log(p_no_outliers);
+    }
+    ++iterations;
+    if (iterations > prm->max_iterations) break;
+  }
+  if (iterations_out) *iterations_out = iterations;
+  if (!have) return 0;
+  auto select = [&](const float* mc, std::vector<int>& out) {
+    out.clear();
+    for (size_t i = 0; i < n; ++i)
+      if (static_cast<double>(std::abs(plane_dot(mc, rec(pts, i, stride)))) < threshold) out.push_back(static_cast<int>(i));
+  };
+  std::vector<int> inl;
+  select(best, inl);
+  float final_c[4] = {best[0], best[1], best[2], best[3]};
+  if (prm->optimize_coefficients) {
+    if (inl.size() > 3) {
+      float cov[9], cen[3];
+      if (wide) {
+        double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int j : inl) {
+          const float* c = rec(pts, j, stride);
+          const double x = c[0], y = c[1], z = c[2];
+          a[0] += x * x, a[1] += x * y, a[2] += x * z, a[3] += y * y, a[4] += y * z, a[5] += z * z, a[6] += x, a[7] += y, a[8] += z;
+        }
+        for (int i = 0; i < 9; ++i) a[i] /= static_cast<double>(inl.size());
+        cov[0] = static_cast<float>(a[0] - a[6] * a[6]);
+        cov[1] = static_cast<float>(a[1] - a[6] * a[7]);
+        cov[2] = static_cast<float>(a[2] - a[6] * a[8]);
+        cov[4] = static_cast<float>(a[3] - a[7] * a[7]);
+        cov[5] = static_cast<float>(a[4] - a[7] * a[8]);
+        cov[8] = static_cast<float>(a[5] - a[8] * a[8]);
+        for (int i = 0; i < 3; ++i) cen[i] = static_cast<float>(a[6 + i]);
+      } else {
+        float a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int j : inl) {
+          const float* c = rec(pts, j, stride);
+          a[0] += c[0] * c[0], a[1] += c[0] * c[1], a[2] += c[0] * c[2], a[3] += c[1] * c[1], a[4] += c[1] * c[2];
+          a[5] += c[2] * c[2], a[6] += c[0], a[7] += c[1], a[8] += c[2];
+        }
+        const float fc = static_cast<float>(inl.size());
+        for (int i = 0; i < 9; ++i) a[i] /= fc;
+        cov[0] = a[0] - a[6] * a[6];
+        cov[1] = a[1] - a[6] * a[7];
+        cov[2] = a[2] - a[6] * a[8];
+        cov[4] = a[3] - a[7] * a[7];
+        cov[5] = a[4] - a[7] * a[8];
+        cov[8] = a[5] - a[8] * a[8];
+        for (int i = 0; i < 3; ++i) cen[i] = a[6 + i];
+      }
+      cov[3] = cov[1];
+      cov[6] = cov[2];
+      cov[7] = cov[5];
+      float ev, vec[3];
+      eigen33(cov, ev, vec);
+      final_c[0] = vec[0];
+      final_c[1] = vec[1];
+      final_c[2] = vec[2];
+      final_c[3] = 0.0f;
+      final_c[3] = -1.0f * (((final_c[0] * cen[0] + final_c[1] * cen[1]) + final_c[2] * cen[2]) + final_c[3] * 1.0f);
+    }
+    select(final_c, inl);  // segment(): "Refine inliers"
+  }
+  for (int i = 0; i < 4; ++i) coeff[i] = final_c[i];
+  *n_inliers = inl.size();
+  if (inliers) std::copy(inl.begin(), inl.end(), inliers);
+  return 1;
+}
+
+ORC_API uint32_t orc_mt19937_nth(uint32_t seed, uint32_t nth) {
+  orc::Mt19937 r(seed);
+  uint32_t v = 0;
+  for (uint32_t i = 0; i < nth; ++i) v = r.next();
+  return v;
+}
+
 ORC_API int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

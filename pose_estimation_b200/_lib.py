@@ -85,6 +85,19 @@ class PrefilterParams(C.Structure):
     ]
 
 
+class SacParams(C.Structure):
+    """peb_sac_params."""
+
+    _fields_ = [
+        ("distance_threshold", C.c_double),
+        ("probability", C.c_double),
+        ("max_iterations", C.c_int32),
+        ("optimize_coefficients", C.c_int32),
+        ("seed", C.c_uint32),
+        ("reserved", C.c_int32),
+    ]
+
+
 class GridInfo(C.Structure):
     _fields_ = [
         ("origin", C.c_float * 3),
@@ -110,6 +123,9 @@ SYMBOLS = {
     "peb_voxel_grid": (_i, [_vp, _vp, _sz, _sz, _f, _f, _f, C.c_uint, _vp, _pp(_sz)]),
     "peb_scene_prefilter": (_i, [_vp, _vp, _sz, _sz, _pp(PrefilterParams), _vp, _pp(_sz)]),
     "peb_scene_prefilter_dev": (_i, [_vp, _vp, _sz, _pp(PrefilterParams), _vp, _pp(_sz)]),
+    "peb_sac_params_default": (None, [_pp(SacParams)]),
+    "peb_sac_plane": (_i, [_vp, _vp, _sz, _sz, _pp(SacParams), _vp, _vp, _pp(_sz), _pp(C.c_int32)]),
+    "peb_sac_plane_dev": (_i, [_vp, _vp, _sz, _pp(SacParams), _vp, _vp, _pp(_sz), _pp(C.c_int32)]),
     "peb_normals_knn": (_i, [_vp, _vp, _sz, _sz, _i, _vp, _vp]),
     "peb_normals_knn_ex": (_i, [_vp, _vp, _sz, _sz, _i, _vp, _vp, _vp]),
     "peb_nn_search": (_i, [_vp, _vp, _sz, _sz, _vp, _vp]),

@@ -178,6 +178,7 @@ PEB_API void peb_ctx_destroy(peb_ctx* ctx) {
   if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
   ctx->h_stage.release();
   ctx->h_small.release();
+  ctx->h_sac.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -322,6 +323,47 @@ PEB_API int peb_scene_prefilter(peb_ctx* ctx, const void* pts, size_t n, size_t 
     PEB_CUDA(ctx, cudaMemcpyAsync(out_xyz4, ctx->vg_out.p, m * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
   PEB_TRY(sync(ctx));
   *out_n = m;
+  return PEB_OK;
+}
+
+// ---- SACSegmentation (plane, RANSAC) --------------------------------------------------------------
+PEB_API void peb_sac_params_default(peb_sac_params* p) {
+  if (!p) return;
+  // [PCL] segmentation/sac_segmentation.h : SACSegmentation() defaults; seed of SampleConsensusModel(random = false)
+  p->distance_threshold = 0.0;
+  p->probability = 0.99;
+  p->max_iterations = 50;
+  p->optimize_coefficients = 1;
+  p->seed = 12345u;
+  p->reserved = 0;
+}
+
+PEB_API int peb_sac_plane_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, const peb_sac_params* params, float out_coeff[4],
+                              int32_t* d_out_inliers, size_t* out_n_inliers, int32_t* out_iterations) {
+  if (!ctx || !params || !out_coeff || !out_n_inliers) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  if (n > 0 && !d_xyz4) return fail(ctx, PEB_E_INVALID_ARG, "sac_plane_dev: null device pointer");
+  if (n > static_cast<size_t>(INT32_MAX) / 2) return fail(ctx, PEB_E_INVALID_ARG, "sac_plane: too many points");
+  return sac_plane_device(ctx, static_cast<const float4*>(d_xyz4), static_cast<int>(n), params, out_coeff, d_out_inliers,
+                          out_n_inliers, out_iterations);
+}
+
+PEB_API int peb_sac_plane(peb_ctx* ctx, const void* pts, size_t n, size_t stride, const peb_sac_params* params,
+                          float out_coeff[4], int32_t* out_inliers, size_t* out_n_inliers, int32_t* out_iterations) {
+  if (!ctx || !params || !out_coeff || !out_n_inliers) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  *out_n_inliers = 0;
+  PEB_TRY(check_cloud(ctx, "sac_plane", pts, n, stride));
+  PEB_CUDA(ctx, ctx->vg_in.ensure(std::max<size_t>(n, 1) * sizeof(float4)));
+  PEB_CUDA(ctx, ctx->vg_out.ensure(std::max<size_t>(n, 1) * sizeof(int32_t)));
+  PEB_TRY(upload_cloud(ctx, pts, n, stride, 1.0f, ctx->vg_in.as<float4>()));
+  size_t m = 0;
+  PEB_TRY(sac_plane_device(ctx, ctx->vg_in.as<float4>(), static_cast<int>(n), params, out_coeff,
+                           out_inliers ? ctx->vg_out.as<int32_t>() : nullptr, &m, out_iterations));
+  if (out_inliers && m > 0)
+    PEB_CUDA(ctx, cudaMemcpyAsync(out_inliers, ctx->vg_out.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  PEB_TRY(sync(ctx));
+  *out_n_inliers = m;
   return PEB_OK;
 }
 

@@ -168,6 +168,7 @@ struct peb_ctx {
   peb::Grid aux_grid;
   peb::DevBuf vg_in, vg_out, vg_flags, vg_scan, vg_starts;
   peb::DevBuf nrm_in, nrm_out;
+  peb::PinnedBuf h_sac;      // plane RANSAC: sample indices / coordinates, candidate planes, counts, moment records
 };
 
 namespace peb {
@@ -242,6 +243,9 @@ int voxel_grid_device(peb_ctx* ctx, const float4* d_in, int n, float lx, float l
 // prefilter.cu
 int scene_prefilter_device(peb_ctx* ctx, const float4* d_in, int n, const peb_prefilter_params* prm, float4* d_out,
                            size_t* out_n);
+// sac.cu
+int sac_plane_device(peb_ctx* ctx, const float4* d_pts, int n, const peb_sac_params* prm, float out_coeff[4],
+                     int32_t* d_out_inliers, size_t* out_n_inliers, int32_t* out_iterations);
 // normals.cu
 int normals_knn_device(peb_ctx* ctx, const float4* d_in, int n, int k, const float vp[3], float* d_out8,
                        int32_t* d_out_nn /*nullable, n x k original indices*/);

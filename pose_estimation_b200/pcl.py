@@ -17,7 +17,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import IcpParams, IcpResult, GridInfo, PrefilterParams, lib
+from ._lib import IcpParams, IcpResult, GridInfo, PrefilterParams, SacParams, lib
 
 DBL_MAX = float(np.finfo(np.float64).max)
 
@@ -149,7 +149,7 @@ class ScenePrefilter:
     """The deterministic part of PoseEstimation::create_surface_match_pc
     (pose_estimation/src/pose_estimation.cpp:246-261): NaN removal, the optional sphere filter around the
     last pose (filter_points, :347-372) and the 5 mm band removal of remove_planes (:309-333) for plane
-    coefficients the caller supplies (the RANSAC fit is not part of this path)."""
+    coefficients the caller supplies (SACSegmentation below computes them)."""
 
     def __init__(self, ctx: Context | None = None):
         self.ctx = ctx or default_context()
@@ -188,6 +188,69 @@ class ScenePrefilter:
         self.ctx.check(lib.peb_scene_prefilter(self.ctx.handle, p.ctypes.data, p.shape[0], _stride(p), C.byref(self.params),
                                                out.ctypes.data, C.byref(m)))
         return out[: m.value].copy()
+
+
+class SACSegmentation:
+    """pcl::SACSegmentation<pcl::PointXYZ> for SACMODEL_PLANE + SAC_RANSAC
+    ([PCL] segmentation/include/pcl/segmentation/sac_segmentation.h), the plane fit of the reference's
+    remove_planes (pose_estimation/src/pose_estimation.cpp:285-297).  Other model / method types have no
+    CUDA implementation and raise PEB_E_UNSUPPORTED."""
+
+    SACMODEL_PLANE = 0  # pcl::SacModel
+    SAC_RANSAC = 0      # pcl::SAC_RANSAC
+
+    def __init__(self, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self._input = None
+        self.params = SacParams()
+        lib.peb_sac_params_default(C.byref(self.params))
+        self._model = None
+        self._method = None
+        self.iterations_ = 0
+
+    def setInputCloud(self, cloud):
+        self._input = _cloud(cloud)
+
+    def setModelType(self, model: int):
+        if model != self.SACMODEL_PLANE:
+            raise PebError(-6, f"SACSegmentation: model type {model} has no CUDA implementation (SACMODEL_PLANE only)")
+        self._model = model
+
+    def setMethodType(self, method: int):
+        if method != self.SAC_RANSAC:
+            raise PebError(-6, f"SACSegmentation: method type {method} has no CUDA implementation (SAC_RANSAC only)")
+        self._method = method
+
+    def setOptimizeCoefficients(self, on: bool):
+        self.params.optimize_coefficients = 1 if on else 0
+
+    def setDistanceThreshold(self, t: float):
+        self.params.distance_threshold = float(t)
+
+    def setMaxIterations(self, n: int):
+        self.params.max_iterations = int(n)
+
+    def setProbability(self, p: float):
+        self.params.probability = float(p)
+
+    def segment(self):
+        """-> (inlier indices int32 ascending, coefficients float32[4]); both empty when no model was found
+        (pcl: inliers.indices.clear(), model_coefficients.values.clear())."""
+        if self._input is None:
+            raise ValueError("SACSegmentation.segment: no input cloud (setInputCloud)")
+        if self._model is None:
+            raise PebError(-1, "SACSegmentation.segment: no model type given (setModelType)")  # PCL: initSACModel fails
+        p = self._input
+        coeff = np.zeros(4, np.float32)
+        inl = np.empty(max(p.shape[0], 1), np.int32)
+        m = C.c_size_t(0)
+        it = C.c_int32(0)
+        self.ctx.check(lib.peb_sac_plane(self.ctx.handle, p.ctypes.data, p.shape[0], _stride(p), C.byref(self.params),
+                                         coeff.ctypes.data, inl.ctypes.data, C.byref(m), C.byref(it)))
+        self.iterations_ = it.value
+        if m.value == 0 and not coeff.any():
+            return np.empty(0, np.int32), np.empty(0, np.float32)
+        return inl[: m.value].copy(), coeff
 
 
 class VoxelGrid:

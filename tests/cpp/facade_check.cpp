@@ -46,6 +46,20 @@ int main(int argc, char** argv) {
     vg.filter(ds);
     std::printf("voxel_grid %zu -> %zu\n", n_tgt, ds.size() / 4);
 
+    pe_b200::SACSegmentation seg(ctx);
+    seg.setModelType(pe_b200::SACSegmentation::SACMODEL_PLANE);
+    seg.setMethodType(pe_b200::SACSegmentation::SAC_RANSAC);
+    seg.setOptimizeCoefficients(true);
+    seg.setDistanceThreshold(0.001);
+    seg.setMaxIterations(100);
+    seg.setInputCloud(tgt.data(), n_tgt, 16);
+    std::vector<int32_t> inliers;
+    std::vector<float> coeff;
+    seg.segment(inliers, coeff);
+    std::printf("sac_plane inliers %zu iterations %d coeff", inliers.size(), seg.iterations());
+    for (float v : coeff) std::printf(" %.9g", v);
+    std::printf("\n");
+
     pe_b200::NormalEstimation ne(ctx);
     ne.setInputCloud(ds.data(), ds.size() / 4, 16);
     ne.setKSearch(k);

@@ -57,6 +57,15 @@ def test_facade_matches_python_host_classes(exe, tmp_path):
     vg.setLeafSize(0.002)
     ds = vg.filter()
     assert int(lines["voxel_grid"][3]) == len(ds)
+    seg = pcl.SACSegmentation(ctx)
+    seg.setModelType(pcl.SACSegmentation.SACMODEL_PLANE)
+    seg.setMethodType(pcl.SACSegmentation.SAC_RANSAC)
+    seg.setDistanceThreshold(0.001)
+    seg.setMaxIterations(100)
+    seg.setInputCloud(prob.target)
+    inl, coeff = seg.segment()
+    assert int(lines["sac_plane"][2]) == len(inl) and int(lines["sac_plane"][4]) == seg.iterations_
+    assert np.array_equal(np.array([float(v) for v in lines["sac_plane"][6:10]], np.float32), coeff)
     ne = pcl.NormalEstimation(ctx)
     ne.setInputCloud(ds)
     ne.setKSearch(12)

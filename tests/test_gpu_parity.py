@@ -349,10 +349,15 @@ def test_icp_batch_equals_single_and_oracle(pcl, ctx, oracle, scene_small):
 
 
 @pytest.mark.parametrize("option,value", [("warm_start", 0), ("cert_margin_x1000", 300), ("nn_group", 8), ("anchor_seed", 0),
-                                          ("pdl", 0), ("batch_streams", 1)])
+                                          ("pdl", 0), ("batch_streams", 1),
+                                          # first iteration of a batch: per-lane verification instead of the warp-cooperative one,
+                                          # a row limit that makes most patches fall back, a guard that sends many points to the
+                                          # next patch's anchor or to a cold search
+                                          ("coop_max_rows", 0), ("coop_max_rows", 40), ("seed_guard_x10", 15)])
 def test_speed_options_never_change_results(pcl, oracle, scene_small, option, value):
-    """warm start, search-skipping certificates and the cold lane-group width are exactness-preserving:
-    every combination must give the bit-identical answer."""
+    """warm start, search-skipping certificates, the cold lane-group width and the cooperative first iteration
+    (packed-arithmetic filter + exact re-evaluation) are exactness-preserving: every combination must give the
+    bit-identical answer."""
     p = scene_small
     rng = np.random.default_rng(5)
     guesses = np.stack([synth.perturb_pose(p.gt_pose, rng, 5.0, 0.006) for _ in range(400)])  # enough for anchor seeding
