@@ -62,7 +62,11 @@ typedef enum peb_convergence_state {
   PEB_ABS_MSE = 3,
   PEB_REL_MSE = 4,
   PEB_NO_CORRESPONDENCES = 5,
-  PEB_FAILURE_AFTER_MAX_ITERATIONS = 6
+  PEB_FAILURE_AFTER_MAX_ITERATIONS = 6,
+  /* not a PCL state: a device-side dependency wait between two iteration launches ran into its bound
+   * (a bug, never data-dependent); every record of that align carries it and the host-buffer entry
+   * points return PEB_E_CUDA */
+  PEB_STATE_INTERNAL_ERROR = -1000
 } peb_convergence_state;
 
 enum { PEB_ESTIMATOR_SVD = 0, PEB_ESTIMATOR_POINT_TO_PLANE_LLS = 1 };

@@ -161,7 +161,7 @@ PEB_API void peb_ctx_destroy(peb_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->d_small, &ctx->d_scratch, &ctx->d_stage, &ctx->tgt_raw, &ctx->tgt_nrm_raw, &ctx->src, &ctx->work, &ctx->slack, &ctx->anchors, &ctx->dbg,
                     &ctx->corr_idx, &ctx->corr_d2, &ctx->partials, &ctx->state, &ctx->trace, &ctx->d_guesses,
                     &ctx->d_results, &ctx->d_aligned, &ctx->vg_in, &ctx->vg_out, &ctx->vg_flags, &ctx->vg_scan,
-                    &ctx->vg_starts, &ctx->nrm_in, &ctx->nrm_out, &ctx->nn_q, &ctx->nn_idx, &ctx->nn_d2};
+                    &ctx->vg_starts, &ctx->nrm_in, &ctx->nrm_out, &ctx->nn_q, &ctx->nn_idx, &ctx->nn_d2, &ctx->epochs};
   for (DevBuf* b : bufs) b->release();
   for (Grid* g : {&ctx->tgt_grid, &ctx->aux_grid, &ctx->src_grid}) {
     g->pts.release();
@@ -232,6 +232,10 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
   if (!strcmp(key, "blocks_factor_cold")) {
     if (value < 0 || value > 4096) return fail(ctx, PEB_E_INVALID_ARG, "blocks_factor_cold out of [0, 4096]");
     ctx->blocks_factor_cold = value;
+    return PEB_OK;
+  }
+  if (!strcmp(key, "flag_deps")) {
+    ctx->flag_deps = value != 0;
     return PEB_OK;
   }
   if (!strcmp(key, "pdl")) {
@@ -547,7 +551,11 @@ PEB_API int peb_icp_align_batch(peb_ctx* ctx, const float* guesses, size_t n_gue
   PEB_TRY(icp_align_device(ctx, d_g, n_guesses, params, ctx->d_results.as<peb_icp_result>(), false));
   PEB_CUDA(ctx, cudaMemcpyAsync(results, ctx->d_results.p, n_guesses * sizeof(peb_icp_result), cudaMemcpyDeviceToHost,
                                 ctx->stream));
-  return sync(ctx);
+  PEB_TRY(sync(ctx));
+  if (results[0].state == PEB_STATE_INTERNAL_ERROR)
+    return fail(ctx, PEB_E_CUDA, "align_batch: a per-hypothesis dependency wait ran into its bound (internal error; "
+                                 "peb_ctx_set_int(ctx, \"flag_deps\", 0) restores whole-grid dependencies)");
+  return PEB_OK;
 }
 
 PEB_API int peb_fitness_score(peb_ctx* ctx, const float T[16], double max_range, double* out_fitness, int32_t* out_n_inliers) {

@@ -109,6 +109,8 @@ struct peb_ctx {
   cudaEvent_t fork_event = nullptr;
   int blocks_factor = 0;        // batched aligns: ~this many blocks per SM and launch in total; 0 = auto
   int blocks_factor_cold = 0;   // the same for launch 0 of a batched align; 0 = like blocks_factor
+  bool flag_deps = true;        // warm launches wait per hypothesis (epoch flags) instead of for the whole previous grid
+  peb::DevBuf epochs;           // H solved-iteration counters + 1 error flag
   bool use_pdl = true;          // programmatic dependent launch between the ICP launches of an align
   bool debug_timers = false;    // development: %globaltimer stamps of the phases of every iteration launch
   peb::DevBuf dbg;

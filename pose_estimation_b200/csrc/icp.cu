@@ -67,11 +67,15 @@ struct IcpLaunch {
   int trace_cap;
   int fitness_only;      // peb_fitness_score: the record's n_correspondences carries the inlier count
   int warm;              // seed every search with the match stored in the working point's .w
+  int* epochs;           // nullable, H: solved iterations per hypothesis, published after the state is complete
+  int* err_flag;         // raised if a dependency wait runs into its bound
   float margin;          // extra search radius that buys the skip-the-search certificate (0: none)
 };
 
-__global__ void icp_init_kernel(IcpState* __restrict__ states, const float* __restrict__ guesses, int H) {
+__global__ void icp_init_kernel(IcpState* __restrict__ states, const float* __restrict__ guesses, int H,
+                                int* __restrict__ epochs) {
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (epochs && h <= H) epochs[h] = 0;  // (entry H is the error flag)
   if (h >= H) return;
   IcpState st;
   st.inc = mat4_identity();
@@ -177,7 +181,8 @@ __global__ void __launch_bounds__(128) icp_anchor_kernel(const IcpLaunch L, int*
     p.y = oy;
     p.z = oz;
   }
-  const NnBest best = grid_nn<1>(L.grid, p.x, p.y, p.z, L.stop_d2);
+  // a seed only (every candidate derived from it is verified later): the first ring that holds a point is enough
+  const NnBest best = grid_nn<1, true>(L.grid, p.x, p.y, p.z, L.stop_d2);
   anchors[static_cast<size_t>(h) * L.n_anchor + a] = best.j;
 }
 
@@ -210,6 +215,36 @@ __device__ __noinline__ void finish_iteration(IcpState* st, const IcpCriteria* c
 __device__ __forceinline__ void pdl_trigger_and_wait() {
   asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+
+constexpr int kFlagSpinLimit = 1 << 24;
+// Waits (thread 0, then the block) until `need` iterations of hypothesis blockIdx.y have been solved and published,
+// or the hypothesis has stopped iterating.  See icp_iteration_kernel for why this cannot deadlock.
+__device__ __forceinline__ void wait_for_hypothesis(const int* __restrict__ solved, const int* __restrict__ active, int need,
+                                                    int* err_flag) {
+  if (threadIdx.x == 0) {
+    int spins = 0;
+    while (ld_acquire_gpu(solved) < need && ld_relaxed_gpu(active) != 0) {
+      __nanosleep(40);
+      if (++spins > kFlagSpinLimit) {
+        atomicExch(err_flag, 1);
+        break;
+      }
+    }
+  }
+  __syncthreads();
 }
 
 // adds one accepted correspondence (working point p, match best) to the estimator's moment sums
@@ -493,14 +528,32 @@ __device__ __forceinline__ void icp_iteration_body(const IcpLaunch& L, const int
       t_dbg[4] = global_ns();
       for (int k = 0; k < 5; ++k) L.dbg[8 * L.launch_idx + k] = t_dbg[k];
     }
+    if (L.epochs) {  // the state of h is complete: blocks of the next launch that wait for h may go on
+      __threadfence();
+      atomicAdd(L.epochs + h, 1);
+    }
   }
 }
 
 // FIRST: launch 0 of an align (the state's iteration counter is 0 exactly then) — a compile-time
 // property so that the first iteration's search code stays out of the warm kernels' register budget.
+// Dependencies between the launches of an align.  A launch is issued with programmatic dependent launch and
+// triggers its successor at once, so the successor's blocks take SM slots as soon as ALL blocks of this launch
+// are resident or done.  Launch 0 then waits for everything before it (griddepcontrol.wait: init, anchors).
+// A warm launch does not wait for the whole previous grid: a block of hypothesis h only needs iteration
+// launch_idx - 1 OF h — its last block publishes epochs[h] after writing the state (release / acquire) —
+// so hypotheses whose solve is done move on while the previous launch still drains its tail.  No deadlock: a
+// waiting block only waits for blocks of earlier launches, and those were all resident before it was dispatched.
+// The wait is bounded (a dependency that never comes would be a bug): it then raises the error flag, which the
+// fitness kernel reports in every record.
 template <int G, int EST, int MB, bool CERT, bool FIRST>
 __global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_kernel(const IcpLaunch L) {
-  pdl_trigger_and_wait();
+  if (FIRST || L.epochs == nullptr) {
+    pdl_trigger_and_wait();
+  } else {
+    asm volatile("griddepcontrol.launch_dependents;");
+    wait_for_hypothesis(L.epochs + blockIdx.y, &L.states[blockIdx.y].active, L.launch_idx, L.err_flag);
+  }
   icp_iteration_body<G, EST, MB, CERT, FIRST>(L, blockIdx.y, blockIdx.x);
 }
 
@@ -510,7 +563,12 @@ template <int G>
 __global__ void __launch_bounds__(kIcpThreads) icp_fitness_kernel(const IcpLaunch L) {
   __shared__ double sm[kIcpThreads / 32][kAccMax];
   __shared__ double sm_tot[kAccMax];
-  pdl_trigger_and_wait();
+  if (L.epochs == nullptr) {
+    pdl_trigger_and_wait();
+  } else {  // only the last iteration of THIS hypothesis is needed (L.launch_idx = number of iteration launches)
+    asm volatile("griddepcontrol.launch_dependents;");
+    wait_for_hypothesis(L.epochs + blockIdx.y, &L.states[blockIdx.y].active, L.launch_idx, L.err_flag);
+  }
   const int h = blockIdx.y;
   IcpState* st = L.states + h;
   float T[16];
@@ -593,6 +651,7 @@ __global__ void __launch_bounds__(kIcpThreads) icp_fitness_kernel(const IcpLaunc
     res.converged = s.converged;
     res.state = s.state;
     res.n_correspondences = L.fitness_only ? s.fit_n : s.ncorr;
+    if (L.err_flag && __ldcg(L.err_flag) != 0) res.state = PEB_STATE_INTERNAL_ERROR;  // a dependency wait hit its bound
     L.results[h] = res;
   }
 }
@@ -810,8 +869,18 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
   const int g_warm = ctx->warm_start ? 1 : g_cold;
   const bool per_launch = ctx->profile_level >= 2;
   const int launches = std::max(prm->max_iterations, 1);  // PCL runs the loop body at least once (do ... while)
-  PEB_LAUNCH(ctx, icp_init_kernel, ceil_div(static_cast<long long>(H), 128), 128, 0, L.states, d_guesses,
-             static_cast<int>(H));
+  // Per-hypothesis dependencies between the iteration launches (see icp_iteration_kernel): needs PDL, and
+  // nothing between the launches (profile level 2 and the debug timers put events there)
+  // (not for a single align or a handful of hypotheses: hundreds of blocks polling one flag slow down the
+  //  one thread everybody waits for — measured 0.74 -> 0.78 ms on C2)
+  const bool flag_deps = ctx->flag_deps && ctx->use_pdl && !per_launch && !ctx->debug_timers && !single_mode && H >= 16;
+  if (flag_deps) {
+    PEB_CUDA(ctx, ctx->epochs.ensure((H + 1) * sizeof(int)));
+    L.epochs = ctx->epochs.as<int>();
+    L.err_flag = L.epochs + H;
+  }
+  PEB_LAUNCH(ctx, icp_init_kernel, ceil_div(static_cast<long long>(H + 1), 128), 128, 0, L.states, d_guesses,
+             static_cast<int>(H), L.epochs);
   if (L.margin > 0.0f)  // no certificate yet (all-ones = NaN: never > 0)
     PEB_CUDA(ctx, cudaMemsetAsync(L.slack, 0xFF, std::max<size_t>(H * static_cast<size_t>(n), 1) * sizeof(float), ctx->stream));
   IcpLaunch Lc = L, Lw = L;
@@ -873,6 +942,7 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
       C.partials += h0 * static_cast<size_t>(base.blocks_per_hyp) * kAccMax;
       C.results += h0;
       if (C.anchors) C.anchors += h0 * static_cast<size_t>(C.n_anchor);
+      if (C.epochs) C.epochs += h0;
       return C;
     };
     // the anchor launch above ran on the main stream for all hypotheses: the fork event orders it
@@ -882,6 +952,7 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
         const size_t h0 = c * per, h1 = std::min(H, h0 + per);
         if (h0 >= h1) continue;
         StreamSwap swap(ctx, ctx->sub_streams[c]);
+        Lc.launch_idx = Lw.launch_idx = it;
         if (it == 0) {
           PEB_TRY(launch_one_iteration_g(ctx, g_cold, true, chunk_of(Lc, h0), h1 - h0, prm->estimator));
         } else if (it < launches) {
@@ -911,6 +982,7 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
       PEB_TRY(launch_one_iteration_g(ctx, g_warm, false, Lw, H, prm->estimator));
     if (per_launch) PEB_TRY(prof_mark(ctx, 2 * it + 1));
   }
+  Lw.launch_idx = launches;  // the fitness launch needs all iteration launches of its hypothesis
   if (per_launch) {
     PEB_TRY(prof_mark(ctx, 2 * launches));
     PEB_TRY(launch_fitness_g(ctx, g_warm, Lw, H));
@@ -950,7 +1022,7 @@ int fitness_device(peb_ctx* ctx, const float* d_T, double max_range, peb_icp_res
   L.fitness_only = 1;
   L.warm = 0;  // an arbitrary transform: nothing to seed the search with
   L.blocks_per_hyp = blocks_for(ctx->n_src_sorted, 1, ctx->nn_group, ctx->blocks_factor);
-  PEB_LAUNCH(ctx, icp_init_kernel, 1, 128, 0, L.states, d_T, 1);
+  PEB_LAUNCH(ctx, icp_init_kernel, 1, 128, 0, L.states, d_T, 1, static_cast<int*>(nullptr));
   return launch_fitness_g(ctx, ctx->nn_group, L, 1);
 }
 

@@ -20,7 +20,9 @@ __device__ __forceinline__ unsigned group_mask() {
 
 // stop_d2: correspondences farther than this are rejected by the caller anyway, so rings whose
 // lower bound exceeds it need not be searched (pass +inf for plain nearestKSearch semantics).
-template <int G>
+// FIRST_HIT: return the best point of the first ring that holds any (a SEED for other searches, not a result:
+// the rings needed to prove it nearest are the most expensive ones)
+template <int G, bool FIRST_HIT = false>
 __device__ __forceinline__ NnBest grid_nn(const GridView& g, float qx, float qy, float qz, float stop_d2) {
   NnBest best;
   best.d2 = pos_inf();
@@ -48,6 +50,7 @@ __device__ __forceinline__ NnBest grid_nn(const GridView& g, float qx, float qy,
     bool covers_all;
     const float b2 = grid_ring_bound2(g, qx, qy, qz, cx, cy, cz, r, covers_all);
     if (covers_all || best.d2 <= b2 || b2 > stop_d2) break;
+    if (FIRST_HIT && best.idx >= 0) break;
     if (r >= kMaxRings) {
       // far query: every point, lanes striding over the sorted array (exact, no bound needed)
       for (int j = lane_in_group; j < g.n; j += G) {

@@ -353,7 +353,9 @@ def test_icp_batch_equals_single_and_oracle(pcl, ctx, oracle, scene_small):
                                           # first iteration of a batch: per-lane verification instead of the warp-cooperative one,
                                           # a row limit that makes most patches fall back, a guard that sends many points to the
                                           # next patch's anchor or to a cold search
-                                          ("coop_max_rows", 0), ("coop_max_rows", 40), ("seed_guard_x10", 15)])
+                                          ("coop_max_rows", 0), ("coop_max_rows", 40), ("seed_guard_x10", 15),
+                                          # whole-grid dependencies between the launches instead of per-hypothesis flags
+                                          ("flag_deps", 0)])
 def test_speed_options_never_change_results(pcl, oracle, scene_small, option, value):
     """warm start, search-skipping certificates, the cold lane-group width and the cooperative first iteration
     (packed-arithmetic filter + exact re-evaluation) are exactness-preserving: every combination must give the

@@ -55,13 +55,12 @@ def main():
         ctx.set_int("profile", 0)
         print(f"H={H} single chain per-launch ms: first {np.round(pr[:4], 3).tolist()} last {np.round(pr[-4:], 3).tolist()} "
               f"sum {pr.sum():.2f} (iterations {pr[:-1].sum():.2f}, fitness {pr[-1]:.3f})", flush=True)
-        for streams in (2,):
-            for factor, cold in ((16, 0), (15, 0), (15, 32), (15, 64), (15, 128), (16, 64), (7, 64), (31, 64)):
+        for deps in (0, 1):
+            for streams in (1, 2, 4):
+                ctx.set_int("flag_deps", deps)
                 ctx.set_int("batch_streams", streams)
-                ctx.set_int("blocks_factor", factor)
-                ctx.set_int("blocks_factor_cold", cold)
-                print(f"H={H} chains {streams} blocks_factor {factor:3d} cold {cold:3d}: wall {wall(H):7.2f} ms", flush=True)
-        ctx.set_int("blocks_factor_cold", 0)
+                print(f"H={H} flag_deps {deps} chains {streams}: wall {wall(H):7.2f} ms", flush=True)
+        ctx.set_int("flag_deps", 1)
         ctx.set_int("batch_streams", 0)
         ctx.set_int("blocks_factor", 0)
         print(f"H={H} defaults: wall {wall(H):7.2f} ms", flush=True)
