@@ -199,29 +199,45 @@ PEB_HD int point_index(const float4& p) {
 // (A 4 x 4 x 4 occupancy bitmap that lets a large ball skip its empty bulk was built and measured:
 //  no gain on C2 / C4 — the slab test already rejects empty rows at ~10 instructions each — so the
 //  rows of the ball's bounding box are walked directly.)
-PEB_HD void grid_ball_direct(const GridView& g, float qx, float qy, float qz, float limit_d2, int y0, int y1, int z0,
-                             int z1, NnBest& best) {
-  const float pad = 0.001f * g.h;  // >> one ulp of any coordinate (h >= 1e-4 * max |coordinate|)
+//
+// The walk runs in CELL units: f = (q - origin) / h once per search, then a row costs a subtraction
+// where the world-unit form cost two multiply-adds per slab and per chord end (-11 of ~46 instructions
+// per row).  f is computed with the expression that assigned the target points to their cells
+// (grid_coord), so both sides carry the same rounding, at most a few ulps of the largest cell
+// coordinate: `pad` covers it at the chord ends and the 1 % shrink of the slab distances in the row test.
+
+// distance (>= 0, in cells) from cell coordinate f to the slab of cell index c, shrunk by 1 % of a cell
+PEB_HD float grid_slab_dist_cells(float f, int c) {
+  const float t = f - static_cast<float>(c);
+  return fmaxf(fmaxf(-t, t - 1.0f) - 0.01f, 0.0f);
+}
+
+PEB_HD int grid_clamp_cell(float v, int dim) {
+  v = fminf(fmaxf(floorf(v), 0.0f), static_cast<float>(dim - 1));
+  return static_cast<int>(v);
+}
+
+PEB_HD void grid_ball_search(const GridView& g, float qx, float qy, float qz, float limit_d2, NnBest& best) {
+  const float fx = (qx - g.ox) * g.inv_h, fy = (qy - g.oy) * g.inv_h, fz = (qz - g.oz) * g.inv_h;
+  const float inv_h2 = g.inv_h * g.inv_h;
+  // 0.001 cell >> the rounding of a cell coordinate (4 ulps of the largest one are added for very large grids)
+  const float pad = 0.001f + 4.8e-7f * static_cast<float>(max(g.dx, max(g.dy, g.dz)));
+  const float R = sqrtf(fminf(best.d2, limit_d2) * inv_h2) * 1.0001f + pad;
+  const int y0 = grid_clamp_cell(fy - R, g.dy), y1 = grid_clamp_cell(fy + R, g.dy);
+  const int z0 = grid_clamp_cell(fz - R, g.dz), z1 = grid_clamp_cell(fz + R, g.dz);
   for (int z = z0; z <= z1; ++z) {
-    const float dz = grid_slab_dist(qz, g.oz, g.h, z);
+    const float dz = grid_slab_dist_cells(fz, z);
     for (int y = y0; y <= y1; ++y) {
-      const float dy = grid_slab_dist(qy, g.oy, g.h, y);
+      const float dy = grid_slab_dist_cells(fy, y);
       const float dyz2 = dy * dy + dz * dz;
-      const float cur = fminf(best.d2, limit_d2);
+      const float cur = fminf(best.d2, limit_d2) * inv_h2;  // (cells^2; shrinks as better points are found)
       if (dyz2 > cur) continue;
       const float rx = sqrtf(cur - dyz2) * 1.0001f + pad;
-      const int x0 = grid_coord(qx - rx, g.ox, g.inv_h, g.dx), x1 = grid_coord(qx + rx, g.ox, g.inv_h, g.dx);
+      const int x0 = grid_clamp_cell(fx - rx, g.dx), x1 = grid_clamp_cell(fx + rx, g.dx);
       const int base = (z * g.dy + y) * g.dx;
       grid_scan_range(g, g.cell_start[base + x0], g.cell_start[base + x1 + 1], qx, qy, qz, best);
     }
   }
-}
-
-PEB_HD void grid_ball_search(const GridView& g, float qx, float qy, float qz, float limit_d2, NnBest& best) {
-  const float R = sqrtf(fminf(best.d2, limit_d2)) * 1.0001f + 0.001f * g.h;
-  const int y0 = grid_coord(qy - R, g.oy, g.inv_h, g.dy), y1 = grid_coord(qy + R, g.oy, g.inv_h, g.dy);
-  const int z0 = grid_coord(qz - R, g.oz, g.inv_h, g.dz), z1 = grid_coord(qz + R, g.oz, g.inv_h, g.dz);
-  grid_ball_direct(g, qx, qy, qz, limit_d2, y0, y1, z0, z1, best);
 }
 
 // Exact 1-NN given one candidate (sorted position j_prev, e.g. last iteration's match)
