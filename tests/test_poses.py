@@ -72,3 +72,27 @@ int main() {
         T32 = np.asarray(T, np.float32)
         assert np.allclose(vals[:7], poses.pack_pose(T32), atol=1e-6)
         assert np.allclose(vals[7:], poses.pack_pose(T32, reference_layout=True), atol=1e-6)
+
+
+def test_grasp_frame_of_the_manager():
+    """pose_transformer.cpp:78-121 against an independent float64 construction with scipy."""
+    rng = np.random.default_rng(3)
+    for trial in range(200):
+        R_cam = Rotation.random(random_state=int(rng.integers(1 << 31)))
+        t_cam = rng.normal(size=3)
+        q = R_cam.as_quat() * rng.uniform(0.5, 2.0)  # the reference normalises whatever it receives
+        he = synth.make_pose(Rotation.random(random_state=int(rng.integers(1 << 31))).as_matrix(), rng.normal(size=3))
+        out = poses.obj_in_base_frame(np.concatenate([t_cam, q]), he)
+        base = he @ synth.make_pose(R_cam.as_matrix(), t_cam)
+        y = base[:3, 1]
+        zb = np.array([1.0, 0, 0]) if abs(y[2]) > 0.6 else np.array([0, 0, -1.0])
+        if abs(abs(y[2]) - 0.6) < 1e-4:
+            continue  # the float32 / float64 branch may differ exactly at the switch
+        z = zb - (zb @ y) / (y @ y) * y
+        x = np.cross(y, z)
+        rot = np.stack([x / np.linalg.norm(x), y / np.linalg.norm(y), z / np.linalg.norm(z)], 1)
+        assert np.allclose(out[:3], base[:3, 3], atol=2e-6 * max(1.0, np.abs(base[:3, 3]).max()))
+        got = Rotation.from_quat(out[3:]).as_matrix()
+        assert np.allclose(got, rot, atol=5e-6)
+        assert abs(np.linalg.det(got) - 1) < 1e-5 and np.allclose(got[:, 1], y / np.linalg.norm(y), atol=5e-6)
+        assert np.allclose(poses.hover_pose(np.concatenate([t_cam, q]), he) - out, [0, 0, 0.1, 0, 0, 0, 0])
