@@ -229,16 +229,20 @@ __device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
 }
 
 
-constexpr int kFlagSpinLimit = 1 << 24;
-// Waits (thread 0, then the block) until `need` iterations of hypothesis blockIdx.y have been solved and published,
-// or the hypothesis has stopped iterating.  See icp_iteration_kernel for why this cannot deadlock.
-__device__ __forceinline__ void wait_for_hypothesis(const int* __restrict__ solved, const int* __restrict__ active, int need,
-                                                    int* err_flag) {
-  if (threadIdx.x == 0) {
-    int spins = 0;
-    while (ld_acquire_gpu(solved) < need && ld_relaxed_gpu(active) != 0) {
+// A hypothesis that has stopped iterating (converged, iteration cap, too few correspondences) publishes this instead
+// of + 1, so that everything that may still wait for it is released by the SAME release / acquire pair that makes
+// its final state visible (looking at IcpState::active instead would race with the state's other fields).
+constexpr int kEpochStopped = 1 << 20;
+constexpr unsigned long long kFlagWaitLimitNs = 20ull * 1000ull * 1000ull * 1000ull;  // a dependency that never comes is a bug: give up after 20 s
+// Waits (thread 0, then the block) until `need` iterations of the hypothesis have been solved and published, or the
+// hypothesis has stopped.  See icp_iteration_kernel for why this cannot deadlock.
+__device__ __forceinline__ void wait_for_hypothesis(const int* __restrict__ solved, int need, int* err_flag) {
+  if (threadIdx.x == 0 && ld_acquire_gpu(solved) < need) {
+    const unsigned long long t0 = global_ns();
+    unsigned spins = 0;
+    while (ld_acquire_gpu(solved) < need) {
       __nanosleep(40);
-      if (++spins > kFlagSpinLimit) {
+      if ((++spins & 0xFFFu) == 0u && global_ns() - t0 > kFlagWaitLimitNs) {
         atomicExch(err_flag, 1);
         break;
       }
@@ -529,8 +533,9 @@ __device__ __forceinline__ void icp_iteration_body(const IcpLaunch& L, const int
       for (int k = 0; k < 5; ++k) L.dbg[8 * L.launch_idx + k] = t_dbg[k];
     }
     if (L.epochs) {  // the state of h is complete: blocks of the next launch that wait for h may go on
+      const int still_active = st->active;  // (this thread wrote it)
       __threadfence();
-      atomicAdd(L.epochs + h, 1);
+      atomicAdd(L.epochs + h, still_active ? 1 : kEpochStopped);
     }
   }
 }
@@ -552,7 +557,7 @@ __global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_kernel(const Ic
     pdl_trigger_and_wait();
   } else {
     asm volatile("griddepcontrol.launch_dependents;");
-    wait_for_hypothesis(L.epochs + blockIdx.y, &L.states[blockIdx.y].active, L.launch_idx, L.err_flag);
+    wait_for_hypothesis(L.epochs + blockIdx.y, L.launch_idx, L.err_flag);
   }
   icp_iteration_body<G, EST, MB, CERT, FIRST>(L, blockIdx.y, blockIdx.x);
 }
@@ -567,7 +572,7 @@ __global__ void __launch_bounds__(kIcpThreads) icp_fitness_kernel(const IcpLaunc
     pdl_trigger_and_wait();
   } else {  // only the last iteration of THIS hypothesis is needed (L.launch_idx = number of iteration launches)
     asm volatile("griddepcontrol.launch_dependents;");
-    wait_for_hypothesis(L.epochs + blockIdx.y, &L.states[blockIdx.y].active, L.launch_idx, L.err_flag);
+    wait_for_hypothesis(L.epochs + blockIdx.y, L.launch_idx, L.err_flag);
   }
   const int h = blockIdx.y;
   IcpState* st = L.states + h;
@@ -873,7 +878,8 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
   // nothing between the launches (profile level 2 and the debug timers put events there)
   // (not for a single align or a handful of hypotheses: hundreds of blocks polling one flag slow down the
   //  one thread everybody waits for — measured 0.74 -> 0.78 ms on C2)
-  const bool flag_deps = ctx->flag_deps && ctx->use_pdl && !per_launch && !ctx->debug_timers && !single_mode && H >= 16;
+  const bool flag_deps = ctx->flag_deps && ctx->use_pdl && !per_launch && !ctx->debug_timers && !single_mode && H >= 16 &&
+                         launches < kEpochStopped;
   if (flag_deps) {
     PEB_CUDA(ctx, ctx->epochs.ensure((H + 1) * sizeof(int)));
     L.epochs = ctx->epochs.as<int>();
