@@ -382,6 +382,39 @@ def test_speed_options_never_change_results(pcl, oracle, scene_small, option, va
     assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
 
 
+def test_batch_with_hypotheses_that_stop_at_different_iterations(pcl, scene_small):
+    """Convergence criteria on: hypotheses stop after different numbers of iterations, some never get a correspondence.
+    The launches of a batch depend on each other per hypothesis (epoch flags, a sentinel when a hypothesis stops): the
+    records must equal those of whole-grid dependencies and those of single aligns, bit for bit."""
+    p = scene_small
+    rng = np.random.default_rng(8)
+    guesses = [synth.perturb_pose(p.gt_pose, rng, a, t) for a, t in [(0.2, 0.0003)] * 24 + [(2.0, 0.003)] * 24 + [(6.0, 0.008)] * 24]
+    far = np.array(p.gt_pose, np.float64)
+    far[:3, 3] += [0.5, 0.5, 0.5]  # nothing within the correspondence distance: PEB_NO_CORRESPONDENCES at iteration 0
+    guesses = np.stack(guesses + [far] * 8)
+    prm = default_params(max_iterations=40, max_corr_dist=0.01, transformation_epsilon=1e-9)
+    out = []
+    for deps in (1, 0):
+        c = pcl.Context(0)
+        c.set_int("flag_deps", deps)
+        icp = pcl.IterativeClosestPoint(c)
+        icp.setInputSource(p.source)
+        icp.setInputTarget(p.target)
+        _set_params(icp, prm)
+        res = icp.alignBatch(guesses)
+        out.append([bytes(r) for r in res])
+        if deps:
+            its = np.array([r.iterations for r in res])
+            states = np.array([r.state for r in res])
+            assert len(set(its[:72].tolist())) > 3 and (states[72:] == 5).all() and (its[72:] == 0).all()
+            for h in (0, 30, 60, 75):
+                icp.align(guesses[h], want_output=False)
+                assert bytes(icp.result.T) == bytes(res[h].T) and icp.result.iterations == res[h].iterations
+                assert icp.result.state == res[h].state
+        c.close()
+    assert out[0] == out[1]
+
+
 def test_icp_edge_cases_and_errors(pcl, ctx, oracle, c1):
     fresh = pcl.Context(0)
     try:
