@@ -437,6 +437,7 @@ def run_ours(args):
         if c2 is not None:
             with torch.cuda.stream(stream):
                 line["align_ms"] = single_align(ctx, c2, torch, stream, flush, pcl, lib)
+                line["align_ms"]["cvicp_reference_call"] = cvicp_leg(ctx, c2, pcl, not args.no_cpu_baseline)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(c4)
     if rank == 0:
@@ -495,6 +496,48 @@ def single_align(ctx, c2, torch, stream, flush, pcl, lib):
             "e2e_host_buffers": {"median": statistics.median(e2e), "min": min(e2e),
                                  "what": "peb_target_set + peb_source_set + peb_icp_align, L2 flushed"},
             "unit": "ms", "target_ms": 2.0, "stages": stages}
+
+
+def cvicp_leg(ctx, c2, pcl, with_cpu: bool):
+    """The reference's own call in the refinement slot (opencv_surface_match.cpp:85-94): cv::ppf_match_3d::ICP(250, 0.005f,
+    2.5f, 8).registerModelToScene(model, scene with normals, 6 poses), on the C2 clouds, through the host-buffer C ABI
+    (uploads, 8 level grids, read-backs included), wall clock."""
+    import time
+
+    from pose_estimation_b200.testing import synth
+
+    def with_normals(cloud):
+        ne = pcl.NormalEstimation(ctx)
+        ne.setInputCloud(cloud)
+        ne.setKSearch(20)  # computeNormalsPC3d(scene, out, 20, true, viewpoint) in the reference
+        nrm = ne.compute()
+        ok = np.isfinite(nrm[:, :3]).all(1) & np.isfinite(cloud[:, :3]).all(1)
+        return np.ascontiguousarray(np.concatenate([cloud[ok, :3], nrm[ok, :3]], 1), np.float32)
+
+    scene6 = with_normals(c2.target)
+    model6 = with_normals(c2.source)
+    rng = np.random.default_rng(7)
+    poses = np.stack([synth.perturb_pose(c2.gt_pose, rng, 4.0, 0.006) for _ in range(6)])
+    icp = pcl.CvIcp(250, 0.005, 2.5, 8, ctx=ctx)
+    icp.registerModelToScene(model6, scene6, poses)
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        got, res = icp.registerModelToScene(model6, scene6, poses)
+        ts.append(1e3 * (time.perf_counter() - t0))
+    out = {"workload": "cv::ppf_match_3d::ICP(250, 0.005, 2.5, 8).registerModelToScene, 6 poses, C2 clouds with k = 20 normals",
+           "n_model": int(len(model6)), "n_scene": int(len(scene6)), "ms_median": statistics.median(ts), "ms_min": min(ts),
+           "residual_median": float(np.median(res)),
+           "pose_error_vs_truth_rad_max": float(max(synth.pose_error(P, c2.gt_pose)[0] for P in got))}
+    if with_cpu:
+        from oracle import Oracle, cvicp_params
+        orc = Oracle(fast=True)
+        t0 = time.perf_counter()
+        ref, _ = orc.cvicp_register(model6, scene6, poses, cvicp_params())
+        out["cpu_port_ms"] = 1e3 * (time.perf_counter() - t0)
+        out["cpu_port_threads"] = min(6, host_threads())
+        out["vs_cpu_port_rad_max"] = float(max(synth.pose_error(a, b)[0] for a, b in zip(got, ref)))
+    return out
 
 
 def preprocessing_stages(ctx, c2, torch, stream, flush, pcl, lib):

@@ -180,6 +180,26 @@ PEB_API int peb_sac_plane(peb_ctx* ctx, const void* pts, size_t n, size_t stride
 PEB_API int peb_sac_plane_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, const peb_sac_params* params,
                               float out_coeff[4], int32_t* d_out_inliers, size_t* out_n_inliers, int32_t* out_iterations);
 
+/* ---- cv::ppf_match_3d::ICP::registerModelToScene(model, scene, poses) --------------------------
+ * What the reference runs in the refinement slot (pose_estimation/src/opencv_surface_match.cpp:85-94:
+ * ICP icp(250, 0.005f, 2.5f, 8); icp.registerModelToScene(models_[object], pc_scene_normals, <= 6 poses)).
+ * [CV] opencv_contrib/modules/surface_matching/src/icp.cpp (not in the reference tree nor in this
+ * image: restated from recollection): per pose the model is moved by the pose,
+ * both clouds are centred and scaled, and a numLevels pyramid of point-to-plane ICP runs with
+ * median/MAD rejection, many-to-one ("picky") elimination and the linearised 6-parameter step.
+ * model, scene: n x 6 float rows (x y z nx ny nz = cv::Mat CV_32F with normals).
+ * poses: n_poses x 16 doubles, row-major 4 x 4 (cv::Matx44d::val), updated IN PLACE like
+ * Pose3D::appendPose (pose <- icp_pose * pose); out_residuals: n_poses doubles (Pose3D::residual). */
+typedef struct peb_cvicp_params {
+  int32_t iterations;      /* ICP(iterations, ...)      : 250 in the reference */
+  int32_t num_levels;      /* ICP(..., numLevels)       : 8                    */
+  float tolerance;         /* ICP(.., tolerance, ..)    : 0.005                */
+  float rejection_scale;   /* ICP(.., rejectionScale,.) : 2.5 (<= 0: no robust rejection) */
+} peb_cvicp_params;
+PEB_API int peb_cvicp_register(peb_ctx* ctx, const float* model_xyzn, size_t n_model, const float* scene_xyzn,
+                               size_t n_scene, const peb_cvicp_params* params, double* poses, size_t n_poses,
+                               double* out_residuals);
+
 /* ---- pcl::NormalEstimation<PointXYZ,Normal>::compute  [PCL] features/.../impl/normal_3d.hpp */
 /* out_normal8: n x 8 floats = pcl::Normal memory image (nx ny nz 0 | curvature 0 0 0). */
 PEB_API int peb_normals_knn(peb_ctx* ctx, const void* pts, size_t n, size_t stride, int k,

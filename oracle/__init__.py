@@ -100,6 +100,17 @@ def sac_params(distance_threshold=0.0, max_iterations=50, probability=0.99, opti
     return SacParams(float(distance_threshold), float(probability), int(max_iterations), int(bool(optimize)), int(seed), 0)
 
 
+class CvIcpParams(C.Structure):
+    """peb_cvicp_params (include/pe_b200.h)."""
+
+    _fields_ = [("iterations", C.c_int32), ("num_levels", C.c_int32), ("tolerance", C.c_float), ("rejection_scale", C.c_float)]
+
+
+def cvicp_params(iterations=250, tolerance=0.005, rejection_scale=2.5, num_levels=8) -> CvIcpParams:
+    """cv::ppf_match_3d::ICP(iterations, tolerance, rejectionScale, numLevels) as the reference constructs it."""
+    return CvIcpParams(int(iterations), int(num_levels), float(tolerance), float(rejection_scale))
+
+
 DBL_MAX = float(np.finfo(np.float64).max)
 
 
@@ -197,6 +208,7 @@ class Oracle:
         L.orc_scene_prefilter.argtypes = [_vp, _sz, _sz, _vp, _vp]
         L.orc_sac_plane.restype = C.c_int
         L.orc_sac_plane.argtypes = [_vp, _sz, _sz, _vp, C.c_int, _vp, _vp, _vp, _vp]
+        L.orc_cvicp_register.argtypes = [_vp, _sz, _vp, _sz, _vp, _vp, _sz, _vp]
         L.orc_mt19937_nth.restype = C.c_uint32
         L.orc_mt19937_nth.argtypes = [C.c_uint32, C.c_uint32]
 
@@ -250,6 +262,17 @@ class Oracle:
         found = self.L.orc_sac_plane(p.ctypes.data, p.shape[0], p.strides[0], C.byref(params), int(wide_accum),
                                      coeff.ctypes.data, inl.ctypes.data, C.byref(m), C.byref(it))
         return bool(found), coeff, inl[: m.value].copy(), it.value
+
+    # ---- cv::ppf_match_3d::ICP::registerModelToScene -------------------------------------------
+    def cvicp_register(self, model6: np.ndarray, scene6: np.ndarray, poses: np.ndarray, params: "CvIcpParams"):
+        """model6 / scene6: (n, 6) float32 x y z nx ny nz; poses: (H, 4, 4) float64 -> (refined poses, residuals)."""
+        m = np.ascontiguousarray(model6, np.float32)
+        sc = np.ascontiguousarray(scene6, np.float32)
+        P = np.ascontiguousarray(np.asarray(poses, np.float64).reshape(-1, 16)).copy()
+        res = np.zeros(P.shape[0], np.float64)
+        self.L.orc_cvicp_register(m.ctypes.data, m.shape[0], sc.ctypes.data, sc.shape[0], C.byref(params), P.ctypes.data,
+                                  P.shape[0], res.ctypes.data)
+        return P.reshape(-1, 4, 4), res
 
     def mt19937_nth(self, seed: int, nth: int) -> int:
         return int(self.L.orc_mt19937_nth(seed, nth))

@@ -1624,6 +1624,275 @@ ORC_API uint32_t orc_mt19937_nth(uint32_t seed, uint32_t nth) {
   return v;
 }
 
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// cv::ppf_match_3d::ICP::registerModelToScene — what the reference runs in the refinement slot
+// (pose_estimation/src/opencv_surface_match.cpp:85-94).  [CV] opencv_contrib/modules/
+// surface_matching/src/icp.cpp, ppf_helpers.cpp (transformPCPose, samplePCUniform), c_utils.hpp
+// (eulerToDCM, rtToPose).  PARITY UNPINNED: the contrib sources are in neither /root/reference nor
+// this image; this is the algorithm as recollected, restated sequentially in
+// the arithmetic OpenCV uses (float clouds, double poses and solves).  Choices where OpenCV's order
+// depends on its hash table: of several sources matched to one scene point the smallest distance
+// wins, ties go to the smaller source index; pairs enter the solve in ascending scene index.
+// ------------------------------------------------------------------------------------------
+namespace orc {
+namespace cvicp {
+
+static const double kEps = 1.192092896e-07;  // OpenCV's EPS (FLT_EPSILON)
+
+// [CV] ppf_helpers.cpp : transformPCPose — points through the 4x4 (homogeneous divide), normals through its 3x3, renormalised
+static void transform_pc_pose(const std::vector<float>& pc, const double* P, std::vector<float>& out) {
+  const size_t n = pc.size() / 6;
+  out.resize(pc.size());
+  for (size_t i = 0; i < n; ++i) {
+    const float* r = &pc[6 * i];
+    double p[4];
+    for (int k = 0; k < 4; ++k) p[k] = P[4 * k] * r[0] + P[4 * k + 1] * r[1] + P[4 * k + 2] * r[2] + P[4 * k + 3];
+    float* o = &out[6 * i];
+    if (std::fabs(p[3]) > kEps) {
+      o[0] = static_cast<float>(p[0] / p[3]);
+      o[1] = static_cast<float>(p[1] / p[3]);
+      o[2] = static_cast<float>(p[2] / p[3]);
+    } else {
+      o[0] = o[1] = o[2] = 0.0f;
+    }
+    double nn[3];
+    for (int k = 0; k < 3; ++k) nn[k] = P[4 * k] * r[3] + P[4 * k + 1] * r[4] + P[4 * k + 2] * r[5];
+    const double norm = std::sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+    if (norm > kEps) {
+      o[3] = static_cast<float>(nn[0] / norm);
+      o[4] = static_cast<float>(nn[1] / norm);
+      o[5] = static_cast<float>(nn[2] / norm);
+    } else {
+      o[3] = o[4] = o[5] = 0.0f;
+    }
+  }
+}
+
+static void sample_uniform(const std::vector<float>& pc, int step, std::vector<float>& out) {
+  const size_t n = pc.size() / 6;
+  out.clear();
+  for (size_t i = 0; i < n; i += static_cast<size_t>(step)) out.insert(out.end(), &pc[6 * i], &pc[6 * i] + 6);
+}
+
+static int cv_round(double v) { return static_cast<int>(std::lrint(v)); }  // cvRound: to nearest, ties to even
+
+static void mat44_mul(const double* A, const double* B, double* C) {
+  double t[16];
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) {
+      double a = 0.0;
+      for (int k = 0; k < 4; ++k) a += A[4 * r + k] * B[4 * k + c];
+      t[4 * r + c] = a;
+    }
+  std::memcpy(C, t, sizeof(t));
+}
+
+// [CV] c_utils.hpp : eulerToDCM (R = Rx * (Ry * Rz)) + rtToPose
+static void pose_from_euler(const double* e, const double* t, double* P) {
+  const double cx = std::cos(e[0]), sx = std::sin(e[0]), cy = std::cos(e[1]), sy = std::sin(e[1]), cz = std::cos(e[2]),
+               sz = std::sin(e[2]);
+  const double Rx[9] = {1, 0, 0, 0, cx, -sx, 0, sx, cx};
+  const double Ry[9] = {cy, 0, sy, 0, 1, 0, -sy, 0, cy};
+  const double Rz[9] = {cz, -sz, 0, sz, cz, 0, 0, 0, 1};
+  double T[9], R[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) T[3 * r + c] = Ry[3 * r] * Rz[c] + Ry[3 * r + 1] * Rz[3 + c] + Ry[3 * r + 2] * Rz[6 + c];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) R[3 * r + c] = Rx[3 * r] * T[c] + Rx[3 * r + 1] * T[3 + c] + Rx[3 * r + 2] * T[6 + c];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) P[4 * r + c] = R[3 * r + c];
+    P[4 * r + 3] = t[r];
+  }
+  P[12] = P[13] = P[14] = 0.0;
+  P[15] = 1.0;
+}
+
+// least squares of the n x 6 system through its normal equations (Gaussian elimination with partial pivoting, double);
+// cv::solve(A, b, x, DECOMP_SVD) gives the same minimiser for a full-rank A
+static bool solve6(double* N /*6x6*/, double* r /*6*/, double* x) {
+  for (int c = 0; c < 6; ++c) {
+    int best = c;
+    for (int rr = c + 1; rr < 6; ++rr)
+      if (std::fabs(N[6 * rr + c]) > std::fabs(N[6 * best + c])) best = rr;
+    if (!(std::fabs(N[6 * best + c]) > 0.0)) return false;
+    if (best != c) {
+      for (int k = 0; k < 6; ++k) std::swap(N[6 * c + k], N[6 * best + k]);
+      std::swap(r[c], r[best]);
+    }
+    for (int rr = c + 1; rr < 6; ++rr) {
+      const double f = N[6 * rr + c] / N[6 * c + c];
+      for (int k = c; k < 6; ++k) N[6 * rr + k] -= f * N[6 * c + k];
+      r[rr] -= f * r[c];
+    }
+  }
+  for (int c = 5; c >= 0; --c) {
+    double a = r[c];
+    for (int k = c + 1; k < 6; ++k) a -= N[6 * c + k] * x[k];
+    x[c] = a / N[6 * c + c];
+  }
+  return true;
+}
+
+static float nth_value(std::vector<float> v, size_t nth) {
+  std::nth_element(v.begin(), v.begin() + static_cast<long>(nth), v.end());
+  return v[nth];
+}
+
+// [CV] icp.cpp : getRejectionThreshold — median + scale * 1.48257968 * MAD, both taken at index m / 2
+static float rejection_threshold(const std::vector<float>& d, float scale) {
+  const size_t m = d.size();
+  const float med = nth_value(d, m / 2);
+  std::vector<float> a(m);
+  for (size_t i = 0; i < m; ++i) a[i] = std::fabs(d[i] - med);
+  const float mad = nth_value(a, m / 2);
+  const float sgm = 1.48257968f * mad;
+  return scale * sgm + med;
+}
+
+// one pose; src = the model already moved by the pose (n x 6 floats); returns the 4x4 ICP pose and the residual
+static void register_one(const std::vector<float>& src_in, const std::vector<float>& dst_in, const peb_cvicp_params& prm,
+                         double* pose, double* residual) {
+  const int n = static_cast<int>(src_in.size() / 6);
+  std::vector<float> src0 = src_in, dst0 = dst_in;
+  auto mean_cols = [](const std::vector<float>& pc, double* m) {
+    m[0] = m[1] = m[2] = 0.0;
+    const size_t r = pc.size() / 6;
+    for (size_t i = 0; i < r; ++i)
+      for (int k = 0; k < 3; ++k) m[k] += pc[6 * i + k];
+    for (int k = 0; k < 3; ++k) m[k] /= static_cast<double>(r);
+  };
+  double ms[3], md[3], mean_avg[3];
+  mean_cols(src0, ms);
+  mean_cols(dst0, md);
+  for (int k = 0; k < 3; ++k) mean_avg[k] = 0.5 * (ms[k] + md[k]);
+  auto subtract = [&](std::vector<float>& pc) {
+    for (size_t i = 0; i < pc.size() / 6; ++i)
+      for (int k = 0; k < 3; ++k) pc[6 * i + k] -= static_cast<float>(mean_avg[k]);
+  };
+  subtract(src0);
+  subtract(dst0);
+  auto dist_to_origin = [](const std::vector<float>& pc) {
+    double d = 0.0;
+    for (size_t i = 0; i < pc.size() / 6; ++i) {
+      const double x = pc[6 * i], y = pc[6 * i + 1], z = pc[6 * i + 2];
+      d += std::sqrt(x * x + y * y + z * z);
+    }
+    return d;
+  };
+  const double scale = static_cast<double>(n) / ((dist_to_origin(src0) + dist_to_origin(dst0)) * 0.5);
+  auto scale_pc = [&](std::vector<float>& pc) {
+    for (size_t i = 0; i < pc.size() / 6; ++i)
+      for (int k = 0; k < 3; ++k) pc[6 * i + k] = static_cast<float>(pc[6 * i + k] * scale);
+  };
+  scale_pc(src0);
+  scale_pc(dst0);
+  for (int i = 0; i < 16; ++i) pose[i] = (i % 5 == 0) ? 1.0 : 0.0;
+  double temp_residual = 0.0;
+  const bool robust = prm.rejection_scale > 0.0f;
+  for (int level = prm.num_levels - 1; level >= 0; --level) {
+    const double div = std::pow(2.0, static_cast<double>(level));
+    const int num_samples = cv_round(static_cast<double>(n) / div);
+    const double tol_p = static_cast<double>(prm.tolerance) * static_cast<double>(level + 1) * (level + 1);
+    const int max_it = cv_round(static_cast<double>(prm.iterations) / (level + 1));
+    std::vector<float> moved_full, src_pct, dst_pcs;
+    transform_pc_pose(src0, pose, moved_full);
+    const int step = std::max(1, cv_round(static_cast<double>(n) / static_cast<double>(std::max(num_samples, 1))));
+    sample_uniform(moved_full, step, src_pct);
+    sample_uniform(dst0, step, dst_pcs);
+    KdTree tree;
+    tree.build(dst_pcs.data(), dst_pcs.size() / 6, 24);
+    double fval_old = 9999999999.0, fval_perc = 0.0, fval_min = 9999999999.0;
+    std::vector<float> src_moved = src_pct;
+    const size_t m = src_pct.size() / 6;
+    std::vector<int> idx(m);
+    std::vector<float> dist(m);
+    double pose_x[16];
+    for (int i = 0; i < 16; ++i) pose_x[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    int it = 0;
+    while (!(fval_perc < (1.0 + tol_p) && fval_perc > (1.0 - tol_p)) && it < max_it) {
+      for (size_t i = 0; i < m; ++i) {
+        int j = -1;
+        float d2 = 0.0f;
+        tree.knn(&src_moved[6 * i], 1, &j, &d2);
+        idx[i] = j;
+        dist[i] = d2;
+      }
+      float thr = std::numeric_limits<float>::infinity();
+      if (robust) thr = rejection_threshold(dist, prm.rejection_scale);
+      // picky ICP: per scene point the closest accepted source (ties: smaller source index)
+      std::vector<int> winner(dst_pcs.size() / 6, -1);
+      for (size_t i = 0; i < m; ++i) {
+        if (idx[i] < 0) continue;
+        if (robust && !(dist[i] < thr)) continue;
+        int& w = winner[static_cast<size_t>(idx[i])];
+        if (w < 0 || dist[i] < dist[static_cast<size_t>(w)]) w = static_cast<int>(i);
+      }
+      double N[36] = {0}, r[6] = {0}, fsum = 0.0;
+      int sel = 0;
+      for (size_t j = 0; j < winner.size(); ++j) {
+        if (winner[j] < 0) continue;
+        ++sel;
+        const float* sp = &src_pct[6 * static_cast<size_t>(winner[j])];
+        const float* dp = &dst_pcs[6 * j];
+        const double sx = sp[0], sy = sp[1], sz = sp[2], dx = dp[0], dy = dp[1], dz = dp[2], nx = dp[3], ny = dp[4], nz = dp[5];
+        const double row[6] = {sy * nz - sz * ny, sz * nx - sx * nz, sx * ny - sy * nx, nx, ny, nz};
+        const double b = (dx - sx) * nx + (dy - sy) * ny + (dz - sz) * nz;
+        for (int a = 0; a < 6; ++a) {
+          for (int c = 0; c < 6; ++c) N[6 * a + c] += row[a] * row[c];
+          r[a] += row[a] * b;
+        }
+        for (int k = 0; k < 6; ++k) {
+          const double e = static_cast<double>(sp[k]) - static_cast<double>(dp[k]);
+          fsum += e * e;
+        }
+      }
+      if (sel < 6) break;
+      double x[6];
+      if (!solve6(N, r, x)) break;
+      bool bad = false;
+      for (int k = 0; k < 6; ++k) bad = bad || std::isnan(x[k]);
+      if (bad) break;
+      pose_from_euler(x, x + 3, pose_x);
+      transform_pc_pose(src_pct, pose_x, src_moved);
+      const double fval = std::sqrt(fsum) / static_cast<double>(m);
+      fval_perc = fval / fval_old;
+      fval_old = fval;
+      if (fval < fval_min) fval_min = fval;
+      ++it;
+    }
+    mat44_mul(pose_x, pose, pose);
+    temp_residual = fval_min;
+  }
+  // undo the normalisation: t = t / scale + meanAvg - R * meanAvg
+  for (int r = 0; r < 3; ++r) {
+    const double rm = pose[4 * r] * mean_avg[0] + pose[4 * r + 1] * mean_avg[1] + pose[4 * r + 2] * mean_avg[2];
+    pose[4 * r + 3] = pose[4 * r + 3] / scale + mean_avg[r] - rm;
+  }
+  *residual = temp_residual;
+}
+
+}  // namespace cvicp
+}  // namespace orc
+
+extern "C" {
+
+// poses: n_poses x 16 doubles (row-major 4x4), updated in place (Pose3D::appendPose); residuals: n_poses
+ORC_API void orc_cvicp_register(const float* model, size_t n_model, const float* scene, size_t n_scene,
+                                const peb_cvicp_params* prm, double* poses, size_t n_poses, double* residuals) {
+  std::vector<float> m(model, model + 6 * n_model), sc(scene, scene + 6 * n_scene);
+#pragma omp parallel for schedule(dynamic)
+  for (long long i = 0; i < static_cast<long long>(n_poses); ++i) {
+    std::vector<float> moved;
+    orc::cvicp::transform_pc_pose(m, poses + 16 * i, moved);
+    double icp_pose[16], res = 0.0;
+    orc::cvicp::register_one(moved, sc, *prm, icp_pose, &res);
+    orc::cvicp::mat44_mul(icp_pose, poses + 16 * i, poses + 16 * i);
+    residuals[i] = res;
+  }
+}
+
 ORC_API int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -98,6 +98,12 @@ class SacParams(C.Structure):
     ]
 
 
+class CvIcpParams(C.Structure):
+    """peb_cvicp_params."""
+
+    _fields_ = [("iterations", C.c_int32), ("num_levels", C.c_int32), ("tolerance", C.c_float), ("rejection_scale", C.c_float)]
+
+
 class GridInfo(C.Structure):
     _fields_ = [
         ("origin", C.c_float * 3),
@@ -126,6 +132,7 @@ SYMBOLS = {
     "peb_sac_params_default": (None, [_pp(SacParams)]),
     "peb_sac_plane": (_i, [_vp, _vp, _sz, _sz, _pp(SacParams), _vp, _vp, _pp(_sz), _pp(C.c_int32)]),
     "peb_sac_plane_dev": (_i, [_vp, _vp, _sz, _pp(SacParams), _vp, _vp, _pp(_sz), _pp(C.c_int32)]),
+    "peb_cvicp_register": (_i, [_vp, _vp, _sz, _vp, _sz, _pp(CvIcpParams), _vp, _sz, _vp]),
     "peb_normals_knn": (_i, [_vp, _vp, _sz, _sz, _i, _vp, _vp]),
     "peb_normals_knn_ex": (_i, [_vp, _vp, _sz, _sz, _i, _vp, _vp, _vp]),
     "peb_nn_search": (_i, [_vp, _vp, _sz, _sz, _vp, _vp]),

@@ -161,7 +161,7 @@ PEB_API void peb_ctx_destroy(peb_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->d_small, &ctx->d_scratch, &ctx->d_stage, &ctx->tgt_raw, &ctx->tgt_nrm_raw, &ctx->src, &ctx->work, &ctx->slack, &ctx->anchors, &ctx->dbg,
                     &ctx->corr_idx, &ctx->corr_d2, &ctx->partials, &ctx->state, &ctx->trace, &ctx->d_guesses,
                     &ctx->d_results, &ctx->d_aligned, &ctx->vg_in, &ctx->vg_out, &ctx->vg_flags, &ctx->vg_scan,
-                    &ctx->vg_starts, &ctx->nrm_in, &ctx->nrm_out, &ctx->nn_q, &ctx->nn_idx, &ctx->nn_d2, &ctx->epochs};
+                    &ctx->vg_starts, &ctx->nrm_in, &ctx->nrm_out, &ctx->nn_q, &ctx->nn_idx, &ctx->nn_d2, &ctx->epochs, &ctx->cv_arena};
   for (DevBuf* b : bufs) b->release();
   for (Grid* g : {&ctx->tgt_grid, &ctx->aux_grid, &ctx->src_grid}) {
     g->pts.release();
@@ -369,6 +369,16 @@ PEB_API int peb_sac_plane(peb_ctx* ctx, const void* pts, size_t n, size_t stride
   PEB_TRY(sync(ctx));
   *out_n_inliers = m;
   return PEB_OK;
+}
+
+// ---- cv::ppf_match_3d::ICP::registerModelToScene ----------------------------------------------------
+PEB_API int peb_cvicp_register(peb_ctx* ctx, const float* model_xyzn, size_t n_model, const float* scene_xyzn, size_t n_scene,
+                               const peb_cvicp_params* params, double* poses, size_t n_poses, double* out_residuals) {
+  if (!ctx || !params) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  if (n_poses == 0) return PEB_OK;
+  if (!model_xyzn || !scene_xyzn || !poses) return fail(ctx, PEB_E_INVALID_ARG, "cvicp_register: null model / scene / poses");
+  return cvicp_register_device(ctx, model_xyzn, n_model, scene_xyzn, n_scene, params, poses, n_poses, out_residuals);
 }
 
 // ---- NormalEstimation ---------------------------------------------------------------------------

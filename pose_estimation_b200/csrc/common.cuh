@@ -172,6 +172,7 @@ struct peb_ctx {
   peb::Grid aux_grid;
   peb::DevBuf vg_in, vg_out, vg_flags, vg_scan, vg_starts;
   peb::DevBuf nrm_in, nrm_out;
+  peb::DevBuf cv_arena;      // cv::ppf_match_3d::ICP mode: all device buffers of a call
   peb::PinnedBuf h_sac;      // plane RANSAC: sample indices / coordinates, candidate planes, counts, moment records
 };
 
@@ -250,6 +251,9 @@ int scene_prefilter_device(peb_ctx* ctx, const float4* d_in, int n, const peb_pr
 // sac.cu
 int sac_plane_device(peb_ctx* ctx, const float4* d_pts, int n, const peb_sac_params* prm, float out_coeff[4],
                      int32_t* d_out_inliers, size_t* out_n_inliers, int32_t* out_iterations);
+// cvicp.cu (host pointers in, results on the host)
+int cvicp_register_device(peb_ctx* ctx, const float* h_model, size_t n_model, const float* h_scene, size_t n_scene,
+                          const peb_cvicp_params* prm, double* poses, size_t n_poses, double* residuals);
 // normals.cu
 int normals_knn_device(peb_ctx* ctx, const float4* d_in, int n, int k, const float vp[3], float* d_out8,
                        int32_t* d_out_nn /*nullable, n x k original indices*/);

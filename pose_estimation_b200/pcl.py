@@ -17,7 +17,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import IcpParams, IcpResult, GridInfo, PrefilterParams, SacParams, lib
+from ._lib import CvIcpParams, IcpParams, IcpResult, GridInfo, PrefilterParams, SacParams, lib
 
 DBL_MAX = float(np.finfo(np.float64).max)
 
@@ -251,6 +251,31 @@ class SACSegmentation:
         if m.value == 0 and not coeff.any():
             return np.empty(0, np.int32), np.empty(0, np.float32)
         return inl[: m.value].copy(), coeff
+
+
+class CvIcp:
+    """cv::ppf_match_3d::ICP (opencv_contrib surface_matching) as the reference constructs and calls it
+    (pose_estimation/src/opencv_surface_match.cpp:85-94): ICP(iterations, tolerance, rejectionScale, numLevels) and
+    registerModelToScene(model, scene, poses) with N x 6 float clouds (points + normals)."""
+
+    def __init__(self, iterations: int = 250, tolerance: float = 0.05, rejection_scale: float = 2.5, num_levels: int = 6,
+                 ctx: Context | None = None):
+        # (defaults of cv::ppf_match_3d::ICP::ICP(); the reference passes 250, 0.005f, 2.5f, 8)
+        self.ctx = ctx or default_context()
+        self.params = CvIcpParams(int(iterations), int(num_levels), float(tolerance), float(rejection_scale))
+
+    def registerModelToScene(self, model6, scene6, poses):
+        """poses: (H, 4, 4) float64 -> (refined poses (H, 4, 4), residuals (H,)); the Pose3D list of OpenCV updated by
+        appendPose, residual per pose."""
+        m = np.ascontiguousarray(model6, np.float32)
+        sc = np.ascontiguousarray(scene6, np.float32)
+        if m.ndim != 2 or m.shape[1] != 6 or sc.ndim != 2 or sc.shape[1] != 6:
+            raise PebError(-1, "CvIcp.registerModelToScene: model and scene must be N x 6 float (points + normals)")
+        P = np.ascontiguousarray(np.asarray(poses, np.float64).reshape(-1, 16)).copy()
+        res = np.zeros(max(P.shape[0], 1), np.float64)
+        self.ctx.check(lib.peb_cvicp_register(self.ctx.handle, m.ctypes.data, m.shape[0], sc.ctypes.data, sc.shape[0],
+                                              C.byref(self.params), P.ctypes.data, P.shape[0], res.ctypes.data))
+        return P.reshape(-1, 4, 4), res[: P.shape[0]]
 
 
 class VoxelGrid:
