@@ -339,6 +339,28 @@ inline void pack_pose(const float* T16, float pose7[7], bool reference_layout = 
   }
 }
 
+// cv::ppf_match_3d::ICP as the reference constructs and calls it (pose_estimation/src/opencv_surface_match.cpp:85-94):
+// ICP icp(250, 0.005f, 2.5f, 8); icp.registerModelToScene(model, scene_with_normals, poses).  Clouds are the N x 6
+// CV_32F rows of OpenCV (x y z nx ny nz, cv::Mat::ptr<float>(0) of a continuous Mat); a pose is the 16 doubles of
+// Pose3D::pose (cv::Matx44d::val, row-major) and is updated in place like Pose3D::appendPose; residual -> Pose3D::residual.
+class CvIcp {
+ public:
+  CvIcp(Context& c, int iterations = 250, float tolerance = 0.05f, float rejection_scale = 2.5f, int num_levels = 6) : c_(c) {
+    p_.iterations = iterations;
+    p_.num_levels = num_levels;
+    p_.tolerance = tolerance;
+    p_.rejection_scale = rejection_scale;
+  }
+  void registerModelToScene(const float* model_xyzn, size_t n_model, const float* scene_xyzn, size_t n_scene, double* poses16,
+                            size_t n_poses, double* residuals) {
+    c_.check(peb_cvicp_register(c_.get(), model_xyzn, n_model, scene_xyzn, n_scene, &p_, poses16, n_poses, residuals));
+  }
+
+ private:
+  Context& c_;
+  peb_cvicp_params p_;
+};
+
 class IterativeClosestPointWithNormals : public IterativeClosestPoint {
  public:
   explicit IterativeClosestPointWithNormals(Context& c) : IterativeClosestPoint(c, PEB_ESTIMATOR_POINT_TO_PLANE_LLS) {}

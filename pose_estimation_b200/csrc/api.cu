@@ -179,6 +179,7 @@ PEB_API void peb_ctx_destroy(peb_ctx* ctx) {
   ctx->h_stage.release();
   ctx->h_small.release();
   ctx->h_sac.release();
+  ctx->h_cv.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

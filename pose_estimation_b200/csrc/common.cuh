@@ -173,6 +173,7 @@ struct peb_ctx {
   peb::DevBuf vg_in, vg_out, vg_flags, vg_scan, vg_starts;
   peb::DevBuf nrm_in, nrm_out;
   peb::DevBuf cv_arena;      // cv::ppf_match_3d::ICP mode: all device buffers of a call
+  peb::PinnedBuf h_cv;       // cv ICP mode: pose tables (two, alternating) + accumulator read-back
   peb::PinnedBuf h_sac;      // plane RANSAC: sample indices / coordinates, candidate planes, counts, moment records
 };
 

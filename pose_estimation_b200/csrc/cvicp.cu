@@ -466,11 +466,19 @@ int cvicp_register_device(peb_ctx* ctx, const float* h_model, size_t n_model, co
   double* d_acc = reinterpret_cast<double*>(base + o_acc);
   float* d_thr = reinterpret_cast<float*>(base + o_thr);
 
+  // pinned staging: two pose tables used alternately (every iteration ends with a synchronising read-back, so a table is
+  // never rewritten while its upload is in flight), and the accumulator read-back
+  const size_t pose_bytes = (sizeof(CvPoseDev) * H + 255) & ~static_cast<size_t>(255);
+  PEB_CUDA(ctx, ctx->h_cv.ensure(2 * pose_bytes + sizeof(double) * kCvAcc * H));
+  CvPoseDev* stage[2] = {reinterpret_cast<CvPoseDev*>(ctx->h_cv.as<char>()), reinterpret_cast<CvPoseDev*>(ctx->h_cv.as<char>() + pose_bytes)};
+  double* h_acc = reinterpret_cast<double*>(ctx->h_cv.as<char>() + 2 * pose_bytes);
+  int stage_k = 0;
   std::vector<CvPoseDev> hp(H);
-  std::vector<double> h_sums(4 * static_cast<size_t>(H) * (sblocks + dblocks)), h_acc(static_cast<size_t>(kCvAcc) * H);
+  std::vector<double> h_sums(4 * static_cast<size_t>(H) * (sblocks + dblocks));
   auto push_poses = [&]() -> int {
-    PEB_CUDA(ctx, cudaMemcpyAsync(d_poses, hp.data(), sizeof(CvPoseDev) * H, cudaMemcpyHostToDevice, st));
-    PEB_CUDA(ctx, cudaStreamSynchronize(st));  // hp is pageable and rewritten right away
+    std::copy(hp.begin(), hp.end(), stage[stage_k]);
+    PEB_CUDA(ctx, cudaMemcpyAsync(d_poses, stage[stage_k], sizeof(CvPoseDev) * H, cudaMemcpyHostToDevice, st));
+    stage_k ^= 1;
     return PEB_OK;
   };
 
@@ -545,59 +553,53 @@ int cvicp_register_device(peb_ctx* ctx, const float* h_model, size_t n_model, co
     }
     PEB_TRY(push_poses());
     PEB_LAUNCH(ctx, cv_level_init, dim3(ceil_div(m, kCvT), H), kCvT, 0, d_src0, n, step, m, d_poses, d_pct, d_moved);
-    for (;;) {
-      int any = 0;
+    // while (!(fval_perc within 1 -/+ TolP) && i < MaxIterationsPyr): fval_perc starts at 0, so every pose enters if max_it > 0
+    int any = 0;
+    for (int h = 0; h < H; ++h) {
+      running[h] = max_it > 0;
+      hp[h].active = running[h];
+      any |= running[h];
+    }
+    if (any) PEB_TRY(push_poses());  // (the kernels of an iteration only read `active`; cv_move also the pose = PoseX)
+    while (any) {
+      PEB_LAUNCH(ctx, cv_nn, dim3(ceil_div(m, 128), H), 128, 0, g, d_scene, step, d_moved, m, d_poses, d_idx, d_dist);
+      if (robust) PEB_LAUNCH(ctx, cv_threshold, H, 1024, 0, d_dist, m, prm->rejection_scale, d_poses, d_thr);
+      PEB_CUDA(ctx, cudaMemsetAsync(d_keys, 0xFF, sizeof(unsigned long long) * msl * static_cast<size_t>(H), st));
+      PEB_LAUNCH(ctx, cv_pick, dim3(ceil_div(m, kCvT), H), kCvT, 0, d_idx, d_dist, m, msl, d_thr, robust ? 1 : 0, d_poses, d_keys);
+      PEB_LAUNCH(ctx, cv_accumulate, H, 1024, 0, d_pct, d_scene, step, d_idx, d_dist, m, msl, d_keys, d_poses, d_acc);
+      PEB_CUDA(ctx, cudaMemcpyAsync(h_acc, d_acc, sizeof(double) * kCvAcc * H, cudaMemcpyDeviceToHost, st));
+      PEB_CUDA(ctx, cudaStreamSynchronize(st));
+      any = 0;
       for (int h = 0; h < H; ++h) {
-        running[h] = hp[h].active && !(fval_perc[h] < (1.0 + tol_p) && fval_perc[h] > (1.0 - tol_p)) && it[h] < max_it;
-        hp[h].active = running[h];
-        any |= running[h];
-      }
-      if (!any) break;
-      // the kernels of this iteration read `active` and, in cv_move, the pose: PoseX of the previous solve
-      for (int h = 0; h < H; ++h) std::copy(&pose_x[16 * h], &pose_x[16 * h] + 16, hp[h].pose);
-      PEB_TRY(push_poses());
-      if (true) {
-        PEB_LAUNCH(ctx, cv_nn, dim3(ceil_div(m, 128), H), 128, 0, g, d_scene, step, d_moved, m, d_poses, d_idx, d_dist);
-        if (robust) PEB_LAUNCH(ctx, cv_threshold, H, 1024, 0, d_dist, m, prm->rejection_scale, d_poses, d_thr);
-        PEB_CUDA(ctx, cudaMemsetAsync(d_keys, 0xFF, sizeof(unsigned long long) * msl * static_cast<size_t>(H), st));
-        PEB_LAUNCH(ctx, cv_pick, dim3(ceil_div(m, kCvT), H), kCvT, 0, d_idx, d_dist, m, msl, d_thr, robust ? 1 : 0, d_poses, d_keys);
-        PEB_LAUNCH(ctx, cv_accumulate, H, 1024, 0, d_pct, d_scene, step, d_idx, d_dist, m, msl, d_keys, d_poses, d_acc);
-        PEB_CUDA(ctx, cudaMemcpyAsync(h_acc.data(), d_acc, sizeof(double) * kCvAcc * H, cudaMemcpyDeviceToHost, st));
-        PEB_CUDA(ctx, cudaStreamSynchronize(st));
-      }
-      bool moved_any = false;
-      for (int h = 0; h < H; ++h) {
-        if (!running[h]) continue;
-        const double* a = &h_acc[static_cast<size_t>(kCvAcc) * h];
-        const int sel = static_cast<int>(a[43]);
-        double N[36], r[6], x[6];
-        std::copy(a, a + 36, N);
-        std::copy(a + 36, a + 42, r);
-        bool ok = sel >= 6 && solve6(N, r, x);
-        if (ok)
-          for (int k = 0; k < 6; ++k) ok = ok && !std::isnan(x[k]);
-        if (!ok) {  // "else break" / NaN break: the level ends for this pose with the PoseX it has
-          hp[h].active = 0;
-          continue;
+        int next = 0;
+        if (running[h]) {
+          const double* a = h_acc + static_cast<size_t>(kCvAcc) * h;
+          const int sel = static_cast<int>(a[43]);
+          double N[36], r[6], x[6];
+          std::copy(a, a + 36, N);
+          std::copy(a + 36, a + 42, r);
+          bool ok = sel >= 6 && solve6(N, r, x);
+          if (ok)
+            for (int k = 0; k < 6; ++k) ok = ok && !std::isnan(x[k]);
+          if (ok) {  // (else: "break" — the level ends for this pose with the PoseX it has)
+            pose_from_euler(x, x + 3, &pose_x[16 * h]);
+            const double fval = std::sqrt(a[42]) / static_cast<double>(m);
+            fval_perc[h] = fval / fval_old[h];
+            fval_old[h] = fval;
+            if (fval < fval_min[h]) fval_min[h] = fval;
+            ++it[h];
+            next = !(fval_perc[h] < (1.0 + tol_p) && fval_perc[h] > (1.0 - tol_p)) && it[h] < max_it;
+          }
         }
-        pose_from_euler(x, x + 3, &pose_x[16 * h]);
-        const double fval = std::sqrt(a[42]) / static_cast<double>(m);
-        fval_perc[h] = fval / fval_old[h];
-        fval_old[h] = fval;
-        if (fval < fval_min[h]) fval_min[h] = fval;
-        ++it[h];
-        moved_any = true;
+        running[h] = next;
+        hp[h].active = next;
+        std::copy(&pose_x[16 * h], &pose_x[16 * h] + 16, hp[h].pose);
+        any |= next;
       }
-      if (moved_any) {
-        std::vector<int> keep(H);
-        for (int h = 0; h < H; ++h) {
-          keep[h] = hp[h].active;
-          std::copy(&pose_x[16 * h], &pose_x[16 * h] + 16, hp[h].pose);
-          hp[h].active = running[h] && keep[h];
-        }
+      if (any) {
         PEB_TRY(push_poses());
+        // Src_Moved = PoseX * srcPCT for the poses that iterate again (a pose that stops does not use it any more)
         PEB_LAUNCH(ctx, cv_move, dim3(ceil_div(m, kCvT), H), kCvT, 0, d_pct, m, d_poses, d_moved);
-        for (int h = 0; h < H; ++h) hp[h].active = keep[h];
       }
     }
     for (int h = 0; h < H; ++h) {
