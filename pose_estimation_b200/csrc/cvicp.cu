@@ -20,7 +20,7 @@
 //     cv_threshold     median + scale * 1.48257968 * MAD (two exact radix selects at index m / 2), one block per pose
 //     cv_pick          per scene point the closest accepted source (atomicMin on (distance, source) keys)
 //     cv_accumulate    the 6 x 6 normal equations of the linearised point-to-plane step over the winners + the
-//                      Frobenius error, one block per pose, fixed summation order
+//                      Frobenius error: one record per block, the host adds them in block order
 //     host             solve, PoseX = [Rx (Ry Rz) | t], fval / fval_old against the level's tolerance
 //     cv_move          Src_Moved = PoseX * srcPCT
 #include <algorithm>
@@ -236,7 +236,8 @@ __global__ void __launch_bounds__(128) cv_nn(const GridView g, const float* __re
 // exact order statistic `nth` of m non-negative floats f(i), by three radix passes over the float bits (11 + 11 + 10);
 // one block; returns the value to every thread
 template <typename F>
-__device__ float block_select_nth(F f, int m, int nth, unsigned* hist /* shared [2048] */, unsigned* s_state /* shared [2] */) {
+__device__ float block_select_nth(F f, int m, int nth, unsigned* hist /* shared [2048] */, unsigned* s_state /* shared [2] */,
+                                  unsigned* s_wsum /* shared [32] */) {
   unsigned prefix = 0u, prefix_mask = 0u;
   int want = nth;
   const int shifts[3] = {21, 10, 0};
@@ -247,17 +248,54 @@ __device__ float block_select_nth(F f, int m, int nth, unsigned* hist /* shared 
     __syncthreads();
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
       const unsigned u = __float_as_uint(f(i));
-      if ((u & prefix_mask) == prefix) atomicAdd(&hist[(u >> shifts[pass]) & (nb - 1)], 1u);
+      const bool in = (u & prefix_mask) == prefix;
+      // distances cluster in a few bins: lanes that hit the same bin add once (the loop bound is warp-uniform up to the tail)
+      const unsigned act = __ballot_sync(__activemask(), in);
+      if (in) {
+        const unsigned bin = (u >> shifts[pass]) & (nb - 1);
+        const unsigned peers = __match_any_sync(act, bin);
+        if ((threadIdx.x & 31) == static_cast<unsigned>(__ffs(peers) - 1)) atomicAdd(&hist[bin], static_cast<unsigned>(__popc(peers)));
+      }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      int acc = 0, b = 0;
-      for (; b < nb; ++b) {
-        if (acc + static_cast<int>(hist[b]) > want) break;
-        acc += static_cast<int>(hist[b]);
+    {
+      // the bin that holds the wanted rank: block-wide prefix sum over the bins (blockDim.x = 1024 threads, 1 or 2 bins each)
+      const int per = nb / static_cast<int>(blockDim.x);
+      unsigned local = 0u;
+      for (int k = 0; k < per; ++k) local += hist[threadIdx.x * per + k];
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      unsigned x = local;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += y;
       }
-      s_state[0] = static_cast<unsigned>(b);
-      s_state[1] = static_cast<unsigned>(want - acc);
+      if (lane == 31) s_wsum[warp] = x;
+      __syncthreads();
+      if (warp == 0) {
+        unsigned w = s_wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned y = __shfl_up_sync(0xFFFFFFFFu, w, o);
+          if (lane >= o) w += y;
+        }
+        s_wsum[lane] = w;
+      }
+      __syncthreads();
+      const unsigned before = x - local + (warp ? s_wsum[warp - 1] : 0u);
+      const unsigned w = static_cast<unsigned>(want);
+      if (w >= before && w < before + local) {
+        unsigned acc = before;
+        for (int k = 0; k < per; ++k) {
+          const unsigned c = hist[threadIdx.x * per + k];
+          if (acc + c > w) {
+            s_state[0] = static_cast<unsigned>(threadIdx.x * per + k);
+            s_state[1] = w - acc;
+            break;
+          }
+          acc += c;
+        }
+      }
     }
     __syncthreads();
     prefix |= s_state[0] << shifts[pass];
@@ -273,11 +311,12 @@ __global__ void __launch_bounds__(1024) cv_threshold(const float* __restrict__ d
                                                      const CvPoseDev* __restrict__ poses, float* __restrict__ thr) {
   __shared__ unsigned hist[2048];
   __shared__ unsigned st[2];
+  __shared__ unsigned wsum[32];
   const int h = blockIdx.x;
   if (!poses[h].active) return;
   const float* d = dist + static_cast<size_t>(h) * m;
-  const float med = block_select_nth([&](int i) { return d[i]; }, m, m / 2, hist, st);
-  const float mad = block_select_nth([&](int i) { return fabsf(d[i] - med); }, m, m / 2, hist, st);
+  const float med = block_select_nth([&](int i) { return d[i]; }, m, m / 2, hist, st, wsum);
+  const float mad = block_select_nth([&](int i) { return fabsf(d[i] - med); }, m, m / 2, hist, st, wsum);
   if (threadIdx.x == 0) {
     const float sgm = 1.48257968f * mad;
     thr[h] = rejection_scale * sgm + med;
@@ -300,51 +339,50 @@ __global__ void __launch_bounds__(kCvT) cv_pick(const int* __restrict__ idx, con
   atomicMin(&keys[static_cast<size_t>(h) * ms + j], key);
 }
 
-// normal equations of the linearised point-to-plane step over the winners, one block per pose, fixed order
-__global__ void __launch_bounds__(1024) cv_accumulate(const float* __restrict__ pct, const float* __restrict__ scene, int step,
+// normal equations of the linearised point-to-plane step over the winners: kCvAccBlocks blocks per pose, one record of
+// kCvAcc doubles per block (the host adds the records in block order: fixed summation order)
+constexpr int kCvAccBlocks = 48;
+__global__ void __launch_bounds__(kCvT) cv_accumulate(const float* __restrict__ pct, const float* __restrict__ scene, int step,
                                                       const int* __restrict__ idx, const float* __restrict__ dist, int m, int ms,
                                                       const unsigned long long* __restrict__ keys,
                                                       const CvPoseDev* __restrict__ poses, double* __restrict__ acc_out) {
-  __shared__ double sm[32 * 4], tot[4];
-  const int h = blockIdx.x;
+  __shared__ double sm[(kCvT / 32) * 4], tot[4];
+  const int h = blockIdx.y;
   if (!poses[h].active) return;
   const CvPoseDev& P = poses[h];
-  // 44 sums in groups of 4 so that the live state stays small (the loop body is recomputed per group: it is cheap)
-  for (int g0 = 0; g0 < kCvAcc; g0 += 4) {
-    double v[4] = {0, 0, 0, 0};
-    for (int s = threadIdx.x; s < m; s += blockDim.x) {
-      const int j = idx[static_cast<size_t>(h) * m + s];
-      if (j < 0) continue;
-      const unsigned long long key =
-          (static_cast<unsigned long long>(__float_as_uint(dist[static_cast<size_t>(h) * m + s])) << 32) | static_cast<unsigned>(s);
-      if (keys[static_cast<size_t>(h) * ms + j] != key) continue;  // not the winner of its scene point (or rejected)
-      const float* sp = pct + (static_cast<size_t>(h) * m + s) * 6;
-      const float* dr = scene + 6 * static_cast<size_t>(j) * step;
-      float dn[3];
-      cv_scene_norm(dr, P, dn);
-      const double sx = sp[0], sy = sp[1], sz = sp[2], dx = dn[0], dy = dn[1], dz = dn[2], nx = dr[3], ny = dr[4], nz = dr[5];
-      const double row[6] = {sy * nz - sz * ny, sz * nx - sx * nz, sx * ny - sy * nx, nx, ny, nz};
-      const double b = (dx - sx) * nx + (dy - sy) * ny + (dz - sz) * nz;
+  double v[kCvAcc];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int e = g0 + q;
-        double t;
-        if (e < 36) {
-          t = row[e / 6] * row[e % 6];
-        } else if (e < 42) {
-          t = row[e - 36] * b;
-        } else if (e == 42) {
-          const double e0 = sx - dx, e1 = sy - dy, e2 = sz - dz, e3 = static_cast<double>(sp[3]) - nx,
-                       e4 = static_cast<double>(sp[4]) - ny, e5 = static_cast<double>(sp[5]) - nz;
-          t = e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3 + e4 * e4 + e5 * e5;
-        } else {
-          t = 1.0;
-        }
-        v[q] += t;
-      }
+  for (int e = 0; e < kCvAcc; ++e) v[e] = 0.0;
+  for (int s = blockIdx.x * kCvT + threadIdx.x; s < m; s += gridDim.x * kCvT) {
+    const int j = idx[static_cast<size_t>(h) * m + s];
+    if (j < 0) continue;
+    const unsigned long long key =
+        (static_cast<unsigned long long>(__float_as_uint(dist[static_cast<size_t>(h) * m + s])) << 32) | static_cast<unsigned>(s);
+    if (keys[static_cast<size_t>(h) * ms + j] != key) continue;  // not the winner of its scene point (or rejected)
+    const float* sp = pct + (static_cast<size_t>(h) * m + s) * 6;
+    const float* dr = scene + 6 * static_cast<size_t>(j) * step;
+    float dn[3];
+    cv_scene_norm(dr, P, dn);
+    const double sx = sp[0], sy = sp[1], sz = sp[2], dx = dn[0], dy = dn[1], dz = dn[2], nx = dr[3], ny = dr[4], nz = dr[5];
+    const double row[6] = {sy * nz - sz * ny, sz * nx - sx * nz, sx * ny - sy * nx, nx, ny, nz};
+    const double b = (dx - sx) * nx + (dy - sy) * ny + (dz - sz) * nz;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) v[6 * a + c] += row[a] * row[c];
+      v[36 + a] += row[a] * b;
     }
-    block_sum<4, 1024>(v, sm, tot);
-    if (threadIdx.x < 4) acc_out[static_cast<size_t>(h) * kCvAcc + g0 + threadIdx.x] = tot[threadIdx.x];
+    const double e0 = sx - dx, e1 = sy - dy, e2 = sz - dz, e3 = static_cast<double>(sp[3]) - nx,
+                 e4 = static_cast<double>(sp[4]) - ny, e5 = static_cast<double>(sp[5]) - nz;
+    v[42] += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3 + e4 * e4 + e5 * e5;
+    v[43] += 1.0;
+  }
+  double* out = acc_out + (static_cast<size_t>(h) * gridDim.x + blockIdx.x) * kCvAcc;
+#pragma unroll
+  for (int g0 = 0; g0 < kCvAcc; g0 += 4) {
+    double w[4] = {v[g0], v[g0 + 1], v[g0 + 2], v[g0 + 3]};
+    block_sum<4, kCvT>(w, sm, tot);
+    if (threadIdx.x < 4) out[g0 + threadIdx.x] = tot[threadIdx.x];
     __syncthreads();
   }
 }
@@ -449,7 +487,7 @@ int cvicp_register_device(peb_ctx* ctx, const float* h_model, size_t n_model, co
   const size_t o_lvl = carve(sizeof(float4) * ns);
   const size_t o_poses = carve(sizeof(CvPoseDev) * H);
   const size_t o_sums = carve(sizeof(double) * 4 * static_cast<size_t>(H) * (sblocks + dblocks));
-  const size_t o_acc = carve(sizeof(double) * kCvAcc * H), o_thr = carve(sizeof(float) * H);
+  const size_t o_acc = carve(sizeof(double) * kCvAcc * kCvAccBlocks * H), o_thr = carve(sizeof(float) * H);
   PEB_CUDA(ctx, ctx->cv_arena.ensure(off));
   char* base = ctx->cv_arena.as<char>();
   float* d_model = reinterpret_cast<float*>(base + o_model);
@@ -469,7 +507,7 @@ int cvicp_register_device(peb_ctx* ctx, const float* h_model, size_t n_model, co
   // pinned staging: two pose tables used alternately (every iteration ends with a synchronising read-back, so a table is
   // never rewritten while its upload is in flight), and the accumulator read-back
   const size_t pose_bytes = (sizeof(CvPoseDev) * H + 255) & ~static_cast<size_t>(255);
-  PEB_CUDA(ctx, ctx->h_cv.ensure(2 * pose_bytes + sizeof(double) * kCvAcc * H));
+  PEB_CUDA(ctx, ctx->h_cv.ensure(2 * pose_bytes + sizeof(double) * kCvAcc * kCvAccBlocks * H));
   CvPoseDev* stage[2] = {reinterpret_cast<CvPoseDev*>(ctx->h_cv.as<char>()), reinterpret_cast<CvPoseDev*>(ctx->h_cv.as<char>() + pose_bytes)};
   double* h_acc = reinterpret_cast<double*>(ctx->h_cv.as<char>() + 2 * pose_bytes);
   int stage_k = 0;
@@ -566,14 +604,18 @@ int cvicp_register_device(peb_ctx* ctx, const float* h_model, size_t n_model, co
       if (robust) PEB_LAUNCH(ctx, cv_threshold, H, 1024, 0, d_dist, m, prm->rejection_scale, d_poses, d_thr);
       PEB_CUDA(ctx, cudaMemsetAsync(d_keys, 0xFF, sizeof(unsigned long long) * msl * static_cast<size_t>(H), st));
       PEB_LAUNCH(ctx, cv_pick, dim3(ceil_div(m, kCvT), H), kCvT, 0, d_idx, d_dist, m, msl, d_thr, robust ? 1 : 0, d_poses, d_keys);
-      PEB_LAUNCH(ctx, cv_accumulate, H, 1024, 0, d_pct, d_scene, step, d_idx, d_dist, m, msl, d_keys, d_poses, d_acc);
-      PEB_CUDA(ctx, cudaMemcpyAsync(h_acc, d_acc, sizeof(double) * kCvAcc * H, cudaMemcpyDeviceToHost, st));
+      const int ablocks = std::max(1, std::min(kCvAccBlocks, ceil_div(m, kCvT)));
+      PEB_LAUNCH(ctx, cv_accumulate, dim3(ablocks, H), kCvT, 0, d_pct, d_scene, step, d_idx, d_dist, m, msl, d_keys, d_poses, d_acc);
+      PEB_CUDA(ctx, cudaMemcpyAsync(h_acc, d_acc, sizeof(double) * kCvAcc * ablocks * H, cudaMemcpyDeviceToHost, st));
       PEB_CUDA(ctx, cudaStreamSynchronize(st));
       any = 0;
       for (int h = 0; h < H; ++h) {
         int next = 0;
         if (running[h]) {
-          const double* a = h_acc + static_cast<size_t>(kCvAcc) * h;
+          double a[kCvAcc];
+          for (int e = 0; e < kCvAcc; ++e) a[e] = 0.0;
+          for (int blk = 0; blk < ablocks; ++blk)  // (records of inactive poses are stale: only running poses are read)
+            for (int e = 0; e < kCvAcc; ++e) a[e] += h_acc[(static_cast<size_t>(h) * ablocks + blk) * kCvAcc + e];
           const int sel = static_cast<int>(a[43]);
           double N[36], r[6], x[6];
           std::copy(a, a + 36, N);
