@@ -233,6 +233,55 @@ __global__ void __launch_bounds__(128) cv_nn(const GridView g, const float* __re
   dist[static_cast<size_t>(h) * m + s] = d2;
 }
 
+// The same for a coarse pyramid level: the few thousand scene points of the level are scanned directly from shared-memory
+// tiles (no grid to build); same distance arithmetic and tie rule (smaller distance, then lower index) as the grid search.
+constexpr int kCvBruteMax = 4096;     // level scene points up to which no grid is built
+__global__ void __launch_bounds__(128) cv_nn_brute(const float4* __restrict__ lvl, int msl, const float* __restrict__ scene, int step,
+                                                   const float* __restrict__ moved, int m, const CvPoseDev* __restrict__ poses,
+                                                   int* __restrict__ idx, float* __restrict__ dist) {
+  __shared__ float4 tile[512];
+  const int h = blockIdx.y;
+  if (!poses[h].active) return;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const CvPoseDev& P = poses[h];
+  float q[3] = {0.f, 0.f, 0.f}, ox = 0.f, oy = 0.f, oz = 0.f;
+  if (s < m) {
+    const float* qq = moved + (static_cast<size_t>(h) * m + s) * 6;
+    q[0] = qq[0];
+    q[1] = qq[1];
+    q[2] = qq[2];
+    ox = static_cast<float>(q[0] / P.scale + P.mean_avg[0]);
+    oy = static_cast<float>(q[1] / P.scale + P.mean_avg[1]);
+    oz = static_cast<float>(q[2] / P.scale + P.mean_avg[2]);
+  }
+  float best_d = pos_inf();
+  int best_j = -1;
+  for (int t0 = 0; t0 < msl; t0 += 512) {
+    const int cnt = min(512, msl - t0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) tile[k] = lvl[t0 + k];
+    __syncthreads();
+    for (int k = 0; k < cnt; ++k) {
+      const float4 p = tile[k];
+      if (!finite3(p.x, p.y, p.z)) continue;  // (the grid leaves non-finite points out as well)
+      const float d2 = l2_simple(ox, oy, oz, p.x, p.y, p.z);
+      if (d2 < best_d) {  // ascending index: the first of equal distances stays
+        best_d = d2;
+        best_j = t0 + k;
+      }
+    }
+  }
+  if (s >= m) return;
+  float d2 = 0.0f;
+  if (best_j >= 0) {
+    float t[3];
+    cv_scene_norm(scene + 6 * static_cast<size_t>(best_j) * step, P, t);
+    d2 = l2_simple(q[0], q[1], q[2], t[0], t[1], t[2]);
+  }
+  idx[static_cast<size_t>(h) * m + s] = best_j;
+  dist[static_cast<size_t>(h) * m + s] = d2;
+}
+
 // exact order statistic `nth` of m non-negative floats f(i), by three radix passes over the float bits (11 + 11 + 10);
 // one block; returns the value to every thread
 template <typename F>
@@ -578,8 +627,12 @@ int cvicp_register_device(peb_ctx* ctx, const float* h_model, size_t n_model, co
     const int m = ceil_div(n, step), msl = ceil_div(ns, step);
     // the level's scene grid (original coordinates, shared by all poses)
     PEB_LAUNCH(ctx, cv_gather_xyz, ceil_div(msl, 256), 256, 0, d_scene, step, msl, d_lvl);
-    PEB_TRY(grid_build(ctx, &ctx->aux_grid, d_lvl, nullptr, msl, 2.0f));
-    const GridView g = ctx->aux_grid.view;
+    const bool brute = msl <= kCvBruteMax;  // coarse levels: scanning the level's scene beats building a grid for it
+    GridView g{};
+    if (!brute) {
+      PEB_TRY(grid_build(ctx, &ctx->aux_grid, d_lvl, nullptr, msl, 2.0f));
+      g = ctx->aux_grid.view;
+    }
     for (int h = 0; h < H; ++h) {
       std::copy(&pose[16 * h], &pose[16 * h] + 16, hp[h].pose);
       hp[h].active = 1;
@@ -600,7 +653,10 @@ int cvicp_register_device(peb_ctx* ctx, const float* h_model, size_t n_model, co
     }
     if (any) PEB_TRY(push_poses());  // (the kernels of an iteration only read `active`; cv_move also the pose = PoseX)
     while (any) {
-      PEB_LAUNCH(ctx, cv_nn, dim3(ceil_div(m, 128), H), 128, 0, g, d_scene, step, d_moved, m, d_poses, d_idx, d_dist);
+      if (brute)
+        PEB_LAUNCH(ctx, cv_nn_brute, dim3(ceil_div(m, 128), H), 128, 0, d_lvl, msl, d_scene, step, d_moved, m, d_poses, d_idx, d_dist);
+      else
+        PEB_LAUNCH(ctx, cv_nn, dim3(ceil_div(m, 128), H), 128, 0, g, d_scene, step, d_moved, m, d_poses, d_idx, d_dist);
       if (robust) PEB_LAUNCH(ctx, cv_threshold, H, 1024, 0, d_dist, m, prm->rejection_scale, d_poses, d_thr);
       PEB_CUDA(ctx, cudaMemsetAsync(d_keys, 0xFF, sizeof(unsigned long long) * msl * static_cast<size_t>(H), st));
       PEB_LAUNCH(ctx, cv_pick, dim3(ceil_div(m, kCvT), H), kCvT, 0, d_idx, d_dist, m, msl, d_thr, robust ? 1 : 0, d_poses, d_keys);
