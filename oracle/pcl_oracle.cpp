@@ -1670,10 +1670,11 @@ static void transform_pc_pose(const std::vector<float>& pc, const double* P, std
   }
 }
 
+// [CV] ppf_helpers.cpp : samplePCUniform — numRows = rows / sampleStep (integer division) rows, taken at 0, step, 2 step, ...
 static void sample_uniform(const std::vector<float>& pc, int step, std::vector<float>& out) {
-  const size_t n = pc.size() / 6;
+  const size_t n = pc.size() / 6, rows = n / static_cast<size_t>(step);
   out.clear();
-  for (size_t i = 0; i < n; i += static_cast<size_t>(step)) out.insert(out.end(), &pc[6 * i], &pc[6 * i] + 6);
+  for (size_t c = 0; c < rows; ++c) out.insert(out.end(), &pc[6 * c * step], &pc[6 * c * step] + 6);
 }
 
 static int cv_round(double v) { return static_cast<int>(std::lrint(v)); }  // cvRound: to nearest, ties to even
@@ -1801,6 +1802,7 @@ static void register_one(const std::vector<float>& src_in, const std::vector<flo
     const int step = std::max(1, cv_round(static_cast<double>(n) / static_cast<double>(std::max(num_samples, 1))));
     sample_uniform(moved_full, step, src_pct);
     sample_uniform(dst0, step, dst_pcs);
+    if (src_pct.empty() || dst_pcs.empty()) continue;  // (a level coarser than the clouds: nothing to iterate on)
     KdTree tree;
     tree.build(dst_pcs.data(), dst_pcs.size() / 6, 24);
     double fval_old = 9999999999.0, fval_perc = 0.0, fval_min = 9999999999.0;

@@ -624,7 +624,9 @@ int cvicp_register_device(peb_ctx* ctx, const float* h_model, size_t n_model, co
     const double tol_p = static_cast<double>(prm->tolerance) * static_cast<double>(level + 1) * (level + 1);
     const int max_it = cv_round(static_cast<double>(prm->iterations) / (level + 1));
     const int step = std::max(1, cv_round(static_cast<double>(n) / static_cast<double>(std::max(num_samples, 1))));
-    const int m = ceil_div(n, step), msl = ceil_div(ns, step);
+    // [CV] samplePCUniform: rows / sampleStep (integer division) rows, taken at 0, step, 2 step, ...
+    const int m = n / step, msl = ns / step;
+    if (m == 0 || msl == 0) continue;  // a level coarser than the clouds: nothing to iterate on (PoseX = I)
     // the level's scene grid (original coordinates, shared by all poses)
     PEB_LAUNCH(ctx, cv_gather_xyz, ceil_div(msl, 256), 256, 0, d_scene, step, msl, d_lvl);
     const bool brute = msl <= kCvBruteMax;  // coarse levels: scanning the level's scene beats building a grid for it
