@@ -113,9 +113,18 @@ PEB_API void peb_icp_params_default(peb_icp_params* p);
 PEB_API void* peb_ctx_stream(peb_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches claim) */
 PEB_API uint64_t peb_ctx_launch_count(const peb_ctx* ctx);
-/* tuning knobs that change speed, never results: "nn_group" (lanes per nearest-neighbour query:
- * 1, 2, 4, 8, 16), "grid_occupancy_x100" (wanted points per occupied target-grid cell x 100;
- * takes effect at the next peb_target_set), "profile" (0/1, see peb_profile_read) */
+/* tuning knobs that change speed, never results (tests/test_gpu_parity.py asserts bit-identical records for
+ * every one of them): "nn_group" (lanes per COLD nearest-neighbour query: 1, 2, 4, 8, 16),
+ * "grid_occupancy_x100" (wanted points per occupied target-grid cell x 100, default 350; takes effect at
+ * the next peb_target_set), "source_sort_occupancy" (points per cell of the source's own sort grid = patch
+ * compactness, default 32), "warm_start" (iterations >= 1 seed their search with the previous match),
+ * "anchor_seed" / "seed_guard_x10" / "coop_max_rows" (first iteration of a batch: one anchor search per
+ * 32-point patch, how far a point may be from its anchor in cells x 10, and up to how many grid rows a patch
+ * verifies its candidates warp-cooperatively; 0 = per lane), "batch_streams" (independent chains of launches
+ * of a batched align, 0 = auto), "blocks_factor" / "blocks_factor_cold" (blocks per SM and launch, 0 = auto),
+ * "flag_deps" (warm launches of a batch wait per hypothesis instead of for the whole previous grid),
+ * "pdl" (programmatic dependent launch), "cert_margin_x1000" (search-skipping certificates, off),
+ * "profile" (0 / 1 / 2, see peb_profile_read), "debug_timers" (development) */
 PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value);
 
 /* ---- pcl::VoxelGrid<PointXYZ>::filter  [PCL] filters/.../impl/voxel_grid.hpp -------- */
