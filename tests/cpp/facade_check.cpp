@@ -95,6 +95,37 @@ int main(int argc, char** argv) {
     print_T("batch0", res[0]);
     print_T("batch1", res[1]);
 
+    // cv::ppf_match_3d::ICP as the reference calls it: model / scene with the normals computed above, two poses
+    {
+      pe_b200::NormalEstimation nes(ctx);
+      nes.setInputCloud(src.data(), n_src, 16);
+      nes.setKSearch(k);
+      std::vector<float> src_normals;
+      nes.compute(src_normals);
+      auto pack6 = [](const std::vector<float>& xyz4, const std::vector<float>& nrm8, std::vector<float>& out) {
+        out.clear();
+        for (size_t i = 0; i < xyz4.size() / 4; ++i) {
+          const float* p = &xyz4[4 * i];
+          const float* q = &nrm8[8 * i];
+          if (!(q[0] == q[0])) continue;  // NaN normal
+          out.insert(out.end(), {p[0], p[1], p[2], q[0], q[1], q[2]});
+        }
+      };
+      std::vector<float> model6, scene6;
+      pack6(src, src_normals, model6);
+      pack6(ds, normals, scene6);
+      std::vector<double> cvposes(32, 0.0), residuals(2, 0.0);
+      for (int p = 0; p < 2; ++p)
+        for (int r = 0; r < 4; ++r)
+          for (int c = 0; c < 4; ++c) cvposes[16 * p + 4 * r + c] = poses[16 * p + 4 * c + r];  // column-major -> row-major
+      pe_b200::CvIcp cvicp(ctx, 250, 0.005f, 2.5f, 8);
+      cvicp.registerModelToScene(model6.data(), model6.size() / 6, scene6.data(), scene6.size() / 6, cvposes.data(), 2,
+                                 residuals.data());
+      std::printf("cvicp residuals %.17g %.17g pose0", residuals[0], residuals[1]);
+      for (int i = 0; i < 16; ++i) std::printf(" %.17g", cvposes[i]);
+      std::printf("\n");
+    }
+
     // PCL options without a CUDA path must be refused, not emulated
     try {
       icp.setUseReciprocalCorrespondences(true);

@@ -88,9 +88,23 @@ def test_facade_matches_python_host_classes(exe, tmp_path):
         assert it == icp.nr_iterations_ and state == icp.result.state
         assert np.array_equal(T, icp.getFinalTransformation())
         assert fit == icp.getFitnessScore()
+        if tag == "icp_p2p":
+            T_p2p = T
     it0, _, fit0, T0 = parse("batch0")
     it1, _, fit1, _ = parse("batch1")
     _, _, fit, T = parse("icp_p2p")
     assert np.array_equal(T0, T) and fit0 == fit and it0 == 30 and it1 == 30 and fit1 <= fit0 * 1.01
     assert "unsupported-option refused: code -6" in r.stdout
+    # the cv ICP of the facade against the Python mirror (same library underneath: bit-identical)
+    nes = pcl.NormalEstimation(ctx)
+    nes.setInputCloud(prob.source)
+    nes.setKSearch(12)
+    sn = nes.compute()
+    ok_m, ok_s = np.isfinite(sn[:, 0]), np.isfinite(nrm[:, 0])
+    model6 = np.concatenate([prob.source[ok_m, :3], sn[ok_m, :3]], 1).astype(np.float32)
+    scene6 = np.concatenate([ds[ok_s, :3], nrm[ok_s, :3]], 1).astype(np.float32)
+    poses2 = np.stack([np.eye(4), np.asarray(T_p2p, np.float64)])
+    got, res = pcl.CvIcp(250, 0.005, 2.5, 8, ctx=ctx).registerModelToScene(model6, scene6, poses2)
+    cv = [float(v) for v in lines["cvicp"][2:4]] , [float(v) for v in lines["cvicp"][5:21]]
+    assert np.array_equal(np.array(cv[0]), res) and np.array_equal(np.array(cv[1]).reshape(4, 4), got[0])
     ctx.close()
