@@ -316,3 +316,25 @@ def make_c4(scale: float = 1.0, n_guesses: int = 1024, seed: int = 4, downsample
     s2 = scale * scale
     return make_scene_problem("C4", seed, max(int(50000 * s2), 500), int(490000 * s2), int(510000 * s2), w, h,
                               n_guesses=n_guesses, downsample=downsample)
+
+
+# ------------------------------------------------------------------------------------------
+# clouds with normals + start poses for the cv::ppf_match_3d::ICP mode (N x 6 float rows)
+# ------------------------------------------------------------------------------------------
+def make_cvicp_case(seed=0, n_model=4000, n_scene=9000, n_poses=6, noise=1e-4, clutter=0, angle=4.0, trans=0.006):
+    rng = np.random.default_rng(seed)
+    surf = Surface(3 + seed)
+    pts, nrm = surf.sample(n_model, rng)
+    gt = default_gt_pose(rng)
+    model = np.concatenate([pts, nrm], 1).astype(np.float32)
+    spts, snrm = surf.sample(n_scene, rng)
+    xyz = apply_pose(gt, spts) + rng.normal(0, noise, spts.shape)
+    sn = (gt[:3, :3] @ snrm.T).T
+    if clutter:
+        cx = rng.uniform([-0.2, -0.2, 0.6], [0.2, 0.2, 0.8], (clutter, 3))
+        cn = rng.normal(size=(clutter, 3))
+        cn /= np.linalg.norm(cn, axis=1, keepdims=True)
+        xyz, sn = np.concatenate([xyz, cx]), np.concatenate([sn, cn])
+    scene = np.concatenate([xyz, sn], 1).astype(np.float32)
+    poses = np.stack([perturb_pose(gt, rng, angle, trans) for _ in range(n_poses)])
+    return model, scene, poses, gt

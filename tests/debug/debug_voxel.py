@@ -1,7 +1,7 @@
 import sys
 from pathlib import Path
 import numpy as np
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 from oracle import Oracle
 from pose_estimation_b200 import pcl

@@ -10,23 +10,7 @@ from oracle import cvicp_params
 from pose_estimation_b200.testing import synth
 
 
-def make_case(seed=0, n_model=4000, n_scene=9000, n_poses=6, noise=1e-4, clutter=0, angle=4.0, trans=0.006):
-    rng = np.random.default_rng(seed)
-    surf = synth.Surface(3 + seed)
-    pts, nrm = surf.sample(n_model, rng)
-    gt = synth.default_gt_pose(rng)
-    model = np.concatenate([pts, nrm], 1).astype(np.float32)
-    spts, snrm = surf.sample(n_scene, rng)
-    xyz = synth.apply_pose(gt, spts) + rng.normal(0, noise, spts.shape)
-    sn = (gt[:3, :3] @ snrm.T).T
-    if clutter:
-        cx = rng.uniform([-0.2, -0.2, 0.6], [0.2, 0.2, 0.8], (clutter, 3))
-        cn = rng.normal(size=(clutter, 3))
-        cn /= np.linalg.norm(cn, axis=1, keepdims=True)
-        xyz, sn = np.concatenate([xyz, cx]), np.concatenate([sn, cn])
-    scene = np.concatenate([xyz, sn], 1).astype(np.float32)
-    poses = np.stack([synth.perturb_pose(gt, rng, angle, trans) for _ in range(n_poses)])
-    return model, scene, poses, gt
+make_case = synth.make_cvicp_case
 
 
 def test_oracle_converges_to_the_ground_truth(oracle):

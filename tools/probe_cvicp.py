@@ -7,9 +7,8 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
-sys.path.insert(0, str(ROOT / "tests"))
 from pose_estimation_b200 import pcl  # noqa: E402
-from test_cvicp import make_case  # noqa: E402
+from pose_estimation_b200.testing.synth import make_cvicp_case as make_case  # noqa: E402
 
 ctx = pcl.Context(0)
 model, scene, poses, gt = make_case(seed=5, n_model=50000, n_scene=200000, clutter=20000)

@@ -8,13 +8,20 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
-from oracle import Oracle, default_params  # noqa: E402  (the oracle only generates the down-sampled scene here)
 from pose_estimation_b200 import pcl  # noqa: E402
 from pose_estimation_b200.testing import synth  # noqa: E402
 
-orc = Oracle()
-prob = synth.make_c2(scale=0.3, downsample=lambda p, leaf: orc.voxel_grid(p, leaf)[0])
 ctx = pcl.Context(0)
+
+
+def _downsample(points, leaf):
+    vg = pcl.VoxelGrid(ctx)
+    vg.setInputCloud(points)
+    vg.setLeafSize(leaf)
+    return vg.filter()
+
+
+prob = synth.make_c2(scale=0.3, downsample=_downsample)
 rng = np.random.default_rng(0)
 bad = 0
 cases = 0
@@ -28,10 +35,10 @@ for trial in range(40):
     icp = pcl.IterativeClosestPoint(ctx)
     icp.setInputSource(src)
     icp.setInputTarget(prob.target)
-    prm = default_params(max_iterations=its, max_corr_dist=0.02, abs_mse_threshold=-1.0 if not crit else 1e-12,
-                         transformation_epsilon=1e-9 if crit else 0.0)
-    for name, _ in prm._fields_:
-        setattr(icp.params, name, getattr(prm, name))
+    icp.setMaximumIterations(its)
+    icp.setMaxCorrespondenceDistance(0.02)
+    icp.getConvergeCriteria().setAbsoluteMSE(-1.0 if not crit else 1e-12)
+    icp.setTransformationEpsilon(1e-9 if crit else 0.0)
     res = icp.alignBatch(guesses)
     for h in rng.choice(H, min(H, 6), replace=False):
         icp.align(guesses[h], want_output=False)
