@@ -769,10 +769,10 @@ int launch_fitness_g(peb_ctx* ctx, int G, const IcpLaunch& L, size_t H) {
 // a single align spreads over the whole chip, batched aligns give every hypothesis a few blocks
 // and let grid.y fill the machine
 // factor = blocks per SM and launch, summed over all hypotheses.  0 = measured defaults (B200, C4):
-// large batches like many small blocks (their cold launch is uneven), small batches pay the fixed
-// cost of a block (state load, 17-value reduction, ticket) per ~10 queries a thread and like fewer
+// a block pays a fixed cost (state load, 17-value reduction, ticket), so fewer and larger blocks win as long
+// as the launch tails are hidden (chains, per-hypothesis dependencies); small batches need enough blocks to fill the machine
 int blocks_for(int n, size_t H, int G, int factor) {
-  if (factor <= 0) factor = H >= 512 ? 64 : (H >= 256 ? 32 : 16);
+  if (factor <= 0) factor = H >= 256 ? 32 : 16;  // (with per-hypothesis launch dependencies: 1024 hypotheses 89.2 ms at 24-32, 90.6 at 64)
   const int want = ceil_div(std::max(n, 1), kIcpThreads / G);
   int bph;
   if (H == 1)
