@@ -143,6 +143,26 @@ def test_warm_started_search_is_exact_for_any_candidate(hc, oracle, occupancy):
     assert (gd[~acc] > lim).all()
 
 
+@pytest.mark.parametrize("offset,occupancy", [(0.0, 0.25), (8.0, 0.25), (40.0, 0.5), (-300.0, 2.0)])
+def test_ball_search_in_cell_units_survives_large_coordinates(hc, oracle, offset, occupancy):
+    """The ball search works in cell units ((q - origin) / h, computed like the cell assignment of the target): clouds
+    far from the origin and grids with thousands of cells per axis stress the rounding its margins must cover."""
+    rng = np.random.default_rng(23)
+    prob = synth.make_c1(6000, seed=24)
+    tgt = np.ascontiguousarray(prob.target[:, :3]) + np.float32(offset)
+    tgt[50:55] = tgt[50]
+    n = 2000
+    base = prob.source[:n, :3] + np.float32(offset)
+    step = rng.normal(size=(n, 3)).astype(np.float32)
+    step *= (rng.uniform(0.0, 0.004, n) / np.linalg.norm(step, axis=1))[:, None].astype(np.float32)
+    q = np.ascontiguousarray(np.concatenate([base + step, tgt[:300] + np.float32(1e-5), tgt[50:51]]))
+    bi, bd = oracle.nn_bruteforce(tgt, q)
+    for name, prev in (("true", bi), ("random", rng.integers(0, len(tgt), len(bi)))):
+        gi, gd = grid_nn_warm(hc, tgt, q, prev, occupancy)
+        assert np.array_equal(gd, bd), (name, offset)
+        assert np.array_equal(gi, bi), (name, offset)
+
+
 @pytest.mark.parametrize("occupancy", [0.5, 2.0, 8.0])
 def test_seeded_and_large_ball_searches_are_exact(hc, oracle, occupancy):
     """Far queries (balls spanning dozens of cells) seeded with the match of
