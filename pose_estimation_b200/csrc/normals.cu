@@ -5,8 +5,8 @@
 // The k nearest neighbours (the point itself included, ascending squared distance, exactly
 // what KdTreeFLANN::nearestKSearch returns) come from a uniform grid over the cloud whose cell
 // edge is chosen so that the 3x3x3 block around a point usually already holds them.  One thread
-// per point; its candidate list lives in shared memory, column per thread (bank = thread), kept
-// sorted by insertion.  Points are processed in grid (cell) order, so the threads of a warp scan
+// per point; its candidate list lives in shared memory, column per thread, kept sorted by insertion
+// (64-bit (distance, position) keys: one compare / load / store per shift).  Points are processed in grid (cell) order, so the threads of a warp scan
 // the same rows and hit L1.  The covariance is then accumulated over the neighbours IN LIST
 // ORDER, sequentially, in float, without FMA — PCL 1.10's single-pass
 // computeMeanAndCovarianceMatrix — followed by the closed-form eigen33 (core_math.cuh).
@@ -17,37 +17,39 @@ namespace peb {
 
 namespace {
 
+// The candidate list of one thread: k entries, ascending.  An entry is the 64-bit key
+// (squared distance bits << 32) | sorted position: squared distances are non-negative floats, so the integer order of
+// the keys is the list's order (smaller distance first, then smaller position) and one 64-bit compare / load / store
+// does the work of two.
 struct KnnList {
-  float* d;   // [k][T], this thread's column
-  int* j;     // sorted positions of the neighbours
-  int stride; // T
+  unsigned long long* e;  // [k][T], this thread's column
+  int stride;             // T
   int k;
   int count;
-  float worst;
-  int worst_j;
+  unsigned long long worst;  // key of the last entry once the list is full
 };
 
+__device__ __forceinline__ unsigned long long knn_key(float d2, int j) {
+  return (static_cast<unsigned long long>(__float_as_uint(d2)) << 32) | static_cast<unsigned>(j);
+}
+__device__ __forceinline__ int knn_key_pos(unsigned long long key) { return static_cast<int>(key & 0xFFFFFFFFull); }
+
 __device__ __forceinline__ void knn_insert(KnnList& l, float d2, int j) {
-  if (l.count == l.k && !(d2 < l.worst || (d2 == l.worst && j < l.worst_j))) return;
+  const unsigned long long key = knn_key(d2, j);
+  if (l.count == l.k && !(key < l.worst)) return;
   int pos = (l.count < l.k) ? l.count : l.k - 1;
   while (pos > 0) {
-    const float pd = l.d[(pos - 1) * l.stride];
-    const int pj = l.j[(pos - 1) * l.stride];
-    if (pd > d2 || (pd == d2 && pj > j)) {
-      l.d[pos * l.stride] = pd;
-      l.j[pos * l.stride] = pj;
+    const unsigned long long prev = l.e[(pos - 1) * l.stride];
+    if (prev > key) {
+      l.e[pos * l.stride] = prev;
       --pos;
     } else {
       break;
     }
   }
-  l.d[pos * l.stride] = d2;
-  l.j[pos * l.stride] = j;
+  l.e[pos * l.stride] = key;
   if (l.count < l.k) ++l.count;
-  if (l.count == l.k) {
-    l.worst = l.d[(l.k - 1) * l.stride];
-    l.worst_j = l.j[(l.k - 1) * l.stride];
-  }
+  if (l.count == l.k) l.worst = l.e[(l.k - 1) * l.stride];
 }
 
 __device__ __forceinline__ void knn_scan_range(const GridView& g, uint32_t s, uint32_t e, float qx, float qy, float qz,
@@ -89,22 +91,19 @@ __global__ void normals_fill_nan_kernel(float* __restrict__ out8, int n) {
 
 __global__ void normals_knn_kernel(const GridView g, int k, float vx, float vy, float vz, float* __restrict__ out8,
                                    int32_t* __restrict__ out_nn) {
-  extern __shared__ unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T = blockDim.x;
-  float* sd = reinterpret_cast<float*>(smem_raw);
-  int* sj = reinterpret_cast<int*>(smem_raw + static_cast<size_t>(k) * T * sizeof(float));
+  unsigned long long* se = reinterpret_cast<unsigned long long*>(smem_raw);
   const int q = blockIdx.x * T + threadIdx.x;
   if (q >= g.n) return;
   const float4 p = g.pts[q];
   const int orig = __float_as_int(p.w);
   KnnList l;
-  l.d = sd + threadIdx.x;
-  l.j = sj + threadIdx.x;
+  l.e = se + threadIdx.x;
   l.stride = T;
   l.k = min(k, g.n);
   l.count = 0;
-  l.worst = pos_inf();
-  l.worst_j = 0x7fffffff;
+  l.worst = ~0ull;
   const int cx = grid_coord(p.x, g.ox, g.inv_h, g.dx);
   const int cy = grid_coord(p.y, g.oy, g.inv_h, g.dy);
   const int cz = grid_coord(p.z, g.oz, g.inv_h, g.dz);
@@ -114,19 +113,19 @@ __global__ void normals_knn_kernel(const GridView g, int k, float vx, float vy, 
     knn_scan_ring(g, p.x, p.y, p.z, cx, cy, cz, r, full, l);
     bool covers_all;
     const float b2 = grid_ring_bound2(g, p.x, p.y, p.z, cx, cy, cz, r, covers_all);
-    if (covers_all || (l.count == l.k && l.worst <= b2)) break;
+    if (covers_all || (l.count == l.k && __uint_as_float(static_cast<unsigned>(l.worst >> 32)) <= b2)) break;
     ++r;
     full = false;
   }
   float* o = out8 + 8 * static_cast<size_t>(orig);
   if (out_nn) {
     for (int i = 0; i < k; ++i)
-      out_nn[static_cast<size_t>(orig) * k + i] = i < l.count ? __float_as_int(g.pts[l.j[i * T]].w) : -1;
+      out_nn[static_cast<size_t>(orig) * k + i] = i < l.count ? __float_as_int(g.pts[knn_key_pos(l.e[i * T])].w) : -1;
   }
   if (l.count < 3) return;  // stays NaN ([PCL] normal_3d.h: computePointNormal fails below 3 points)
   float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int i = 0; i < l.count; ++i) {
-    const float4 c = g.pts[l.j[i * T]];
+    const float4 c = g.pts[knn_key_pos(l.e[i * T])];
     accu[0] += c.x * c.x;
     accu[1] += c.x * c.y;
     accu[2] += c.x * c.z;
