@@ -18,8 +18,13 @@
 //     vectors in tests/golden/;
 //   - umeyama against a float64 numpy Kabsch, the LLS step against numpy lstsq, eigen33 against
 //     numpy eigh, VoxelGrid against an independent numpy dict-of-cells restatement.
+//   - the plane RANSAC (pcl::SACSegmentation, SACMODEL_PLANE + SAC_RANSAC; tests/test_sac.py): its Mersenne twister
+//     against the C++ standard's known answer and numpy's RandomState(12345) stream, the sequential loop against an
+//     independent numpy restatement (bit-identical coefficients, iteration counts, inlier lists).
 // The remaining statements (operation order, float/double choices, the convergence state
-// machine) are recollections of upstream source and carry no external pin.
+// machine) are recollections of upstream source and carry no external pin.  The same holds for
+// the cv::ppf_match_3d::ICP restatement at the end of this file (opencv_contrib is not in the image
+// either): it is checked for what an ICP must do (tests/test_cvicp.py), not against OpenCV.
 //
 // Canonical arithmetic: IEEE-754 binary32/binary64, round-to-nearest, NO fused contraction
 // (build with -ffp-contract=off), PCL's source-level operation order.
