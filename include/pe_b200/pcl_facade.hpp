@@ -361,6 +361,69 @@ class CvIcp {
   peb_cvicp_params p_;
 };
 
+// The manager's side of the pose (pose_estimation_manager/src/pose_transformer.cpp:78-121, PoseTransformer::obj_in_base_frame):
+// the published {x, y, z, qx, qy, qz, qw} (camera frame) -> hand-eye calibration (row-major 4x4, he_calibration_mat_) -> the
+// grasp frame sent to the robot: the object's y axis is kept, z is the base's -z (or +x when y is more than ~37 degrees out of
+// the horizontal) made orthogonal to y, x = y x z.  float like the reference's Eigen types; out7 = 7 doubles.
+inline void obj_in_base_frame(const float pose7[7], const float he16[16], double out7[7]) {
+  float q[4] = {pose7[3], pose7[4], pose7[5], pose7[6]};  // x y z w
+  const float qn = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (float& v : q) v /= qn;
+  const float x = q[0], y = q[1], z = q[2], w = q[3];
+  const float R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - z * w),     2 * (x * z + y * w),
+                      2 * (x * y + z * w),     1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                      2 * (x * z - y * w),     2 * (y * z + x * w),     1 - 2 * (x * x + y * y)};
+  float cam[16] = {R[0], R[1], R[2], pose7[0], R[3], R[4], R[5], pose7[1], R[6], R[7], R[8], pose7[2], 0, 0, 0, 1};
+  float base[16];
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) {
+      float a = 0.0f;
+      for (int k = 0; k < 4; ++k) a += he16[4 * r + k] * cam[4 * k + c];
+      base[4 * r + c] = a;
+    }
+  const float yv[3] = {base[1], base[5], base[9]};
+  float zb[3] = {0.0f, 0.0f, -1.0f};
+  if (std::fabs(yv[2]) > 0.6f) zb[0] = 1.0f, zb[2] = 0.0f;
+  const float f = (zb[0] * yv[0] + zb[1] * yv[1] + zb[2] * yv[2]) / (yv[0] * yv[0] + yv[1] * yv[1] + yv[2] * yv[2]);
+  const float zv[3] = {zb[0] - f * yv[0], zb[1] - f * yv[1], zb[2] - f * yv[2]};
+  const float xv[3] = {yv[1] * zv[2] - yv[2] * zv[1], yv[2] * zv[0] - yv[0] * zv[2], yv[0] * zv[1] - yv[1] * zv[0]};
+  auto norm3 = [](const float* v) { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); };
+  const float nx = norm3(xv), ny = norm3(yv), nz = norm3(zv);
+  float T[16] = {0};  // column-major for rotation_to_quat: columns x, y, z
+  for (int i = 0; i < 3; ++i) {
+    T[i] = xv[i] / nx;
+    T[4 + i] = yv[i] / ny;
+    T[8 + i] = zv[i] / nz;
+  }
+  // Eigen::Quaternionf(Matrix3f): no sign normalisation
+  const float m00 = T[0], m10 = T[1], m20 = T[2], m01 = T[4], m11 = T[5], m21 = T[6], m02 = T[8], m12 = T[9], m22 = T[10];
+  const float m[3][3] = {{m00, m01, m02}, {m10, m11, m12}, {m20, m21, m22}};
+  float qo[4];  // x y z w
+  float t = m00 + m11 + m22;
+  if (t > 0.0f) {
+    t = std::sqrt(t + 1.0f);
+    qo[3] = 0.5f * t;
+    t = 0.5f / t;
+    qo[0] = (m21 - m12) * t;
+    qo[1] = (m02 - m20) * t;
+    qo[2] = (m10 - m01) * t;
+  } else {
+    int i = 0;
+    if (m11 > m00) i = 1;
+    if (m22 > m[i][i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(m[i][i] - m[j][j] - m[k][k] + 1.0f);
+    qo[i] = 0.5f * t;
+    t = 0.5f / t;
+    qo[3] = (m[k][j] - m[j][k]) * t;
+    qo[j] = (m[j][i] + m[i][j]) * t;
+    qo[k] = (m[k][i] + m[i][k]) * t;
+  }
+  const float qm = std::sqrt(qo[0] * qo[0] + qo[1] * qo[1] + qo[2] * qo[2] + qo[3] * qo[3]);
+  out7[0] = base[3], out7[1] = base[7], out7[2] = base[11];
+  for (int i = 0; i < 4; ++i) out7[3 + i] = qo[i] / qm;
+}
+
 class IterativeClosestPointWithNormals : public IterativeClosestPoint {
  public:
   explicit IterativeClosestPointWithNormals(Context& c) : IterativeClosestPoint(c, PEB_ESTIMATOR_POINT_TO_PLANE_LLS) {}

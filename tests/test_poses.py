@@ -96,3 +96,42 @@ def test_grasp_frame_of_the_manager():
         assert np.allclose(got, rot, atol=5e-6)
         assert abs(np.linalg.det(got) - 1) < 1e-5 and np.allclose(got[:, 1], y / np.linalg.norm(y), atol=5e-6)
         assert np.allclose(poses.hover_pose(np.concatenate([t_cam, q]), he) - out, [0, 0, 0.1, 0, 0, 0, 0])
+
+
+def test_cpp_grasp_frame_agrees_with_the_python_mirror(tmp_path):
+    src = tmp_path / "grasp_check.cpp"
+    src.write_text(r"""
+#include <cstdio>
+#include "pe_b200/pcl_facade.hpp"
+int main() {
+  float in[23];
+  for (;;) {
+    for (int i = 0; i < 23; ++i) if (std::scanf("%f", in + i) != 1) return 0;
+    double out[7];
+    pe_b200::obj_in_base_frame(in, in + 7, out);
+    for (int i = 0; i < 7; ++i) std::printf("%.9g ", out[i]);
+    std::printf("\n");
+  }
+}
+""")
+    exe = tmp_path / "grasp_check"
+    r = subprocess.run(["g++", "-std=c++17", "-I", str(ROOT / "include"), str(src), "-o", str(exe), "-L",
+                        str(ROOT / "pose_estimation_b200"), "-lpe_b200", f"-Wl,-rpath,{ROOT / 'pose_estimation_b200'}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rng = np.random.default_rng(9)
+    cases = []
+    for _ in range(100):
+        q = Rotation.random(random_state=int(rng.integers(1 << 31))).as_quat() * rng.uniform(0.5, 2.0)
+        he = synth.make_pose(Rotation.random(random_state=int(rng.integers(1 << 31))).as_matrix(), rng.normal(size=3))
+        cases.append((np.concatenate([rng.normal(size=3), q]).astype(np.float32), np.asarray(he, np.float32)))
+    inp = "\n".join(" ".join(f"{v:.9g}" for v in np.concatenate([p, he.reshape(-1)])) for p, he in cases)
+    out = subprocess.run([str(exe)], input=inp, capture_output=True, text=True).stdout.strip().splitlines()
+    assert len(out) == len(cases)
+    for (p, he), line in zip(cases, out):
+        got = np.array([float(v) for v in line.split()])
+        ref = poses.obj_in_base_frame(p, he)
+        y2 = (he @ synth.make_pose(Rotation.from_quat(p[3:] / np.linalg.norm(p[3:])).as_matrix(), p[:3]))[2, 1]
+        if abs(abs(y2) - 0.6) < 1e-3:
+            continue  # the two float32 evaluation orders may take different branches exactly at the switch
+        assert np.allclose(got[:3], ref[:3], atol=5e-6) and np.allclose(got[3:], ref[3:], atol=5e-6)
