@@ -189,6 +189,18 @@ PEB_API int peb_sac_plane(peb_ctx* ctx, const void* pts, size_t n, size_t stride
 PEB_API int peb_sac_plane_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, const peb_sac_params* params,
                               float out_coeff[4], int32_t* d_out_inliers, size_t* out_n_inliers, int32_t* out_iterations);
 
+/* ---- PoseEstimation::create_surface_match_pc in one call ------------------------------------------
+ * pose_estimation/src/pose_estimation.cpp:246-261 (+ remove_planes :281-345): NaN removal, the optional sphere
+ * filter, then num_planes times { plane RANSAC on what is left; removal of the plane band }, then — if
+ * leaf > 0 — VoxelGrid.  Same arithmetic and results as peb_scene_prefilter / peb_sac_plane / peb_voxel_grid
+ * called one after the other, but the cloud crosses PCIe once in each direction instead of seven times.
+ * filter: use_sphere / remove_inliers / sphere_* / plane_band are read, its planes are ignored.
+ * out_planes (nullable): num_planes x 4 coefficients; a plane that could not be estimated is all zeros and
+ * removes nothing (the reference prints an error and goes on). */
+PEB_API int peb_scene_prepare(peb_ctx* ctx, const void* pts, size_t n, size_t stride, const peb_prefilter_params* filter,
+                              int num_planes, const peb_sac_params* sac, float leaf, float* out_xyz4, size_t* out_n,
+                              float* out_planes);
+
 /* ---- cv::ppf_match_3d::ICP::registerModelToScene(model, scene, poses) --------------------------
  * What the reference runs in the refinement slot (pose_estimation/src/opencv_surface_match.cpp:85-94:
  * ICP icp(250, 0.005f, 2.5f, 8); icp.registerModelToScene(models_[object], pc_scene_normals, <= 6 poses)).

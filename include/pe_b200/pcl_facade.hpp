@@ -93,6 +93,33 @@ class ScenePrefilter {
   peb_prefilter_params p_;
 };
 
+// PoseEstimation::create_surface_match_pc (pose_estimation/src/pose_estimation.cpp:246-261 + remove_planes :281-345) in ONE
+// library call: NaN removal, optional sphere filter, num_planes rounds of plane RANSAC + band removal, optional VoxelGrid.
+// The cloud crosses PCIe once in each direction.  planes (optional): num_planes x 4 coefficients.
+inline void create_surface_match_pc(Context& c, const void* pts, size_t n, size_t stride, const float* filter_pose,
+                                    float filter_radius, const std::string& filter_out, int num_planes, float leaf,
+                                    std::vector<float>& out_xyz4, std::vector<float>* planes = nullptr) {
+  peb_prefilter_params f;
+  std::memset(&f, 0, sizeof(f));
+  f.plane_band = 0.005f;                                    // :320
+  if (filter_pose && filter_radius > 0.0f) {                // :250-256
+    f.use_sphere = 1;
+    f.remove_inliers = filter_out == "inliers" ? 1 : 0;
+    for (int i = 0; i < 3; ++i) f.sphere_center[i] = filter_pose[i];
+    f.sphere_radius = filter_radius;
+  }
+  peb_sac_params sac;
+  peb_sac_params_default(&sac);
+  sac.distance_threshold = 0.0001;                          // :294
+  sac.max_iterations = 100;                                 // :295
+  out_xyz4.resize(4 * (n ? n : 1));
+  std::vector<float> pl(4 * static_cast<size_t>(num_planes > 0 ? num_planes : 1), 0.0f);
+  size_t m = 0;
+  c.check(peb_scene_prepare(c.get(), pts, n, stride, &f, num_planes, &sac, leaf, out_xyz4.data(), &m, pl.data()));
+  out_xyz4.resize(4 * m);
+  if (planes) planes->assign(pl.begin(), pl.begin() + 4 * static_cast<size_t>(num_planes > 0 ? num_planes : 0));
+}
+
 // pcl::SACSegmentation<pcl::PointXYZ> for SACMODEL_PLANE + SAC_RANSAC: the plane fit of remove_planes
 // (pose_estimation/src/pose_estimation.cpp:285-297).  Same setters and defaults as
 // [PCL] segmentation/include/pcl/segmentation/sac_segmentation.h; other model / method types throw

@@ -2,6 +2,7 @@
 // staging and the mapping of every entry point onto the CUDA stages.  No exceptions leave this
 // file and there is no CPU implementation behind any entry point: if the device path cannot run,
 // the call fails with a peb_status and a message.
+#include <algorithm>
 #include <cstring>
 #include <new>
 
@@ -369,6 +370,56 @@ PEB_API int peb_sac_plane(peb_ctx* ctx, const void* pts, size_t n, size_t stride
     PEB_CUDA(ctx, cudaMemcpyAsync(out_inliers, ctx->vg_out.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   PEB_TRY(sync(ctx));
   *out_n_inliers = m;
+  return PEB_OK;
+}
+
+// ---- create_surface_match_pc in one call ---------------------------------------------------------------
+PEB_API int peb_scene_prepare(peb_ctx* ctx, const void* pts, size_t n, size_t stride, const peb_prefilter_params* filter,
+                              int num_planes, const peb_sac_params* sac, float leaf, float* out_xyz4, size_t* out_n,
+                              float* out_planes) {
+  if (!ctx || !filter || !out_n) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  *out_n = 0;
+  PEB_TRY(check_cloud(ctx, "scene_prepare", pts, n, stride));
+  if (num_planes < 0 || num_planes > PEB_PREFILTER_MAX_PLANES)
+    return fail(ctx, PEB_E_INVALID_ARG, "scene_prepare: num_planes %d out of [0, %d]", num_planes, PEB_PREFILTER_MAX_PLANES);
+  if (num_planes > 0 && !sac) return fail(ctx, PEB_E_INVALID_ARG, "scene_prepare: plane removal needs RANSAC parameters");
+  if (n > 0 && !out_xyz4) return fail(ctx, PEB_E_INVALID_ARG, "scene_prepare: null output");
+  if (n == 0) return PEB_OK;
+  PEB_CUDA(ctx, ctx->vg_in.ensure(n * sizeof(float4)));
+  PEB_CUDA(ctx, ctx->vg_out.ensure(n * sizeof(float4)));
+  float4* cur = ctx->vg_in.as<float4>();
+  float4* other = ctx->vg_out.as<float4>();
+  PEB_TRY(upload_cloud(ctx, pts, n, stride, 1.0f, cur));
+  size_t m = 0;
+  peb_prefilter_params f = *filter;
+  f.n_planes = 0;  // :246-256, NaN removal + sphere filter
+  PEB_TRY(scene_prefilter_device(ctx, cur, static_cast<int>(n), &f, other, &m));
+  std::swap(cur, other);
+  for (int k = 0; k < num_planes; ++k) {  // remove_planes, recursively in the reference
+    float coeff[4] = {0.f, 0.f, 0.f, 0.f};
+    size_t n_inl = 0;
+    PEB_TRY(sac_plane_device(ctx, cur, static_cast<int>(m), sac, coeff, nullptr, &n_inl, nullptr));
+    if (out_planes) std::copy(coeff, coeff + 4, out_planes + 4 * k);
+    if (coeff[0] == 0.f && coeff[1] == 0.f && coeff[2] == 0.f && coeff[3] == 0.f) continue;  // no model: nothing is near "the plane"
+    peb_prefilter_params band{};
+    band.plane_band = filter->plane_band;
+    band.n_planes = 1;
+    std::copy(coeff, coeff + 4, band.planes);
+    size_t kept = 0;
+    PEB_TRY(scene_prefilter_device(ctx, cur, static_cast<int>(m), &band, other, &kept));
+    std::swap(cur, other);
+    m = kept;
+  }
+  if (leaf > 0.0f && m > 0) {
+    size_t v = 0;
+    PEB_TRY(voxel_grid_device(ctx, cur, static_cast<int>(m), leaf, leaf, leaf, 0, other, &v));
+    std::swap(cur, other);
+    m = v;
+  }
+  if (m > 0) PEB_CUDA(ctx, cudaMemcpyAsync(out_xyz4, cur, m * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  PEB_TRY(sync(ctx));
+  *out_n = m;
   return PEB_OK;
 }
 

@@ -190,6 +190,34 @@ class ScenePrefilter:
         return out[: m.value].copy()
 
 
+def create_surface_match_pc(cloud, ctx: Context | None = None, filter_pose=None, filter_radius: float = 0.0,
+                            filter_out: str = "outliers", num_planes: int = 0, leaf: float = 0.0, plane_band: float = 0.005,
+                            distance_threshold: float = 0.0001, max_iterations: int = 100):
+    """PoseEstimation::create_surface_match_pc (pose_estimation/src/pose_estimation.cpp:211-279) from the organized cloud
+    on: NaN removal, the optional sphere filter around the last pose, num_planes rounds of plane RANSAC + 5 mm band
+    removal (remove_planes, :281-345, with the reference's RANSAC settings as defaults) and — leaf > 0 — the VoxelGrid,
+    in ONE library call (peb_scene_prepare).  -> (points (M, 4) float32, plane coefficients (num_planes, 4))."""
+    ctx = ctx or default_context()
+    p = _cloud(cloud)
+    f = PrefilterParams()
+    f.plane_band = float(plane_band)
+    if filter_pose is not None and filter_radius > 0:
+        f.use_sphere = 1
+        f.remove_inliers = 1 if filter_out == "inliers" else 0
+        f.sphere_center[:] = [float(v) for v in filter_pose[:3]]
+        f.sphere_radius = float(filter_radius)
+    sp = SacParams()
+    lib.peb_sac_params_default(C.byref(sp))
+    sp.distance_threshold = float(distance_threshold)
+    sp.max_iterations = int(max_iterations)
+    out = np.empty((max(p.shape[0], 1), 4), np.float32)
+    planes = np.zeros((max(num_planes, 1), 4), np.float32)
+    m = C.c_size_t(0)
+    ctx.check(lib.peb_scene_prepare(ctx.handle, p.ctypes.data, p.shape[0], _stride(p), C.byref(f), int(num_planes), C.byref(sp),
+                                    float(leaf), out.ctypes.data, C.byref(m), planes.ctypes.data))
+    return out[: m.value].copy(), planes[:num_planes].copy()
+
+
 class SACSegmentation:
     """pcl::SACSegmentation<pcl::PointXYZ> for SACMODEL_PLANE + SAC_RANSAC
     ([PCL] segmentation/include/pcl/segmentation/sac_segmentation.h), the plane fit of the reference's

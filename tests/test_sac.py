@@ -229,3 +229,34 @@ def test_plane_ransac_full_scene_and_band_removal(pcl, ctx, oracle):
     from oracle import prefilter_params
     ref = oracle.scene_prefilter(cloud, prefilter_params(planes=[rc]))
     assert abs(len(kept) - len(ref)) <= 2 and len(kept) < 0.5 * len(cloud)
+
+
+@pytest.mark.gpu
+def test_scene_preparation_in_one_call_equals_the_steps(pcl, ctx):
+    """peb_scene_prepare (create_surface_match_pc in one call) against the same stages called one after the other."""
+    rng = np.random.default_rng(12)
+    surf = synth.Surface(12)
+    gt = synth.default_gt_pose(rng)
+    scene = synth.render_scene(surf, gt, rng, 972, 600)
+    centre, radius = gt[:3, 3], 0.35
+    got, planes = pcl.create_surface_match_pc(scene, ctx, filter_pose=centre, filter_radius=radius, num_planes=2, leaf=0.002)
+    pf = pcl.ScenePrefilter(ctx)
+    pf.setInputCloud(scene)
+    pf.setSphereFilter(centre, radius)
+    cloud = pf.filter()
+    ref_planes = []
+    for _ in range(2):
+        inl, coeff, _ = _segment(pcl, ctx, cloud, 1e-4, 100, True)
+        ref_planes.append(coeff)
+        band = pcl.ScenePrefilter(ctx)
+        band.setInputCloud(cloud)
+        band.addPlane(*[float(v) for v in coeff])
+        cloud = band.filter()
+    vg = pcl.VoxelGrid(ctx)
+    vg.setInputCloud(cloud)
+    vg.setLeafSize(0.002)
+    ref = vg.filter()
+    assert np.array_equal(planes, np.stack(ref_planes)) and got.tobytes() == ref.tobytes() and 1000 < len(got) < len(scene)
+    # no planes, no sphere, no VoxelGrid: plain NaN removal
+    only, none = pcl.create_surface_match_pc(scene, ctx)
+    assert len(none) == 0 and np.array_equal(only, scene[np.isfinite(scene[:, :3]).all(1)])
