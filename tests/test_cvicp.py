@@ -38,6 +38,19 @@ def test_oracle_rejection_and_pyramid(oracle):
     assert synth.pose_error(P2[0], gt)[0] < 5e-4
 
 
+def test_oracle_degenerate_inputs(oracle):
+    model, scene, poses, gt = make_case(seed=4, n_model=40, n_scene=90, n_poses=2)
+    # 8 levels on 40 points: the coarse levels hold fewer than 6 pairs (or no point at all) and must leave the pose alone
+    P, res = oracle.cvicp_register(model, scene, poses, cvicp_params())
+    assert np.isfinite(P).all() and np.isfinite(res).all()
+    # fewer than 6 points: no level can solve, the poses come back unchanged and the residual is the initial sentinel or 0
+    P5, _ = oracle.cvicp_register(model[:5], scene, poses, cvicp_params())
+    assert np.allclose(P5, poses, atol=1e-12)
+    # no iterations allowed: unchanged as well
+    P0, _ = oracle.cvicp_register(model, scene, poses, cvicp_params(iterations=0))
+    assert np.allclose(P0, poses, atol=1e-12)
+
+
 @pytest.fixture(scope="module")
 def pcl():
     from pose_estimation_b200 import pcl as m
