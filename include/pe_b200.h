@@ -265,6 +265,39 @@ PEB_API int peb_icp_align_batch(peb_ctx* ctx, const float* guesses, size_t n_gue
 PEB_API int peb_fitness_score(peb_ctx* ctx, const float T[16], double max_range, double* out_fitness,
                               int32_t* out_n_inliers);
 
+/* ---- several devices behind one handle -------------------------------- */
+/* The reference node is one process (a component container with a single-threaded executor,
+ * pose_estimation/launch/pose_estimation.launch.py:17-35), so the drop-in for the refinement slot
+ * (pose_estimation/src/opencv_surface_match.cpp:85-94) that uses every GPU of the box lives behind
+ * one handle: one context per device, a replica of the scene grid and of the model on each, the H
+ * initial poses split into contiguous blocks (device i refines [lo, hi) of peb_multi_shard_range).
+ * Hypotheses are independent: no collective; each device copies its records into `results`.
+ * devices: ndev CUDA device indices (NULL = 0 .. ndev-1).  An index may repeat — the contexts are
+ * independent, which is how the single-GPU tests exercise the sharding.  Calls on one peb_multi
+ * must be serialised by the caller, like calls on one peb_ctx.  Results are identical to
+ * peb_icp_align_batch on one device, record for record. */
+typedef struct peb_multi peb_multi;
+PEB_API int peb_multi_create(int ndev, const int* devices, peb_multi** out);
+PEB_API void peb_multi_destroy(peb_multi* m);
+/* message of the last failing call on m (m == NULL: of the last failing peb_multi_create of this thread) */
+PEB_API const char* peb_multi_last_error(const peb_multi* m);
+PEB_API int peb_multi_size(const peb_multi* m);
+/* context i (borrowed; for per-device introspection, not for concurrent use) */
+PEB_API peb_ctx* peb_multi_ctx(peb_multi* m, int i);
+/* peb_ctx_set_int on every context */
+PEB_API int peb_multi_set_int(peb_multi* m, const char* key, int value);
+/* [lo, hi) of the n_items hypotheses device i of ndev refines: blocks of ceil(n_items / ndev) */
+PEB_API void peb_multi_shard_range(size_t n_items, int ndev, int i, size_t* lo, size_t* hi);
+/* peb_target_set / peb_source_set on every device (same host buffers, concurrently) */
+PEB_API int peb_multi_target_set(peb_multi* m, const void* pts, size_t n, size_t stride,
+                                 const void* normals, size_t nstride);
+PEB_API int peb_multi_source_set(peb_multi* m, const void* pts, size_t n, size_t stride);
+/* peb_icp_align_batch, sharded: guesses H x 16 floats, results H records, hypothesis order */
+PEB_API int peb_multi_icp_align_batch(peb_multi* m, const float* guesses, size_t n_guesses,
+                                      const peb_icp_params* params, peb_icp_result* results);
+/* kernel launches of all contexts so far */
+PEB_API uint64_t peb_multi_launch_count(const peb_multi* m);
+
 /* ---- device-resident variants (bench harness: inputs already in HBM) ---------------- */
 /* d_*: device pointers on the context's device, float4 records (xyz + pad), 16-byte aligned.
  * Asynchronous on peb_ctx_stream(); *_dev results are device pointers too. */

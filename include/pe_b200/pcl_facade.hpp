@@ -292,6 +292,7 @@ class IterativeClosestPoint {
   }
   int nr_iterations() const { return result_.iterations; }
   const peb_icp_result& result() const { return result_; }
+  const peb_icp_params& params() const { return params_; }
 
  protected:
   Context& c_;
@@ -454,6 +455,46 @@ inline void obj_in_base_frame(const float pose7[7], const float he16[16], double
 class IterativeClosestPointWithNormals : public IterativeClosestPoint {
  public:
   explicit IterativeClosestPointWithNormals(Context& c) : IterativeClosestPoint(c, PEB_ESTIMATOR_POINT_TO_PLANE_LLS) {}
+};
+
+// ---- every GPU of the box from the node's one process (peb_multi_*) ---------------------
+// owns one peb_multi: one context per device, scene grid and model replicated on each
+class MultiContext {
+ public:
+  explicit MultiContext(const std::vector<int>& devices) {
+    if (int rc = peb_multi_create(static_cast<int>(devices.size()), devices.data(), &m_)) throw Error(rc, peb_multi_last_error(nullptr));
+  }
+  ~MultiContext() { peb_multi_destroy(m_); }
+  MultiContext(const MultiContext&) = delete;
+  MultiContext& operator=(const MultiContext&) = delete;
+  peb_multi* get() const { return m_; }
+  int size() const { return peb_multi_size(m_); }
+  void check(int rc) const {
+    if (rc != PEB_OK) throw Error(rc, peb_multi_last_error(m_));
+  }
+
+ private:
+  peb_multi* m_ = nullptr;
+};
+
+// The batched refinement of the slot (opencv_surface_match.cpp:85-94) sharded over the devices of a MultiContext:
+// contiguous blocks of the H poses per device, results in hypothesis order, identical to alignBatch on one device.
+// Configure a pe_b200::IterativeClosestPoint(+WithNormals) with PCL's setters as usual and hand it over as `like`.
+class MultiDeviceICP {
+ public:
+  MultiDeviceICP(MultiContext& m, const IterativeClosestPoint& like) : m_(m), params_(like.params()) {}
+  void setInputSource(const void* pts, size_t n, size_t stride = 16) { m_.check(peb_multi_source_set(m_.get(), pts, n, stride)); }
+  void setInputTarget(const void* pts, size_t n, size_t stride = 16, const void* normals = nullptr, size_t nstride = 32) {
+    m_.check(peb_multi_target_set(m_.get(), pts, n, stride, normals, nstride));
+  }
+  void alignBatch(const float* guesses16, size_t n_guesses, std::vector<peb_icp_result>& results) {
+    results.resize(n_guesses);
+    m_.check(peb_multi_icp_align_batch(m_.get(), guesses16, n_guesses, &params_, results.data()));
+  }
+
+ private:
+  MultiContext& m_;
+  peb_icp_params params_;
 };
 
 }  // namespace pe_b200

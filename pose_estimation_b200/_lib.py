@@ -153,6 +153,17 @@ SYMBOLS = {
     "peb_target_grid_info": (_i, [_vp, _pp(GridInfo)]),
     "peb_icp_trace": (_i, [_vp, _vp, _sz, _pp(_sz)]),
     "peb_profile_read": (_i, [_vp, _vp, _sz, _pp(_sz)]),
+    "peb_multi_create": (_i, [_i, _pp(_i), _pp(_vp)]),
+    "peb_multi_destroy": (None, [_vp]),
+    "peb_multi_last_error": (C.c_char_p, [_vp]),
+    "peb_multi_size": (_i, [_vp]),
+    "peb_multi_ctx": (_vp, [_vp, _i]),
+    "peb_multi_set_int": (_i, [_vp, C.c_char_p, _i]),
+    "peb_multi_shard_range": (None, [_sz, _i, _i, _pp(_sz), _pp(_sz)]),
+    "peb_multi_target_set": (_i, [_vp, _vp, _sz, _sz, _vp, _sz]),
+    "peb_multi_source_set": (_i, [_vp, _vp, _sz, _sz]),
+    "peb_multi_icp_align_batch": (_i, [_vp, _vp, _sz, _pp(IcpParams), _vp]),
+    "peb_multi_launch_count": (C.c_uint64, [_vp]),
 }
 
 

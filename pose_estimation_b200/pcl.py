@@ -138,6 +138,91 @@ class Context:
 _default_ctx: Context | None = None
 
 
+class MultiContext:
+    """peb_multi: several devices behind one handle (include/pe_b200.h) — what the reference's single
+    process binds to refine the poses of registerModelToScene(model, scene, poses) on every GPU of the box.  One context
+    per device, the scene grid and the model replicated, the hypotheses of alignBatch split into contiguous blocks.
+    Pass it as `ctx` to IterativeClosestPoint(+WithNormals); a single align() is not sharded (replicas only) and runs
+    on the first device.  A device index may repeat (independent contexts on one GPU)."""
+
+    is_multi = True
+
+    def __init__(self, devices):
+        devs = list(range(devices)) if isinstance(devices, int) else [int(d) for d in devices]
+        arr = (C.c_int * max(len(devs), 1))(*devs)
+        h = C.c_void_p()
+        rc = lib.peb_multi_create(len(devs), arr, C.byref(h))
+        if rc != 0:
+            raise PebError(rc, lib.peb_multi_last_error(None).decode())
+        self._h = h
+        self.devices = devs
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.peb_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise PebError(rc, lib.peb_multi_last_error(self._h).decode())
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def size(self) -> int:
+        return int(lib.peb_multi_size(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib.peb_multi_launch_count(self._h))
+
+    def first(self) -> "Context":
+        """Context 0, borrowed (closing it is a no-op): where the unsharded calls run."""
+        c = Context.__new__(Context)
+        c._h = C.c_void_p(lib.peb_multi_ctx(self._h, 0))
+        c.close = lambda: None
+        return c
+
+    def shard_range(self, n_items: int, i: int) -> tuple[int, int]:
+        lo, hi = C.c_size_t(0), C.c_size_t(0)
+        lib.peb_multi_shard_range(n_items, self.size, i, C.byref(lo), C.byref(hi))
+        return lo.value, hi.value
+
+    def set_int(self, key: str, value: int):
+        self.check(lib.peb_multi_set_int(self._h, key.encode(), int(value)))
+
+    def target_set(self, pts, normals=None):
+        p = _cloud(pts)
+        if normals is None:
+            self.check(lib.peb_multi_target_set(self._h, p.ctypes.data, p.shape[0], _stride(p), None, 0))
+        else:
+            nm = _cloud(normals)
+            if nm.shape[0] != p.shape[0]:
+                raise ValueError("target normals must have one row per target point")
+            self.check(lib.peb_multi_target_set(self._h, p.ctypes.data, p.shape[0], _stride(p), nm.ctypes.data, _stride(nm)))
+
+    def source_set(self, pts):
+        p = _cloud(pts)
+        self.check(lib.peb_multi_source_set(self._h, p.ctypes.data, p.shape[0], _stride(p)))
+
+    def icp_align_batch(self, g16: np.ndarray, params: IcpParams, res):
+        self.check(lib.peb_multi_icp_align_batch(self._h, g16.ctypes.data, g16.shape[0], C.byref(params), res))
+
+
 def default_context() -> Context:
     global _default_ctx
     if _default_ctx is None:
@@ -423,6 +508,15 @@ class IterativeClosestPoint:
         self._n_src = 0
         self.correspondences = None
 
+    @property
+    def _sctx(self) -> Context:
+        """The context of the unsharded calls (align, fitness, trace): with a MultiContext, its first device."""
+        if getattr(self.ctx, "is_multi", False):
+            if getattr(self, "_first", None) is None:
+                self._first = self.ctx.first()
+            return self._first
+        return self.ctx
+
     # -- pcl::Registration setters ------------------------------------------------------------
     def setInputSource(self, cloud):
         self.ctx.source_set(cloud)
@@ -486,7 +580,7 @@ class IterativeClosestPoint:
         out = np.empty((n, 4), np.float32) if (want_output and n) else None
         idx = np.empty(n, np.int32) if (want_correspondences and n) else None
         d2 = np.empty(n, np.float32) if (want_correspondences and n) else None
-        self.ctx.check(lib.peb_icp_align(self.ctx.handle, g.ctypes.data if g is not None else None, C.byref(self.params),
+        self._sctx.check(lib.peb_icp_align(self._sctx.handle, g.ctypes.data if g is not None else None, C.byref(self.params),
                                          C.byref(res), out.ctypes.data if out is not None else None,
                                          idx.ctypes.data if idx is not None else None,
                                          d2.ctypes.data if d2 is not None else None))
@@ -502,7 +596,10 @@ class IterativeClosestPoint:
         g = np.ascontiguousarray(np.asarray(guesses, np.float32).reshape(-1, 4, 4).transpose(0, 2, 1)).reshape(-1, 16)
         H = g.shape[0]
         res = (IcpResult * max(H, 1))()
-        self.ctx.check(lib.peb_icp_align_batch(self.ctx.handle, g.ctypes.data, H, C.byref(self.params), res))
+        if getattr(self.ctx, "is_multi", False):
+            self.ctx.icp_align_batch(g, self.params, res)  # contiguous blocks of hypotheses per device
+        else:
+            self.ctx.check(lib.peb_icp_align_batch(self.ctx.handle, g.ctypes.data, H, C.byref(self.params), res))
         return list(res)[:H]
 
     def hasConverged(self) -> bool:
@@ -518,7 +615,7 @@ class IterativeClosestPoint:
             raise ValueError("getFitnessScore before align")
         if max_range == self.params.fitness_max_range:
             return self._result.fitness
-        return self.ctx.fitness_score(self.getFinalTransformation(), max_range)[0]
+        return self._sctx.fitness_score(self.getFinalTransformation(), max_range)[0]
 
     @property
     def nr_iterations_(self) -> int:
@@ -533,7 +630,7 @@ class IterativeClosestPoint:
         cap = max(self.nr_iterations_, 1)
         buf = np.zeros((cap, 16), np.float32)
         n = C.c_size_t(0)
-        self.ctx.check(lib.peb_icp_trace(self.ctx.handle, buf.ctypes.data, cap, C.byref(n)))
+        self._sctx.check(lib.peb_icp_trace(self._sctx.handle, buf.ctypes.data, cap, C.byref(n)))
         return buf[: n.value].reshape(-1, 4, 4).transpose(0, 2, 1).copy()
 
 

@@ -95,6 +95,18 @@ int main(int argc, char** argv) {
     print_T("batch0", res[0]);
     print_T("batch1", res[1]);
 
+    // the same batch sharded over two contexts on this device (peb_multi_*): must reproduce batch0 / batch1
+    {
+      pe_b200::MultiContext many(std::vector<int>{0, 0});
+      pe_b200::MultiDeviceICP micp(many, icp);
+      micp.setInputSource(src.data(), n_src, 16);
+      micp.setInputTarget(ds.data(), ds.size() / 4, 16);
+      std::vector<peb_icp_result> mres;
+      micp.alignBatch(poses.data(), 2, mres);
+      std::printf("multi_batch contexts %d identical %d\n", many.size(),
+                  static_cast<int>(std::memcmp(mres.data(), res.data(), 2 * sizeof(peb_icp_result)) == 0));
+    }
+
     // cv::ppf_match_3d::ICP as the reference calls it: model / scene with the normals computed above, two poses
     {
       pe_b200::NormalEstimation nes(ctx);

@@ -95,6 +95,7 @@ def test_facade_matches_python_host_classes(exe, tmp_path):
     _, _, fit, T = parse("icp_p2p")
     assert np.array_equal(T0, T) and fit0 == fit and it0 == 30 and it1 == 30 and fit1 <= fit0 * 1.01
     assert "unsupported-option refused: code -6" in r.stdout
+    assert lines["multi_batch"][2] == "2" and lines["multi_batch"][4] == "1"  # two contexts, records identical to alignBatch
     # the cv ICP of the facade against the Python mirror (same library underneath: bit-identical)
     nes = pcl.NormalEstimation(ctx)
     nes.setInputCloud(prob.source)
