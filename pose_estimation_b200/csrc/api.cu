@@ -92,6 +92,26 @@ int upload_guesses(peb_ctx* ctx, const float* guesses, size_t H, const float** d
   return PEB_OK;
 }
 
+// No C++ exception leaves the library (include/pe_b200.h): the entry points whose host side allocates (std::vector
+// staging of the RANSAC candidates and the cv ICP pose tables, stream / event lists, error strings) run behind this.
+template <typename Fn>
+int guarded(peb_ctx* ctx, const char* what, Fn fn) noexcept {
+  int code = PEB_E_CUDA;
+  const char* why = "unexpected C++ exception";
+  try {
+    return fn();
+  } catch (const std::bad_alloc&) {
+    code = PEB_E_OOM;
+    why = "out of host memory";
+  } catch (...) {
+  }
+  try {
+    if (ctx) ctx->err = std::string(what) + ": " + why;
+  } catch (...) {
+  }
+  return code;
+}
+
 }  // namespace
 }  // namespace peb
 
@@ -344,7 +364,7 @@ PEB_API void peb_sac_params_default(peb_sac_params* p) {
   p->reserved = 0;
 }
 
-PEB_API int peb_sac_plane_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, const peb_sac_params* params, float out_coeff[4],
+static int sac_plane_dev_impl(peb_ctx* ctx, const void* d_xyz4, size_t n, const peb_sac_params* params, float out_coeff[4],
                               int32_t* d_out_inliers, size_t* out_n_inliers, int32_t* out_iterations) {
   if (!ctx || !params || !out_coeff || !out_n_inliers) return PEB_E_INVALID_ARG;
   DeviceGuard guard(ctx->device);
@@ -354,7 +374,7 @@ PEB_API int peb_sac_plane_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, const 
                           out_n_inliers, out_iterations);
 }
 
-PEB_API int peb_sac_plane(peb_ctx* ctx, const void* pts, size_t n, size_t stride, const peb_sac_params* params,
+static int sac_plane_impl(peb_ctx* ctx, const void* pts, size_t n, size_t stride, const peb_sac_params* params,
                           float out_coeff[4], int32_t* out_inliers, size_t* out_n_inliers, int32_t* out_iterations) {
   if (!ctx || !params || !out_coeff || !out_n_inliers) return PEB_E_INVALID_ARG;
   DeviceGuard guard(ctx->device);
@@ -374,7 +394,7 @@ PEB_API int peb_sac_plane(peb_ctx* ctx, const void* pts, size_t n, size_t stride
 }
 
 // ---- create_surface_match_pc in one call ---------------------------------------------------------------
-PEB_API int peb_scene_prepare(peb_ctx* ctx, const void* pts, size_t n, size_t stride, const peb_prefilter_params* filter,
+static int scene_prepare_impl(peb_ctx* ctx, const void* pts, size_t n, size_t stride, const peb_prefilter_params* filter,
                               int num_planes, const peb_sac_params* sac, float leaf, float* out_xyz4, size_t* out_n,
                               float* out_planes) {
   if (!ctx || !filter || !out_n) return PEB_E_INVALID_ARG;
@@ -424,7 +444,7 @@ PEB_API int peb_scene_prepare(peb_ctx* ctx, const void* pts, size_t n, size_t st
 }
 
 // ---- cv::ppf_match_3d::ICP::registerModelToScene ----------------------------------------------------
-PEB_API int peb_cvicp_register(peb_ctx* ctx, const float* model_xyzn, size_t n_model, const float* scene_xyzn, size_t n_scene,
+static int cvicp_register_impl(peb_ctx* ctx, const float* model_xyzn, size_t n_model, const float* scene_xyzn, size_t n_scene,
                                const peb_cvicp_params* params, double* poses, size_t n_poses, double* out_residuals) {
   if (!ctx || !params) return PEB_E_INVALID_ARG;
   DeviceGuard guard(ctx->device);
@@ -561,7 +581,7 @@ PEB_API int peb_nn_search_bruteforce(peb_ctx* ctx, const void* queries, size_t n
 }
 
 // ---- ICP ---------------------------------------------------------------------------------------------
-PEB_API int peb_icp_align_batch_dev(peb_ctx* ctx, const float* d_guesses, size_t n_guesses, const peb_icp_params* params,
+static int icp_align_batch_dev_impl(peb_ctx* ctx, const float* d_guesses, size_t n_guesses, const peb_icp_params* params,
                                     peb_icp_result* d_results) {
   if (!ctx || !params) return PEB_E_INVALID_ARG;
   DeviceGuard guard(ctx->device);
@@ -569,7 +589,7 @@ PEB_API int peb_icp_align_batch_dev(peb_ctx* ctx, const float* d_guesses, size_t
   return icp_align_device(ctx, d_guesses, n_guesses, params, d_results, false);
 }
 
-PEB_API int peb_icp_align_dev(peb_ctx* ctx, const float guess[16], const peb_icp_params* params, peb_icp_result* d_result) {
+static int icp_align_dev_impl(peb_ctx* ctx, const float guess[16], const peb_icp_params* params, peb_icp_result* d_result) {
   if (!ctx || !params || !d_result) return PEB_E_INVALID_ARG;
   DeviceGuard guard(ctx->device);
   const float* d_g = nullptr;
@@ -577,7 +597,7 @@ PEB_API int peb_icp_align_dev(peb_ctx* ctx, const float guess[16], const peb_icp
   return icp_align_device(ctx, d_g, 1, params, d_result, true);
 }
 
-PEB_API int peb_icp_align(peb_ctx* ctx, const float guess[16], const peb_icp_params* params, peb_icp_result* result,
+static int icp_align_impl(peb_ctx* ctx, const float guess[16], const peb_icp_params* params, peb_icp_result* result,
                           float* out_aligned_xyz4, int32_t* out_corr_idx, float* out_corr_d2) {
   if (!ctx || !params || !result) return PEB_E_INVALID_ARG;
   DeviceGuard guard(ctx->device);
@@ -601,7 +621,7 @@ PEB_API int peb_icp_align(peb_ctx* ctx, const float guess[16], const peb_icp_par
   return PEB_OK;
 }
 
-PEB_API int peb_icp_align_batch(peb_ctx* ctx, const float* guesses, size_t n_guesses, const peb_icp_params* params,
+static int icp_align_batch_impl(peb_ctx* ctx, const float* guesses, size_t n_guesses, const peb_icp_params* params,
                                 peb_icp_result* results) {
   if (!ctx || !params) return PEB_E_INVALID_ARG;
   DeviceGuard guard(ctx->device);
@@ -690,6 +710,39 @@ PEB_API int peb_icp_trace(peb_ctx* ctx, float* out_T, size_t cap, size_t* out_n)
     PEB_TRY(sync(ctx));
   }
   return PEB_OK;
+}
+
+// ---- entry points behind the exception barrier ------------------------------------------------------------
+PEB_API int peb_sac_plane_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, const peb_sac_params* params, float out_coeff[4], int32_t* d_out_inliers, size_t* out_n_inliers, int32_t* out_iterations) {
+  return guarded(ctx, "peb_sac_plane_dev", [&]() { return sac_plane_dev_impl(ctx, d_xyz4, n, params, out_coeff, d_out_inliers, out_n_inliers, out_iterations); });
+}
+
+PEB_API int peb_sac_plane(peb_ctx* ctx, const void* pts, size_t n, size_t stride, const peb_sac_params* params, float out_coeff[4], int32_t* out_inliers, size_t* out_n_inliers, int32_t* out_iterations) {
+  return guarded(ctx, "peb_sac_plane", [&]() { return sac_plane_impl(ctx, pts, n, stride, params, out_coeff, out_inliers, out_n_inliers, out_iterations); });
+}
+
+PEB_API int peb_scene_prepare(peb_ctx* ctx, const void* pts, size_t n, size_t stride, const peb_prefilter_params* filter, int num_planes, const peb_sac_params* sac, float leaf, float* out_xyz4, size_t* out_n, float* out_planes) {
+  return guarded(ctx, "peb_scene_prepare", [&]() { return scene_prepare_impl(ctx, pts, n, stride, filter, num_planes, sac, leaf, out_xyz4, out_n, out_planes); });
+}
+
+PEB_API int peb_cvicp_register(peb_ctx* ctx, const float* model_xyzn, size_t n_model, const float* scene_xyzn, size_t n_scene, const peb_cvicp_params* params, double* poses, size_t n_poses, double* out_residuals) {
+  return guarded(ctx, "peb_cvicp_register", [&]() { return cvicp_register_impl(ctx, model_xyzn, n_model, scene_xyzn, n_scene, params, poses, n_poses, out_residuals); });
+}
+
+PEB_API int peb_icp_align_batch_dev(peb_ctx* ctx, const float* d_guesses, size_t n_guesses, const peb_icp_params* params, peb_icp_result* d_results) {
+  return guarded(ctx, "peb_icp_align_batch_dev", [&]() { return icp_align_batch_dev_impl(ctx, d_guesses, n_guesses, params, d_results); });
+}
+
+PEB_API int peb_icp_align_dev(peb_ctx* ctx, const float guess[16], const peb_icp_params* params, peb_icp_result* d_result) {
+  return guarded(ctx, "peb_icp_align_dev", [&]() { return icp_align_dev_impl(ctx, guess, params, d_result); });
+}
+
+PEB_API int peb_icp_align(peb_ctx* ctx, const float guess[16], const peb_icp_params* params, peb_icp_result* result, float* out_aligned_xyz4, int32_t* out_corr_idx, float* out_corr_d2) {
+  return guarded(ctx, "peb_icp_align", [&]() { return icp_align_impl(ctx, guess, params, result, out_aligned_xyz4, out_corr_idx, out_corr_d2); });
+}
+
+PEB_API int peb_icp_align_batch(peb_ctx* ctx, const float* guesses, size_t n_guesses, const peb_icp_params* params, peb_icp_result* results) {
+  return guarded(ctx, "peb_icp_align_batch", [&]() { return icp_align_batch_impl(ctx, guesses, n_guesses, params, results); });
 }
 
 }  // extern "C"
