@@ -1,0 +1,142 @@
+"""Adversarial inputs for the grid searches that replace pcl::KdTreeFLANN::nearestKSearch: the
+__host__ __device__ search code of core_math.cuh, compiled for the CPU (tests/host/host_check.cu), against the oracle's
+brute force (same float L2_Simple arithmetic, lowest index on exact ties) on clouds built to sit on the edges of what
+the margins of the searches cover: points and queries exactly on cell boundaries, extents of a few ulps, clouds a
+kilometre from the origin, lattices full of exact ties, sheets, lines, duplicates, clusters with empty space between.
+Runs without a GPU; the kernels execute the same source."""
+import numpy as np
+import pytest
+
+from test_host_logic import grid_nn, grid_nn_warm, hc  # noqa: F401  (hc is the fixture)
+
+F = np.float32
+
+
+def _lattice(rng, n, step, dims=3):
+    """points on multiples of `step` (a power of two): every coordinate difference is exact, ties are exact"""
+    k = rng.integers(-12, 13, (n, 3)).astype(F)
+    k[:, dims:] = 0
+    return k * F(step)
+
+
+def clouds(rng):
+    """name -> (n, 3) float32 target"""
+    out = {}
+    out["lattice"] = _lattice(rng, 300, 2.0 ** -6)
+    out["lattice_sheet"] = _lattice(rng, 300, 2.0 ** -8, dims=2) + F([0, 0, 0.5])
+    out["lattice_line"] = _lattice(rng, 120, 2.0 ** -5, dims=1)
+    out["lattice_far"] = _lattice(rng, 300, 2.0 ** -4) + F([1024.0, -2048.0, 512.0])   # spacing = 512 ulps of x
+    out["tiny_extent"] = (F(0.7) + rng.integers(0, 40, (200, 3)).astype(F) * np.spacing(F(0.7))).astype(F)  # a few ulps wide
+    out["anisotropic"] = (rng.uniform(0, 1, (400, 3)) * [1.0, 1e-3, 1e-6]).astype(F)
+    two = rng.normal(0, 0.01, (300, 3))
+    two[150:] += [5.0, -3.0, 2.0]
+    out["two_clusters"] = two.astype(F)
+    dup = rng.uniform(-1, 1, (40, 3)).astype(F)
+    out["duplicates"] = np.concatenate([dup, dup[::-1], dup])
+    out["single"] = F([[0.25, -0.5, 0.125]])
+    out["pair"] = F([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0]])
+    big = rng.uniform(-1, 1, (400, 3))
+    out["kilometre_off"] = (big * 0.05 + [1000.0, 1000.0, 1000.0]).astype(F)
+    out["negative_far"] = (big * 3.0 - [5e3, 0.0, 2e3]).astype(F)
+    out["huge_coords"] = (rng.uniform(-5, 5, (300, 3)) + [1e5, -1e5, 3e4]).astype(F)   # coordinates quantised to 1/128
+    mixed = rng.normal(0, 1e-4, (300, 3))
+    mixed[:6] = rng.uniform(-100, 100, (6, 3))                                        # a dense knot + outliers 100 m away
+    out["mixed_scale"] = mixed.astype(F)
+    out["with_nonfinite"] = np.where(rng.uniform(size=(300, 3)) < 0.05, np.nan, rng.uniform(-1, 1, (300, 3))).astype(F)
+    surf = rng.uniform(-0.06, 0.06, (600, 2))
+    out["surface"] = np.column_stack([surf, 0.7 + 0.02 * np.sin(40 * surf[:, 0]) * np.cos(35 * surf[:, 1])]).astype(F)
+    return out
+
+
+def queries(rng, tgt):
+    tgt = tgt[np.isfinite(tgt).all(1)]
+    n = len(tgt)
+    lo, hi = tgt.min(0), tgt.max(0)
+    ext = np.maximum(hi - lo, np.spacing(np.abs(hi).max().astype(F)) * 4)
+    pick = rng.integers(0, n, 160)
+    a, b = tgt[rng.integers(0, n, 160)], tgt[rng.integers(0, n, 160)]
+    qs = [
+        tgt[pick],                                                        # on top of target points
+        ((a.astype(np.float64) + b) * 0.5).astype(F),                     # midpoints: exact ties on lattices
+        np.nextafter(tgt[pick], F(np.inf)), np.nextafter(tgt[pick], F(-np.inf)),   # one ulp off a target point
+        (lo + rng.uniform(0, 1, (160, 3)) * ext).astype(F),               # inside the box
+        (lo + rng.uniform(-2, 3, (160, 3)) * ext).astype(F),              # around the box
+        (lo + rng.uniform(-40, 41, (60, 3)) * ext).astype(F),             # far outside
+        np.array([lo, hi, (lo + hi) / 2, [lo[0], hi[1], lo[2]], [hi[0], lo[1], hi[2]]], F),  # corners
+        (lo + rng.integers(0, 9, (100, 3)) * (ext / 8)).astype(F),        # a coarse lattice over the box (cell edges for some h)
+    ]
+    return np.ascontiguousarray(np.concatenate(qs).astype(F))
+
+
+OCCUPANCIES = [0.25, 1.0, 3.5, 16.0]
+
+
+def grid_nn_seeded(hc, tgt, q, sq, occupancy, limit=np.inf):  # noqa: F811
+    tgt = np.ascontiguousarray(tgt, F)
+    idx = np.empty(len(q), np.int32)
+    d2 = np.empty(len(q), F)
+    hc.hc_grid_nn_seeded(tgt.ctypes.data, len(tgt), tgt.strides[0], q.ctypes.data, sq.ctypes.data, len(q), occupancy, limit,
+                         idx.ctypes.data, d2.ctypes.data)
+    return idx, d2
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_ring_search_is_exact_on_adversarial_clouds(hc, oracle, seed):  # noqa: F811
+    rng = np.random.default_rng(1000 + seed)
+    for name, tgt in clouds(rng).items():
+        q = queries(rng, tgt)
+        bi, bd = oracle.nn_bruteforce(tgt, q)
+        for occ in OCCUPANCIES:
+            gi, gd, _ = grid_nn(hc, tgt, q, occupancy=occ)
+            assert np.array_equal(gd, bd), (name, occ, np.flatnonzero(gd != bd)[:5])
+            assert np.array_equal(gi, bi), (name, occ, np.flatnonzero(gi != bi)[:5])
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_warm_ball_search_is_exact_on_adversarial_clouds(hc, oracle, seed):  # noqa: F811
+    """whatever the candidate: the true match, a neighbour in index order, a random point"""
+    rng = np.random.default_rng(2000 + seed)
+    for name, tgt in clouds(rng).items():
+        q = queries(rng, tgt)
+        bi, bd = oracle.nn_bruteforce(tgt, q)
+        ok = np.flatnonzero(np.isfinite(tgt).all(1))  # candidates are previous matches: always finite points
+        for occ in OCCUPANCIES:
+            for kind, prev in (("true", bi), ("next", ok[(np.searchsorted(ok, bi) + 1) % len(ok)]), ("random", rng.choice(ok, len(q)))):
+                gi, gd = grid_nn_warm(hc, tgt, q, prev.astype(np.int32), occ)
+                assert np.array_equal(gd, bd), (name, occ, kind, np.flatnonzero(gd != bd)[:5])
+                assert np.array_equal(gi, bi), (name, occ, kind, np.flatnonzero(gi != bi)[:5])
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_warm_search_with_a_rejection_limit_is_exact_where_it_matters(hc, oracle, seed):  # noqa: F811
+    """limit_d2 (the max-correspondence-distance cut): matches within the limit are exact, the others stay beyond it"""
+    rng = np.random.default_rng(3000 + seed)
+    for name, tgt in clouds(rng).items():
+        q = queries(rng, tgt)
+        bi, bd = oracle.nn_bruteforce(tgt, q)
+        finite = bd[np.isfinite(bd) & (bd > 0)]
+        if finite.size == 0:
+            continue
+        lim = F(np.median(finite))
+        prev = rng.choice(np.flatnonzero(np.isfinite(tgt).all(1)), len(q)).astype(np.int32)
+        for occ in (1.0, 3.5):
+            gi, gd = grid_nn_warm(hc, tgt, q, prev, occ, float(lim))
+            acc = bd <= lim
+            assert np.array_equal(gd[acc], bd[acc]) and np.array_equal(gi[acc], bi[acc]), (name, occ)
+            assert (gd[~acc] > lim).all(), (name, occ)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_seeded_search_is_exact_on_adversarial_clouds(hc, oracle, seed):  # noqa: F811
+    """the first-iteration scheme: a query seeded with the match of a nearby (or not so nearby) query"""
+    rng = np.random.default_rng(4000 + seed)
+    for name, tgt in clouds(rng).items():
+        q = queries(rng, tgt)
+        ext = np.maximum(np.nanmax(tgt, 0) - np.nanmin(tgt, 0), F(1e-6))
+        for spread in (1e-3, 0.05, 2.0):
+            sq = np.ascontiguousarray((q + rng.normal(0, 1, q.shape) * ext * spread).astype(F))
+            bi, bd = oracle.nn_bruteforce(tgt, q)
+            for occ in (0.25, 3.5):
+                gi, gd = grid_nn_seeded(hc, tgt, q, sq, occ)
+                assert np.array_equal(gd, bd), (name, occ, spread, np.flatnonzero(gd != bd)[:5])
+                assert np.array_equal(gi, bi), (name, occ, spread, np.flatnonzero(gi != bi)[:5])
