@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../pose_estimation_b200/csrc/core_math.cuh"
+#include "../../pose_estimation_b200/csrc/nn_upfront.cuh"
 
 using namespace peb;
 
@@ -153,6 +154,75 @@ HC_API void hc_grid_nn_warm(const float* tgt, size_t n, size_t tstride, const fl
     out_idx[i] = b.idx;
     out_d2[i] = b.d2;
     out_slack[i] = slack;
+  }
+}
+
+// the staged variant of the warm search (csrc/nn_upfront.cuh): same interface as hc_grid_nn_warm without the certificate
+HC_API void hc_grid_nn_warm_upfront(const float* tgt, size_t n, size_t tstride, const float* q, size_t nq, size_t qstride,
+                                    float occupancy, const int32_t* prev, float limit_d2, int32_t* out_idx, float* out_d2) {
+  HostGrid g;
+  build_grid(tgt, n, tstride / 4, occupancy, 0.0f, g);
+  std::vector<int> pos(n, -1);
+  for (int j = 0; j < g.v.n; ++j) pos[point_index(g.pts[j])] = j;
+  for (size_t i = 0; i < nq; ++i) {
+    const float* p = q + i * (qstride / 4);
+    NnBest b = grid_nn_warm_upfront(g.v, p[0], p[1], p[2], pos[prev[i]], limit_d2);
+    out_idx[i] = b.idx;
+    out_d2[i] = b.d2;
+  }
+}
+
+// The warm ball search once more with counters (tests/debug/warm_search_anatomy.py): the loop of
+// core_math.cuh : grid_ball_search, statement for statement.  out4 per query: rows of the ball's bounding box, rows
+// that pass the slab test (two cell_start loads each), points scanned, improvements of the candidate.
+HC_API void hc_warm_stats(const float* tgt, size_t n, size_t tstride, const float* q, size_t nq, size_t qstride,
+                          float occupancy, const int32_t* prev, float limit_d2, int32_t* out_idx, int32_t* out4,
+                          float* out_cell) {
+  HostGrid hg;
+  build_grid(tgt, n, tstride / 4, occupancy, 0.0f, hg);
+  const GridView& g = hg.v;
+  if (out_cell) *out_cell = g.h;
+  std::vector<int> pos(n, -1);
+  for (int j = 0; j < g.n; ++j) pos[point_index(hg.pts[j])] = j;
+  for (size_t i = 0; i < nq; ++i) {
+    const float* p = q + i * (qstride / 4);
+    const float qx = p[0], qy = p[1], qz = p[2];
+    NnBest best;
+    const float4 t0 = g.pts[pos[prev[i]]];
+    best.d2 = l2_simple(qx, qy, qz, t0.x, t0.y, t0.z);
+    best.idx = point_index(t0);
+    best.j = pos[prev[i]];
+    int rows_box = 0, rows_scanned = 0, points = 0, improved = 0;
+    const float fx = (qx - g.ox) * g.inv_h, fy = (qy - g.oy) * g.inv_h, fz = (qz - g.oz) * g.inv_h;
+    const float inv_h2 = g.inv_h * g.inv_h;
+    const float pad = 0.001f + 4.8e-7f * static_cast<float>(std::max(g.dx, std::max(g.dy, g.dz)));
+    const float R = sqrtf(fminf(best.d2, limit_d2) * inv_h2) * 1.0001f + pad;
+    const int y0 = grid_clamp_cell(fy - R, g.dy), y1 = grid_clamp_cell(fy + R, g.dy);
+    const int z0 = grid_clamp_cell(fz - R, g.dz), z1 = grid_clamp_cell(fz + R, g.dz);
+    for (int z = z0; z <= z1; ++z) {
+      const float dz = grid_slab_dist_cells(fz, z);
+      for (int y = y0; y <= y1; ++y) {
+        ++rows_box;
+        const float dy = grid_slab_dist_cells(fy, y);
+        const float dyz2 = dy * dy + dz * dz;
+        const float cur = fminf(best.d2, limit_d2) * inv_h2;
+        if (dyz2 > cur) continue;
+        ++rows_scanned;
+        const float rx = sqrtf(cur - dyz2) * 1.0001f + pad;
+        const int x0 = grid_clamp_cell(fx - rx, g.dx), x1 = grid_clamp_cell(fx + rx, g.dx);
+        const int base = (z * g.dy + y) * g.dx;
+        const uint32_t s = g.cell_start[base + x0], e = g.cell_start[base + x1 + 1];
+        points += static_cast<int>(e - s);
+        const int before = best.j;
+        grid_scan_range(g, s, e, qx, qy, qz, best);
+        improved += best.j != before;
+      }
+    }
+    out_idx[i] = best.idx;
+    out4[4 * i] = rows_box;
+    out4[4 * i + 1] = rows_scanned;
+    out4[4 * i + 2] = points;
+    out4[4 * i + 3] = improved;
   }
 }
 

@@ -140,3 +140,46 @@ def test_seeded_search_is_exact_on_adversarial_clouds(hc, oracle, seed):  # noqa
                 gi, gd = grid_nn_seeded(hc, tgt, q, sq, occ)
                 assert np.array_equal(gd, bd), (name, occ, spread, np.flatnonzero(gd != bd)[:5])
                 assert np.array_equal(gi, bi), (name, occ, spread, np.flatnonzero(gi != bi)[:5])
+
+
+def grid_nn_warm_upfront(hc, tgt, q, prev, occupancy, limit=np.inf):  # noqa: F811
+    import ctypes as C
+
+    tgt = np.ascontiguousarray(tgt, F)
+    prev = np.ascontiguousarray(prev, np.int32)
+    idx = np.empty(len(q), np.int32)
+    d2 = np.empty(len(q), F)
+    vp, sz = C.c_void_p, C.c_size_t
+    hc.hc_grid_nn_warm_upfront.argtypes = [vp, sz, sz, vp, sz, sz, C.c_float, vp, C.c_float, vp, vp]
+    hc.hc_grid_nn_warm_upfront(tgt.ctypes.data, len(tgt), tgt.strides[0], q.ctypes.data, len(q), q.strides[0], occupancy,
+                               prev.ctypes.data, limit, idx.ctypes.data, d2.ctypes.data)
+    return idx, d2
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_staged_upfront_warm_search_is_exact_too(hc, oracle, seed):  # noqa: F811
+    """csrc/nn_upfront.cuh (staged for the next round, not in any kernel yet): row bounds of the initial ball fetched up
+    front, chords not narrowed — must return what the row-after-row walk returns, on the same adversarial inputs and on
+    an ICP-like surface case where most balls are small (the 2 x 2 path) and some are not (the fallback)."""
+    from pose_estimation_b200.testing import synth
+
+    rng = np.random.default_rng(5000 + seed)
+    cases = dict(clouds(rng))
+    prob = synth.make_c1(5000, seed=40 + seed)
+    cases["icp_like"] = np.ascontiguousarray(prob.target[:, :3])
+    for name, tgt in cases.items():
+        q = queries(rng, tgt)
+        if name == "icp_like":
+            q = np.ascontiguousarray(np.concatenate([q, prob.source[:, :3]]))
+        bi, bd = oracle.nn_bruteforce(tgt, q)
+        ok = np.flatnonzero(np.isfinite(tgt).all(1))
+        for occ in OCCUPANCIES:
+            for kind, prev in (("true", bi), ("next", ok[(np.searchsorted(ok, bi) + 1) % len(ok)]), ("random", rng.choice(ok, len(q)))):
+                gi, gd = grid_nn_warm_upfront(hc, tgt, q, prev, occ)
+                assert np.array_equal(gd, bd), (name, occ, kind, np.flatnonzero(gd != bd)[:5])
+                assert np.array_equal(gi, bi), (name, occ, kind, np.flatnonzero(gi != bi)[:5])
+        lim = F(np.median(bd[np.isfinite(bd)])) if np.isfinite(bd).any() else F(1.0)
+        gi, gd = grid_nn_warm_upfront(hc, tgt, q, rng.choice(ok, len(q)), 3.5, float(lim))
+        acc = bd <= lim
+        assert np.array_equal(gd[acc], bd[acc]) and np.array_equal(gi[acc], bi[acc]), name
+        assert (gd[~acc] > lim).all(), name
