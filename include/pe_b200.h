@@ -124,7 +124,9 @@ PEB_API uint64_t peb_ctx_launch_count(const peb_ctx* ctx);
  * of a batched align, 0 = auto), "blocks_factor" / "blocks_factor_cold" (blocks per SM and launch, 0 = auto),
  * "flag_deps" (warm launches of a batch wait per hypothesis instead of for the whole previous grid),
  * "pdl" (programmatic dependent launch), "cert_margin_x1000" (search-skipping certificates, off),
- * "profile" (0 / 1 / 2, see peb_profile_read), "debug_timers" (development) */
+ * "profile" (0 / 1 / 2, see peb_profile_read), "debug_timers" (development),
+ * "warm_upfront" (experimental, default 0: warm searches fetch the row bounds of their ball up front,
+ * csrc/nn_upfront.cuh — exact on the CPU checks, never run or measured on a GPU yet) */
 PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value);
 
 /* ---- pcl::VoxelGrid<PointXYZ>::filter  [PCL] filters/.../impl/voxel_grid.hpp -------- */

@@ -276,6 +276,10 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
     ctx->warm_start = value != 0;
     return PEB_OK;
   }
+  if (!strcmp(key, "warm_upfront")) {
+    ctx->warm_upfront = value != 0;
+    return PEB_OK;
+  }
   if (!strcmp(key, "profile")) {
     ctx->profile = value != 0;
     ctx->profile_level = value;

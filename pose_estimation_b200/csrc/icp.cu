@@ -26,6 +26,7 @@
 #include <algorithm>
 
 #include "nn_search.cuh"
+#include "nn_upfront.cuh"
 
 namespace peb {
 
@@ -385,7 +386,8 @@ __device__ __forceinline__ NnBest first_iteration_search(const IcpLaunch& L, int
 // increment, or the guess in the first iteration), its exact nearest neighbour is searched (seeded
 // by its previous match when there is one), the correspondence is thresholded and added to the
 // estimator's moment sums.  Shared by the per-iteration kernel and the work-queue kernel.
-template <int G, int EST, bool CERT, int NACC>
+// UPF: the warm search fetches all row bounds of its ball up front (nn_upfront.cuh; experimental, off by default)
+template <int G, int EST, bool CERT, bool UPF, int NACC>
 __device__ __forceinline__ void icp_query(const IcpLaunch& L, const int h, float4* __restrict__ work, const int i,
                                           const bool first, const bool apply, const float* T, CoopTile* tile,
                                           double (&acc)[NACC]) {
@@ -434,7 +436,8 @@ __device__ __forceinline__ void icp_query(const IcpLaunch& L, const int h, float
         }
         *sl = slack;
       } else {
-        best = grid_nn_warm(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2);
+        best = UPF ? grid_nn_warm_upfront(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2)
+                   : grid_nn_warm(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2);
       }
     } else {
       best = grid_nn<G>(L.grid, p.x, p.y, p.z, L.stop_d2);
@@ -458,7 +461,7 @@ __device__ __forceinline__ void icp_query(const IcpLaunch& L, const int h, float
 
 // One block's share of one ICP iteration of hypothesis h: chunk `blk` of L.blocks_per_hyp.  Shared by
 // the per-iteration kernel (blk = blockIdx.x, h = blockIdx.y) and the work-queue kernel below.
-template <int G, int EST, int MB, bool CERT, bool FIRST>
+template <int G, int EST, int MB, bool CERT, bool FIRST, bool UPF>
 __device__ __forceinline__ void icp_iteration_body(const IcpLaunch& L, const int h, const int blk) {
   unsigned long long t_dbg[5];
   if (L.dbg) t_dbg[0] = global_ns();
@@ -502,7 +505,7 @@ __device__ __forceinline__ void icp_iteration_body(const IcpLaunch& L, const int
   constexpr int kQ = kIcpThreads / G;  // queries per block per pass
   const int q_local = threadIdx.x / G;
   for (int base = blk * kQ; base < L.n_src; base += L.blocks_per_hyp * kQ)
-    icp_query<G, EST, CERT>(L, h, work, base + q_local, first, apply, T, &s_tile[threadIdx.x >> 5], acc);
+    icp_query<G, EST, CERT, UPF>(L, h, work, base + q_local, first, apply, T, &s_tile[threadIdx.x >> 5], acc);
 
   if (L.dbg) t_dbg[1] = global_ns();
   const double r = block_reduce_acc<NACC>(acc, sm);
@@ -546,7 +549,7 @@ __device__ __forceinline__ void icp_iteration_body(const IcpLaunch& L, const int
 // waiting block only waits for blocks of earlier launches, and those were all resident before it was dispatched.
 // The wait is bounded (a dependency that never comes would be a bug): it then raises the error flag, which the
 // fitness kernel reports in every record.
-template <int G, int EST, int MB, bool CERT, bool FIRST>
+template <int G, int EST, int MB, bool CERT, bool FIRST, bool UPF = false>
 __global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_kernel(const IcpLaunch L) {
   if (FIRST || L.epochs == nullptr) {
     pdl_trigger_and_wait();
@@ -554,7 +557,7 @@ __global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_kernel(const Ic
     asm volatile("griddepcontrol.launch_dependents;");
     wait_for_hypothesis(L.epochs + blockIdx.y, L.launch_idx, L.err_flag);
   }
-  icp_iteration_body<G, EST, MB, CERT, FIRST>(L, blockIdx.y, blockIdx.x);
+  icp_iteration_body<G, EST, MB, CERT, FIRST, UPF>(L, blockIdx.y, blockIdx.x);
 }
 
 // [PCL] registration/impl/registration.hpp : getFitnessScore(max_range) with the final transform
@@ -723,6 +726,14 @@ int launch_one_iteration(peb_ctx* ctx, const IcpLaunch& L, size_t H, int estimat
   const bool svd = estimator == PEB_ESTIMATOR_SVD;
 #define PEB_ICP_LAUNCH(EST, MB, CERT) \
   PEB_LAUNCH_PDL(ctx, (icp_iteration_kernel<G, EST, MB, CERT, FIRST>), grid, dim3(kIcpThreads), L)
+  if (G == 1 && !FIRST && !cert && ctx->warm_upfront && L.warm) {  // experimental warm search (peb_ctx_set_int "warm_upfront")
+#define PEB_ICP_LAUNCH_UPF(EST, MB) \
+  PEB_LAUNCH_PDL(ctx, (icp_iteration_kernel<1, EST, MB, false, false, true>), grid, dim3(kIcpThreads), L)
+    if (H == 1) { if (svd) PEB_ICP_LAUNCH_UPF(S, kMinBlocksSingle); else PEB_ICP_LAUNCH_UPF(P, kMinBlocksSingle); }
+    else        { if (svd) PEB_ICP_LAUNCH_UPF(S, kMinBlocksBatch);  else PEB_ICP_LAUNCH_UPF(P, kMinBlocksBatch); }
+#undef PEB_ICP_LAUNCH_UPF
+    return PEB_OK;
+  }
   if (H == 1) {
     if (cert) { if (svd) PEB_ICP_LAUNCH(S, kMinBlocksSingle, (G == 1)); else PEB_ICP_LAUNCH(P, kMinBlocksSingle, (G == 1)); }
     else      { if (svd) PEB_ICP_LAUNCH(S, kMinBlocksSingle, false);    else PEB_ICP_LAUNCH(P, kMinBlocksSingle, false); }

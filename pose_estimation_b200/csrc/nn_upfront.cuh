@@ -1,6 +1,8 @@
 // nn_upfront.cuh — the warm ball search with every row bound fetched before the first scan.
 //
-// STATUS: staged for round 2, NOT yet included by any kernel (icp.cu still calls core_math.cuh : grid_nn_warm).
+// STATUS: experimental.  icp.cu instantiates the warm iteration kernels a second time with it (template flag UPF), chosen
+// by peb_ctx_set_int(ctx, "warm_upfront", 1); the default stays core_math.cuh : grid_nn_warm, and the default kernels are
+// byte-identical in SASS with and without this file.  Never run on a GPU yet (written after the round's GPU time was spent).
 // Exactness is checked on the CPU (tests/host/host_check.cu : hc_grid_nn_warm_upfront, tests/test_host_fuzz.py);
 // whether it is faster has to be measured on the B200 before it replaces anything.
 //
