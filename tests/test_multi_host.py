@@ -115,3 +115,24 @@ def test_product_never_touches_the_oracle():
         for path in base.rglob("*"):
             if path.suffix in (".py", ".cu", ".cuh", ".h", ".hpp", ".cpp") or path.name == "Makefile":
                 assert not pat.search(path.read_text()), path
+
+
+def test_header_is_plain_c99_and_the_library_links_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: the header must compile as C (pedantic C99), the library must link without a
+    C++ driver, the POD layouts are fixed, and with no GPU the entry points refuse instead of computing on the CPU."""
+    import subprocess
+
+    exe = tmp_path / "abi_check"
+    lib_dir = ROOT / "pose_estimation_b200"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", str(ROOT / "include"),
+                        str(ROOT / "tests" / "c" / "abi_check.c"), "-o", str(exe), "-L", str(lib_dir), "-lpe_b200", "-lm",
+                        f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    import torch
+
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "ctx ok" in r.stdout, r.stdout
+    else:
+        assert r.returncode == 10, r.stdout
+        assert "no CPU fallback" in r.stdout and "multi_create" in r.stdout
