@@ -263,6 +263,54 @@ class Problem:
     meta: dict = field(default_factory=dict)
 
 
+# ------------------------------------------------------------------------------------------
+# on-disk form of a problem: raw little-endian float32 N x 4 records (x, y, z, 1.0 — the memory image of
+# pcl::PointXYZ) + one JSON sidecar, so that the oracle, the library and the C++ checks read the same bytes
+# ------------------------------------------------------------------------------------------
+def save_problem(problem: Problem, directory) -> None:
+    """source.f32 / target.f32 / organized.f32 (N x 4 float32, C order), guess.f64 (H x 16 or 16 float64, row-major 4 x 4)
+    and problem.json (name, counts, organized width x height, ground-truth pose, leaf, generator meta)."""
+    import json
+    from pathlib import Path
+
+    d = Path(directory)
+    d.mkdir(parents=True, exist_ok=True)
+    for name in ("source", "target", "organized"):
+        a = getattr(problem, name)
+        if a is not None:
+            np.ascontiguousarray(a, "<f4").tofile(d / f"{name}.f32")
+    np.ascontiguousarray(problem.guess, "<f8").tofile(d / "guess.f64")
+    side = {
+        "name": problem.name, "format": "float32 little-endian, N x 4 (x y z 1.0) per cloud; guess float64 row-major 4 x 4",
+        "n_source": int(len(problem.source)), "n_target": int(len(problem.target)),
+        "n_organized": None if problem.organized is None else int(len(problem.organized)),
+        "n_guesses": int(np.asarray(problem.guess).reshape(-1, 16).shape[0]), "guess_is_batch": bool(np.asarray(problem.guess).ndim == 3),
+        "gt_pose": np.asarray(problem.gt_pose, np.float64).tolist(), "leaf": problem.leaf, "meta": problem.meta,
+    }
+    (d / "problem.json").write_text(json.dumps(side, indent=1))
+
+
+def load_problem(directory) -> Problem:
+    import json
+    from pathlib import Path
+
+    d = Path(directory)
+    side = json.loads((d / "problem.json").read_text())
+
+    def cloud(name, n):
+        if n is None:
+            return None
+        a = np.fromfile(d / f"{name}.f32", "<f4")
+        if a.size != 4 * n:
+            raise ValueError(f"{name}.f32 holds {a.size} floats, the sidecar says {n} x 4")
+        return a.reshape(n, 4)
+
+    g = np.fromfile(d / "guess.f64", "<f8").reshape(-1, 4, 4)
+    return Problem(side["name"], cloud("source", side["n_source"]), cloud("target", side["n_target"]),
+                   g if side["guess_is_batch"] else g[0], np.array(side["gt_pose"], np.float64),
+                   organized=cloud("organized", side["n_organized"]), leaf=side["leaf"], meta=side["meta"])
+
+
 def make_c1(n: int = 20000, seed: int = 1) -> Problem:
     """C1: 20k-pt model vs a rigidly moved, 1 mm-noise copy; the CPU-runnable case."""
     rng = np.random.default_rng(seed)
