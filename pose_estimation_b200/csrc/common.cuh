@@ -102,7 +102,8 @@ struct peb_ctx {
                                 // 1.5 94.1, 2.0 97.1, 2.5 93.4, 3.0 91.8, 3.5 91.5, 4.0 91.2, 5.0 92.7, 6.0 95.4, 8.0 101.0 per
                                 // 1024-hypothesis batch; single align 0.736 ms at 2.0, 0.721 at 3.0, 0.729 at 4.0)
   bool warm_start = true;       // iterations >= 1 seed the search with the previous match
-  bool warm_upfront = false;    // experimental: warm searches fetch the row bounds of their ball up front (nn_upfront.cuh); unmeasured
+  int warm_upfront = 0;         // experimental: warm searches fetch the row bounds of their ball up front (nn_upfront.cuh):
+                                // 0 = off, 1 or 2 = boxes up to 2 x 2 rows, 3 = up to 3 x 3; unmeasured
   bool anchor_seed = true;      // iteration 0: one cold search per 32-point patch seeds the patch
   int coop_max_rows = 1024;     // first iteration of a batch: a patch verifies its 32 candidates together (nn_search.cuh) up to this many grid rows
   float seed_guard = 10.0f;     // seeds farther than this many cells from the query are not used

@@ -386,8 +386,9 @@ __device__ __forceinline__ NnBest first_iteration_search(const IcpLaunch& L, int
 // increment, or the guess in the first iteration), its exact nearest neighbour is searched (seeded
 // by its previous match when there is one), the correspondence is thresholded and added to the
 // estimator's moment sums.  Shared by the per-iteration kernel and the work-queue kernel.
-// UPF: the warm search fetches all row bounds of its ball up front (nn_upfront.cuh; experimental, off by default)
-template <int G, int EST, bool CERT, bool UPF, int NACC>
+// UPF: the warm search fetches all row bounds of its ball up front (nn_upfront.cuh; experimental, off by default):
+// 0 = off, 2 / 3 = balls whose box spans up to 2 x 2 / 3 x 3 grid rows take that path
+template <int G, int EST, bool CERT, int UPF, int NACC>
 __device__ __forceinline__ void icp_query(const IcpLaunch& L, const int h, float4* __restrict__ work, const int i,
                                           const bool first, const bool apply, const float* T, CoopTile* tile,
                                           double (&acc)[NACC]) {
@@ -436,7 +437,7 @@ __device__ __forceinline__ void icp_query(const IcpLaunch& L, const int h, float
         }
         *sl = slack;
       } else {
-        best = UPF ? grid_nn_warm_upfront(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2)
+        best = UPF ? grid_nn_warm_upfront<(UPF > 0 ? UPF : 2)>(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2)
                    : grid_nn_warm(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2);
       }
     } else {
@@ -461,7 +462,7 @@ __device__ __forceinline__ void icp_query(const IcpLaunch& L, const int h, float
 
 // One block's share of one ICP iteration of hypothesis h: chunk `blk` of L.blocks_per_hyp.  Shared by
 // the per-iteration kernel (blk = blockIdx.x, h = blockIdx.y) and the work-queue kernel below.
-template <int G, int EST, int MB, bool CERT, bool FIRST, bool UPF>
+template <int G, int EST, int MB, bool CERT, bool FIRST, int UPF>
 __device__ __forceinline__ void icp_iteration_body(const IcpLaunch& L, const int h, const int blk) {
   unsigned long long t_dbg[5];
   if (L.dbg) t_dbg[0] = global_ns();
@@ -549,7 +550,7 @@ __device__ __forceinline__ void icp_iteration_body(const IcpLaunch& L, const int
 // waiting block only waits for blocks of earlier launches, and those were all resident before it was dispatched.
 // The wait is bounded (a dependency that never comes would be a bug): it then raises the error flag, which the
 // fitness kernel reports in every record.
-template <int G, int EST, int MB, bool CERT, bool FIRST, bool UPF = false>
+template <int G, int EST, int MB, bool CERT, bool FIRST, int UPF = 0>
 __global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_kernel(const IcpLaunch L) {
   if (FIRST || L.epochs == nullptr) {
     pdl_trigger_and_wait();
@@ -727,10 +728,15 @@ int launch_one_iteration(peb_ctx* ctx, const IcpLaunch& L, size_t H, int estimat
 #define PEB_ICP_LAUNCH(EST, MB, CERT) \
   PEB_LAUNCH_PDL(ctx, (icp_iteration_kernel<G, EST, MB, CERT, FIRST>), grid, dim3(kIcpThreads), L)
   if (G == 1 && !FIRST && !cert && ctx->warm_upfront && L.warm) {  // experimental warm search (peb_ctx_set_int "warm_upfront")
-#define PEB_ICP_LAUNCH_UPF(EST, MB) \
-  PEB_LAUNCH_PDL(ctx, (icp_iteration_kernel<1, EST, MB, false, false, true>), grid, dim3(kIcpThreads), L)
-    if (H == 1) { if (svd) PEB_ICP_LAUNCH_UPF(S, kMinBlocksSingle); else PEB_ICP_LAUNCH_UPF(P, kMinBlocksSingle); }
-    else        { if (svd) PEB_ICP_LAUNCH_UPF(S, kMinBlocksBatch);  else PEB_ICP_LAUNCH_UPF(P, kMinBlocksBatch); }
+#define PEB_ICP_LAUNCH_UPF(EST, MB, RW) \
+  PEB_LAUNCH_PDL(ctx, (icp_iteration_kernel<1, EST, MB, false, false, RW>), grid, dim3(kIcpThreads), L)
+    if (ctx->warm_upfront == 3) {
+      if (H == 1) { if (svd) PEB_ICP_LAUNCH_UPF(S, kMinBlocksSingle, 3); else PEB_ICP_LAUNCH_UPF(P, kMinBlocksSingle, 3); }
+      else        { if (svd) PEB_ICP_LAUNCH_UPF(S, kMinBlocksBatch, 3);  else PEB_ICP_LAUNCH_UPF(P, kMinBlocksBatch, 3); }
+    } else {
+      if (H == 1) { if (svd) PEB_ICP_LAUNCH_UPF(S, kMinBlocksSingle, 2); else PEB_ICP_LAUNCH_UPF(P, kMinBlocksSingle, 2); }
+      else        { if (svd) PEB_ICP_LAUNCH_UPF(S, kMinBlocksBatch, 2);  else PEB_ICP_LAUNCH_UPF(P, kMinBlocksBatch, 2); }
+    }
 #undef PEB_ICP_LAUNCH_UPF
     return PEB_OK;
   }

@@ -57,6 +57,7 @@ def main():
     print(f"scene {len(tgt)} points, model {len(src)} points, occupancy {occupancy}")
     limit = np.float32(0.02 ** 2)
     rows_hist = np.zeros(12, np.int64)
+    box_big, box_huge, box_n = np.zeros(30, np.int64), np.zeros(30, np.int64), np.zeros(30, np.int64)
     total = np.zeros(5)
     for h in range(len(prob.guess)):
         T = np.asarray(prob.guess[h], np.float64)
@@ -75,12 +76,20 @@ def main():
                 changed = float((out_idx != prev).mean())
                 if h == 0 and it in (1, 2, 5, 10, 20, 29):
                     r_cells = np.sqrt(np.minimum(((q - tgt[prev]) ** 2).sum(1), limit)) / cell.value
+                    # the bound-only variant (nn_upfront.cuh : grid_nn_bounded_upfront) searches d_old + |movement| instead
+                    r_bound = np.minimum(prev_d + np.linalg.norm(work - prev_work, axis=1), 0.02) / cell.value
+                    print(f"         bound-only ball: {np.median(r_bound):.2f} cells median ({np.median(r_bound / np.maximum(r_cells, 1e-9)):.2f} x the "
+                          f"candidate's ball), 2 x 2 rows suffice for {100 * np.mean(r_bound < 0.5):.0f} % (candidate: {100 * np.mean(r_cells < 0.5):.0f} %)")
                     print(f"  it {it:2d}: ball radius {np.median(r_cells):.2f} cells (median; cell {1e3 * cell.value:.2f} mm)  rows in box "
                           f"{st[:, 0].mean():.2f}  rows scanned {st[:, 1].mean():.2f}  points scanned {st[:, 2].mean():.1f}  "
                           f"match changed {100 * changed:.1f} %")
+                box_big[it] += int((~np.isin(st[:, 0], (1, 2, 4))).sum())   # 3 x 1, 3 x 2, ...: more than 2 x 2 rows in the box
+                box_huge[it] += int((st[:, 0] > 9).sum())                       # more than 3 x 3
+                box_n[it] += len(q)
                 rows_hist += np.bincount(np.minimum(st[:, 1], 11), minlength=12)
                 total += [len(q), st[:, 0].sum(), st[:, 1].sum(), st[:, 2].sum(), changed * len(q)]
             prev = idx.astype(np.int32)
+            prev_d, prev_work = d.copy(), work.copy()
             R, t = kabsch(work[keep], tgt[idx[keep]].astype(np.float64))
             work = work @ R.T + t
     n = total[0]
@@ -88,6 +97,9 @@ def main():
           f"{total[3] / n:.1f}, match changed {100 * total[4] / n:.1f} %")
     print("rows scanned per query, share of the queries: " + "  ".join(f"{k}{'+' if k == 11 else ''}: {100 * v / n:.1f} %"
                                                                        for k, v in enumerate(rows_hist) if v))
+    print("queries whose box exceeds 2 x 2 rows (the up-front variant's fallback), by iteration: " +
+          "  ".join(f"{it}: {100 * box_big[it] / box_n[it]:.0f} %" for it in (1, 2, 3, 5, 10, 20, 29)) +
+          f"  all: {100 * box_big.sum() / box_n.sum():.1f} %;  exceeding 3 x 3: {100 * box_huge.sum() / box_n.sum():.2f} %")
     # dependent L2 round trips of one query: work[i], pts[j_prev], then per scanned row bounds -> points, row after row
     serial = 2 + 2 * total[2] / n
     upfront = 2 + 2  # all row bounds at once, then all point ranges

@@ -159,16 +159,59 @@ HC_API void hc_grid_nn_warm(const float* tgt, size_t n, size_t tstride, const fl
 
 // the staged variant of the warm search (csrc/nn_upfront.cuh): same interface as hc_grid_nn_warm without the certificate
 HC_API void hc_grid_nn_warm_upfront(const float* tgt, size_t n, size_t tstride, const float* q, size_t nq, size_t qstride,
-                                    float occupancy, const int32_t* prev, float limit_d2, int32_t* out_idx, float* out_d2) {
+                                    float occupancy, const int32_t* prev, float limit_d2, int32_t* out_idx, float* out_d2,
+                                    int rows3) {
   HostGrid g;
   build_grid(tgt, n, tstride / 4, occupancy, 0.0f, g);
   std::vector<int> pos(n, -1);
   for (int j = 0; j < g.v.n; ++j) pos[point_index(g.pts[j])] = j;
   for (size_t i = 0; i < nq; ++i) {
     const float* p = q + i * (qstride / 4);
-    NnBest b = grid_nn_warm_upfront(g.v, p[0], p[1], p[2], pos[prev[i]], limit_d2);
+    NnBest b = rows3 ? grid_nn_warm_upfront<3>(g.v, p[0], p[1], p[2], pos[prev[i]], limit_d2)
+                     : grid_nn_warm_upfront<2>(g.v, p[0], p[1], p[2], pos[prev[i]], limit_d2);
     out_idx[i] = b.idx;
     out_d2[i] = b.d2;
+  }
+}
+
+// the bound-only warm search (csrc/nn_upfront.cuh, staged): bound_d2[i] is handed in per query
+HC_API void hc_grid_nn_bounded(const float* tgt, size_t n, size_t tstride, const float* q, size_t nq, size_t qstride,
+                               float occupancy, const float* bound_d2, float limit_d2, int32_t* out_idx, float* out_d2) {
+  HostGrid g;
+  build_grid(tgt, n, tstride / 4, occupancy, 0.0f, g);
+  for (size_t i = 0; i < nq; ++i) {
+    const float* p = q + i * (qstride / 4);
+    NnBest b = grid_nn_bounded_upfront(g.v, p[0], p[1], p[2], bound_d2[i], limit_d2);
+    out_idx[i] = b.idx;
+    out_d2[i] = b.d2;
+  }
+}
+
+// An ICP-like sequence of warm searches as a kernel would run them: query set k is searched with the bound
+// warm_bound_d2(d2 found for set k - 1, |q_k - q_(k-1)| in float, h).  q: steps x nq x 3 floats.  Set 0 is searched cold.
+HC_API void hc_bounded_trajectory(const float* tgt, size_t n, size_t tstride, const float* q, size_t nq, size_t steps,
+                                  float occupancy, float limit_d2, int32_t* out_idx, float* out_d2) {
+  HostGrid g;
+  build_grid(tgt, n, tstride / 4, occupancy, 0.0f, g);
+  std::vector<float> d2_old(nq);
+  for (size_t k = 0; k < steps; ++k) {
+    for (size_t i = 0; i < nq; ++i) {
+      const float* p = q + (k * nq + i) * 3;
+      NnBest b;
+      bool cold = k == 0 || !(d2_old[i] < INFINITY);
+      if (!cold) {
+        const float* o = q + ((k - 1) * nq + i) * 3;
+        const float mx = p[0] - o[0], my = p[1] - o[1], mz = p[2] - o[2];
+        const float moved = sqrtf(mx * mx + my * my + mz * mz);
+        b = grid_nn_bounded_upfront(g.v, p[0], p[1], p[2], warm_bound_d2(d2_old[i], moved, g.v.h), limit_d2);
+      } else {
+        int rings;
+        b = grid_nn_host(g.v, p[0], p[1], p[2], limit_d2, &rings);
+      }
+      out_idx[k * nq + i] = b.idx;
+      out_d2[k * nq + i] = b.d2;
+      d2_old[i] = (b.idx >= 0 && b.d2 <= limit_d2) ? b.d2 : INFINITY;  // a rejected query searches cold next time
+    }
   }
 }
 

@@ -142,7 +142,7 @@ def test_seeded_search_is_exact_on_adversarial_clouds(hc, oracle, seed):  # noqa
                 assert np.array_equal(gi, bi), (name, occ, spread, np.flatnonzero(gi != bi)[:5])
 
 
-def grid_nn_warm_upfront(hc, tgt, q, prev, occupancy, limit=np.inf):  # noqa: F811
+def grid_nn_warm_upfront(hc, tgt, q, prev, occupancy, limit=np.inf, rows3=0):  # noqa: F811
     import ctypes as C
 
     tgt = np.ascontiguousarray(tgt, F)
@@ -150,9 +150,9 @@ def grid_nn_warm_upfront(hc, tgt, q, prev, occupancy, limit=np.inf):  # noqa: F8
     idx = np.empty(len(q), np.int32)
     d2 = np.empty(len(q), F)
     vp, sz = C.c_void_p, C.c_size_t
-    hc.hc_grid_nn_warm_upfront.argtypes = [vp, sz, sz, vp, sz, sz, C.c_float, vp, C.c_float, vp, vp]
+    hc.hc_grid_nn_warm_upfront.argtypes = [vp, sz, sz, vp, sz, sz, C.c_float, vp, C.c_float, vp, vp, C.c_int]
     hc.hc_grid_nn_warm_upfront(tgt.ctypes.data, len(tgt), tgt.strides[0], q.ctypes.data, len(q), q.strides[0], occupancy,
-                               prev.ctypes.data, limit, idx.ctypes.data, d2.ctypes.data)
+                               prev.ctypes.data, limit, idx.ctypes.data, d2.ctypes.data, rows3)
     return idx, d2
 
 
@@ -175,11 +175,93 @@ def test_staged_upfront_warm_search_is_exact_too(hc, oracle, seed):  # noqa: F81
         ok = np.flatnonzero(np.isfinite(tgt).all(1))
         for occ in OCCUPANCIES:
             for kind, prev in (("true", bi), ("next", ok[(np.searchsorted(ok, bi) + 1) % len(ok)]), ("random", rng.choice(ok, len(q)))):
-                gi, gd = grid_nn_warm_upfront(hc, tgt, q, prev, occ)
-                assert np.array_equal(gd, bd), (name, occ, kind, np.flatnonzero(gd != bd)[:5])
-                assert np.array_equal(gi, bi), (name, occ, kind, np.flatnonzero(gi != bi)[:5])
+                for rows3 in (0, 1):  # boxes up to 2 x 2 rows, up to 3 x 3 rows
+                    gi, gd = grid_nn_warm_upfront(hc, tgt, q, prev, occ, rows3=rows3)
+                    assert np.array_equal(gd, bd), (name, occ, kind, rows3, np.flatnonzero(gd != bd)[:5])
+                    assert np.array_equal(gi, bi), (name, occ, kind, rows3, np.flatnonzero(gi != bi)[:5])
         lim = F(np.median(bd[np.isfinite(bd)])) if np.isfinite(bd).any() else F(1.0)
         gi, gd = grid_nn_warm_upfront(hc, tgt, q, rng.choice(ok, len(q)), 3.5, float(lim))
         acc = bd <= lim
         assert np.array_equal(gd[acc], bd[acc]) and np.array_equal(gi[acc], bi[acc]), name
         assert (gd[~acc] > lim).all(), name
+
+
+def _bounded(hc, tgt, q, bound_d2, occupancy, limit=np.inf):
+    import ctypes as C
+
+    tgt = np.ascontiguousarray(tgt, F)
+    bound_d2 = np.ascontiguousarray(bound_d2, F)
+    idx = np.empty(len(q), np.int32)
+    d2 = np.empty(len(q), F)
+    vp, sz = C.c_void_p, C.c_size_t
+    hc.hc_grid_nn_bounded.argtypes = [vp, sz, sz, vp, sz, sz, C.c_float, vp, C.c_float, vp, vp]
+    hc.hc_grid_nn_bounded(tgt.ctypes.data, len(tgt), tgt.strides[0], q.ctypes.data, len(q), q.strides[0], occupancy,
+                          bound_d2.ctypes.data, limit, idx.ctypes.data, d2.ctypes.data)
+    return idx, d2
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_staged_bound_only_search_is_exact_for_any_true_bound(hc, oracle, seed):  # noqa: F811
+    """csrc/nn_upfront.cuh : grid_nn_bounded_upfront (staged): no candidate, only an upper bound of the nearest
+    neighbour's squared distance — exact for the tightest possible bound (the distance itself) and for loose ones;
+    a bound cut by the rejection limit reports 'nothing' exactly for the queries brute force rejects."""
+    rng = np.random.default_rng(6000 + seed)
+    for name, tgt in clouds(rng).items():
+        q = queries(rng, tgt)
+        bi, bd = oracle.nn_bruteforce(tgt, q)
+        for occ in (0.25, 3.5, 16.0):
+            for k in (0.0, 1e-6, 0.5, 10.0):
+                bound = (bd.astype(np.float64) * (1.0 + k)).astype(F)
+                bound = np.maximum(bound, bd)  # (rounding of the product must not undercut the distance)
+                gi, gd = _bounded(hc, tgt, q, bound, occ)
+                assert np.array_equal(gd, bd), (name, occ, k, np.flatnonzero(gd != bd)[:5])
+                assert np.array_equal(gi, bi), (name, occ, k, np.flatnonzero(gi != bi)[:5])
+        pos = bd[bd > 0]
+        if pos.size:
+            lim = F(np.median(pos))
+            gi, gd = _bounded(hc, tgt, q, np.full(len(q), np.inf, F), 3.5, float(lim))
+            acc = bd <= lim
+            assert np.array_equal(gi[acc], bi[acc]) and np.array_equal(gd[acc], bd[acc]), name
+            assert (gi[~acc] == -1).all(), name
+
+
+@pytest.mark.parametrize("limit", [np.inf, 0.02 ** 2, 0.002 ** 2])
+def test_staged_bound_only_search_along_an_icp_trajectory(hc, oracle, limit):  # noqa: F811
+    """The invariant the kernel would rely on: d_old + |movement| (inflated by warm_bound_d2) bounds the new nearest
+    distance.  Query sets = the working cloud of a simulated ICP (float32 coordinates, as the kernel stores them),
+    including a large first step; every warm search must equal brute force wherever the match is accepted."""
+    import ctypes as C
+
+    from scipy.spatial import cKDTree
+
+    from pose_estimation_b200.testing import synth
+
+    prob = synth.make_c1(6000, seed=61)
+    tgt = np.ascontiguousarray(prob.target[:, :3], F)
+    tree = cKDTree(tgt.astype(np.float64))
+    work = prob.source[:, :3].astype(np.float64)
+    sets = []
+    for it in range(12):
+        sets.append(work.astype(F))
+        d, idx = tree.query(work)
+        src, dst = work, tgt[idx].astype(np.float64)
+        cs, cd = src.mean(0), dst.mean(0)
+        U, _, Vt = np.linalg.svd((dst - cd).T @ (src - cs))
+        R = U @ np.diag([1.0, 1.0, np.sign(np.linalg.det(U @ Vt))]) @ Vt
+        work = work @ R.T + (cd - R @ cs)
+    q = np.ascontiguousarray(np.stack(sets))
+    steps, nq = q.shape[0], q.shape[1]
+    out_idx = np.empty((steps, nq), np.int32)
+    out_d2 = np.empty((steps, nq), F)
+    vp, sz = C.c_void_p, C.c_size_t
+    hc.hc_bounded_trajectory.argtypes = [vp, sz, sz, vp, sz, sz, C.c_float, C.c_float, vp, vp]
+    hc.hc_bounded_trajectory(tgt.ctypes.data, len(tgt), tgt.strides[0], q.ctypes.data, nq, steps, 3.5, limit,
+                             out_idx.ctypes.data, out_d2.ctypes.data)
+    accepted_warm = 0
+    for k in range(steps):
+        bi, bd = oracle.nn_bruteforce(tgt, q[k])
+        acc = bd <= limit
+        assert np.array_equal(out_idx[k][acc], bi[acc]) and np.array_equal(out_d2[k][acc], bd[acc]), k
+        assert ((out_idx[k][~acc] == -1) | (out_d2[k][~acc] > limit)).all(), k
+        accepted_warm += int(acc.sum()) if k else 0
+    assert accepted_warm > 0

@@ -30,11 +30,12 @@ def scene_small(oracle):
 
 
 def _run(pcl, p, cls, normals, guesses, upfront, **params):
+    """upfront: 0 = the default kernels, 1 = balls up to 2 x 2 grid rows take the up-front path, 3 = up to 3 x 3"""
     from oracle import default_params
 
     c = pcl.Context(0)
     if upfront:
-        c.set_int("warm_upfront", 1)
+        c.set_int("warm_upfront", upfront)
     icp = cls(c)
     icp.setInputSource(p.source)
     icp.setInputTarget(p.target, normals)
@@ -49,17 +50,19 @@ def _run(pcl, p, cls, normals, guesses, upfront, **params):
     return out
 
 
-def test_upfront_warm_search_never_changes_results(pcl, scene_small):
+@pytest.mark.parametrize("rows", [1, 3])
+def test_upfront_warm_search_never_changes_results(pcl, scene_small, rows):
     p = scene_small
     rng = np.random.default_rng(5)
     guesses = np.stack([synth.perturb_pose(p.gt_pose, rng, 5.0, 0.006) for _ in range(200)])
-    a = _run(pcl, p, pcl.IterativeClosestPoint, None, guesses, False, max_iterations=25, max_corr_dist=0.02, abs_mse_threshold=-1.0)
-    b = _run(pcl, p, pcl.IterativeClosestPoint, None, guesses, True, max_iterations=25, max_corr_dist=0.02, abs_mse_threshold=-1.0)
+    a = _run(pcl, p, pcl.IterativeClosestPoint, None, guesses, 0, max_iterations=25, max_corr_dist=0.02, abs_mse_threshold=-1.0)
+    b = _run(pcl, p, pcl.IterativeClosestPoint, None, guesses, rows, max_iterations=25, max_corr_dist=0.02, abs_mse_threshold=-1.0)
     assert a[0] == b[0] and a[1] == b[1]
     assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
 
 
-def test_upfront_warm_search_point_to_plane_and_criteria(pcl, scene_small):
+@pytest.mark.parametrize("rows", [1, 3])
+def test_upfront_warm_search_point_to_plane_and_criteria(pcl, scene_small, rows):
     p = scene_small
     c = pcl.Context(0)
     ne = pcl.NormalEstimation(c)
@@ -70,7 +73,7 @@ def test_upfront_warm_search_point_to_plane_and_criteria(pcl, scene_small):
     rng = np.random.default_rng(6)
     guesses = np.stack([synth.perturb_pose(p.gt_pose, rng, 4.0, 0.004) for _ in range(40)])
     kw = dict(max_iterations=30, max_corr_dist=0.01, transformation_epsilon=1e-9)  # hypotheses stop at different iterations
-    a = _run(pcl, p, pcl.IterativeClosestPointWithNormals, normals, guesses, False, **kw)
-    b = _run(pcl, p, pcl.IterativeClosestPointWithNormals, normals, guesses, True, **kw)
+    a = _run(pcl, p, pcl.IterativeClosestPointWithNormals, normals, guesses, 0, **kw)
+    b = _run(pcl, p, pcl.IterativeClosestPointWithNormals, normals, guesses, rows, **kw)
     assert a[0] == b[0] and a[1] == b[1]
     assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])

@@ -12,7 +12,8 @@ python -m pytest tests/test_zz_experimental_gpu.py tests/test_multi_device.py -q
 echo "rc=$?" >> gpurun_out/next_pytest.log
 for rep in 1 2; do
   python bench.py --steps 5 --warmup 3 --no-single --no-cpu-baseline > gpurun_out/next_bench_default_$rep.json 2> gpurun_out/next_bench_default_$rep.err
-  PEB_OPTS=warm_upfront=1 python bench.py --steps 5 --warmup 3 --no-single --no-cpu-baseline > gpurun_out/next_bench_upfront_$rep.json 2> gpurun_out/next_bench_upfront_$rep.err
+  PEB_OPTS=warm_upfront=1 python bench.py --steps 5 --warmup 3 --no-single --no-cpu-baseline > gpurun_out/next_bench_upfront2x2_$rep.json 2> gpurun_out/next_bench_upfront2x2_$rep.err
+  PEB_OPTS=warm_upfront=3 python bench.py --steps 5 --warmup 3 --no-single --no-cpu-baseline > gpurun_out/next_bench_upfront3x3_$rep.json 2> gpurun_out/next_bench_upfront3x3_$rep.err
 done
 python tools/bench_multi_inproc.py --devices 1,2 --same-device --reps 3 > gpurun_out/next_multi_inproc.jsonl 2> gpurun_out/next_multi_inproc.err
 python - <<'PY'
