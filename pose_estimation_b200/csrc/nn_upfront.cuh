@@ -8,15 +8,16 @@
 //
 // Why: a warm query is a chain of DEPENDENT L2 round trips — work[i] -> pts[j_prev] -> for every row of the ball:
 // (two cell_start loads -> the points of the row), and row k + 1 cannot start before row k is scanned because its chord
-// is cut with the distance found so far.  On the C4 geometry (tests/debug/warm_search_anatomy.py) a query scans 2.4 rows
-// on average (1: 27 %, 2: 41 %, 3: 5 %, 4: 25 %, more: 2.6 %) and 9 points, and its match changes in 12 % of the
-// searches only: 6.8 dependent load levels, of which the shrinking chord saves almost nothing.  Here the chords of the
+// is cut with the distance found so far.  On the C4 clouds (tests/debug/warm_search_anatomy.py, full scale) a query scans
+// 3.1 rows on average (1: 19 %, 2: 35 %, 3: 6 %, 4: 32 %, more: 8 %) and 10 points, and its match changes in 18 % of the
+// searches only: 8.2 dependent load levels, of which the shrinking chord saves almost nothing.  Here the chords of the
 // up to 2 x 2 rows of a small ball are cut with the INITIAL radius (a superset of what the row-after-row walk examines,
 // so the result is the same: the comparison (smaller distance, then lower index) does not depend on the order or on
 // extra candidates farther than the winner), all eight bounds are loaded at once, and the four ranges are scanned back
 // to back: 4 dependent levels, and the same instruction sequence for every lane of a warp (predicated rows instead of
-// data-dependent loop trip counts).  Larger balls take the general walk: 2.9 % of the warm queries exceed a 2 x 2 box
-// (28 % in iteration 1, 9 % in iteration 2, < 2 % from iteration 10 on), 0.3 % a 3 x 3 box (template parameter RW).
+// data-dependent loop trip counts).  Larger balls take the general walk: at full scale 9 % of the warm queries exceed a
+// 2 x 2 box (64 % in iteration 1, 28 % in iteration 2, 9 % in iteration 10, 1 % in iteration 29), 2.4 % a 3 x 3 box
+// (template parameter RW).
 // Checked offline (nvcc 12.9, sm_100a, a kernel that does nothing but this search, __launch_bounds__(128, 8)): 45
 // registers and no spills for this variant and for grid_nn_warm alike; in the SASS the four pairs of cell_start loads
 // are issued in four predicated regions with no use of their results in between (all eight in flight together), the
@@ -27,8 +28,8 @@
 
 namespace peb {
 
-// RW: the ball's bounding box may span up to RW x RW grid rows (2: 97 % of the warm queries of the C4 geometry, 28 % fall
-// back in iteration 1 and ~0 % in iteration 29; 3: 99.7 %, at 18 instead of 8 bound registers)
+// RW: the ball's bounding box may span up to RW x RW grid rows (2: 91 % of the warm queries of the C4 clouds; 3: 97.6 %,
+// at 18 instead of 8 bound registers)
 template <int RW = 2>
 PEB_HD void grid_ball_search_upfront(const GridView& g, float qx, float qy, float qz, float limit_d2, NnBest& best) {
   const float fx = (qx - g.ox) * g.inv_h, fy = (qy - g.oy) * g.inv_h, fz = (qz - g.oz) * g.inv_h;
