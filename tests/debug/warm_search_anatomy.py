@@ -54,6 +54,14 @@ def main():
     tgt = np.ascontiguousarray(prob.target[:, :3], np.float32)
     src = prob.source[:, :3].astype(np.float64)
     tree = cKDTree(tgt.astype(np.float64))
+    # warps: the library stores the source in 32-point patches (cells of its own sort grid, ~32 points each, x fastest)
+    ext = np.sort(src.max(0) - src.min(0))[::-1]
+    hs = np.sqrt(32.0 * ext[0] * ext[1] / len(src))
+    cell = np.floor((src - src.min(0)) / hs).astype(np.int64)
+    order = np.lexsort((cell[:, 0], cell[:, 1], cell[:, 2]))
+    n_warp = len(src) // 32
+    warp_of = order[: n_warp * 32].reshape(n_warp, 32)
+    warp_big, warp_huge, warp_n = np.zeros(30, np.int64), np.zeros(30, np.int64), np.zeros(30, np.int64)
     print(f"scene {len(tgt)} points, model {len(src)} points, occupancy {occupancy}")
     limit = np.float32(0.02 ** 2)
     rows_hist = np.zeros(12, np.int64)
@@ -86,6 +94,9 @@ def main():
                 box_big[it] += int((~np.isin(st[:, 0], (1, 2, 4))).sum())   # 3 x 1, 3 x 2, ...: more than 2 x 2 rows in the box
                 box_huge[it] += int((st[:, 0] > 9).sum())                       # more than 3 x 3
                 box_n[it] += len(q)
+                warp_big[it] += int((~np.isin(st[:, 0], (1, 2, 4)))[warp_of].any(1).sum())
+                warp_huge[it] += int((st[:, 0] > 9)[warp_of].any(1).sum())
+                warp_n[it] += n_warp
                 rows_hist += np.bincount(np.minimum(st[:, 1], 11), minlength=12)
                 total += [len(q), st[:, 0].sum(), st[:, 1].sum(), st[:, 2].sum(), changed * len(q)]
             prev = idx.astype(np.int32)
@@ -100,6 +111,11 @@ def main():
     print("queries whose box exceeds 2 x 2 rows (the up-front variant's fallback), by iteration: " +
           "  ".join(f"{it}: {100 * box_big[it] / box_n[it]:.0f} %" for it in (1, 2, 3, 5, 10, 20, 29)) +
           f"  all: {100 * box_big.sum() / box_n.sum():.1f} %;  exceeding 3 x 3: {100 * box_huge.sum() / box_n.sum():.2f} %")
+    print("WARPS (32-point source patches) with at least one lane beyond 2 x 2 rows, by iteration: " +
+          "  ".join(f"{it}: {100 * warp_big[it] / warp_n[it]:.0f} %" for it in (1, 2, 3, 5, 10, 20, 29)) +
+          f"  all: {100 * warp_big.sum() / warp_n.sum():.0f} %;  beyond 3 x 3: " +
+          "  ".join(f"{it}: {100 * warp_huge[it] / warp_n[it]:.0f} %" for it in (1, 2, 3, 5, 10, 20, 29)) +
+          f"  all: {100 * warp_huge.sum() / warp_n.sum():.0f} %")
     # dependent L2 round trips of one query: work[i], pts[j_prev], then per scanned row bounds -> points, row after row
     serial = 2 + 2 * total[2] / n
     upfront = 2 + 2  # all row bounds at once, then all point ranges
