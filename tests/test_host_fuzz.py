@@ -265,3 +265,17 @@ def test_staged_bound_only_search_along_an_icp_trajectory(hc, oracle, limit):  #
         assert ((out_idx[k][~acc] == -1) | (out_d2[k][~acc] > limit)).all(), k
         accepted_warm += int(acc.sum()) if k else 0
     assert accepted_warm > 0
+
+
+def test_staged_device_code_compiles_for_sm_100a(tmp_path):
+    """grid_nn_bounded_upfront<2 / 3> + warm_bound_d2 are templates nothing in the library instantiates yet: compile them
+    as device code so that the next round starts from something nvcc accepts (no spills expected at 48 registers)."""
+    import subprocess
+    from pathlib import Path
+
+    src = Path(__file__).resolve().parent / "host" / "staged_compile.cu"
+    r = subprocess.run(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-fmad=false",
+                        "--expt-relaxed-constexpr", "-Xptxas", "-v", "-c", str(src), "-o", str(tmp_path / "staged.o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stderr.count("0 bytes spill stores") == 2, r.stderr
