@@ -127,7 +127,7 @@ PEB_API uint64_t peb_ctx_launch_count(const peb_ctx* ctx);
  * "profile" (0 / 1 / 2, see peb_profile_read), "debug_timers" (development),
  * "warm_upfront" (experimental, default 0; 1 / 2: warm searches whose ball spans up to 2 x 2 grid rows fetch all
  * row bounds up front, 3: up to 3 x 3 — csrc/nn_upfront.cuh; exact on the CPU checks, never run or measured on
- * a GPU yet) */
+ * a GPU yet; "warm_upfront_from": the first iteration launch that uses it, default 2) */
 PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value);
 
 /* ---- pcl::VoxelGrid<PointXYZ>::filter  [PCL] filters/.../impl/voxel_grid.hpp -------- */

@@ -281,6 +281,11 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
     ctx->warm_upfront = value;
     return PEB_OK;
   }
+  if (!strcmp(key, "warm_upfront_from")) {
+    if (value < 1) return fail(ctx, PEB_E_INVALID_ARG, "warm_upfront_from must be >= 1 (launch 0 is never a warm launch)");
+    ctx->warm_upfront_from = value;
+    return PEB_OK;
+  }
   if (!strcmp(key, "profile")) {
     ctx->profile = value != 0;
     ctx->profile_level = value;

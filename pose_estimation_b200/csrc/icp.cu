@@ -727,7 +727,9 @@ int launch_one_iteration(peb_ctx* ctx, const IcpLaunch& L, size_t H, int estimat
   const bool svd = estimator == PEB_ESTIMATOR_SVD;
 #define PEB_ICP_LAUNCH(EST, MB, CERT) \
   PEB_LAUNCH_PDL(ctx, (icp_iteration_kernel<G, EST, MB, CERT, FIRST>), grid, dim3(kIcpThreads), L)
-  if (G == 1 && !FIRST && !cert && ctx->warm_upfront && L.warm) {  // experimental warm search (peb_ctx_set_int "warm_upfront")
+  // experimental warm search (peb_ctx_set_int "warm_upfront"); the first warm launches search balls of more than a cell
+  // (the first ICP step moves the points by millimetres) and keep the narrowing walk ("warm_upfront_from", default 2)
+  if (G == 1 && !FIRST && !cert && ctx->warm_upfront && L.warm && L.launch_idx >= ctx->warm_upfront_from) {
 #define PEB_ICP_LAUNCH_UPF(EST, MB, RW) \
   PEB_LAUNCH_PDL(ctx, (icp_iteration_kernel<1, EST, MB, false, false, RW>), grid, dim3(kIcpThreads), L)
     if (ctx->warm_upfront == 3) {

@@ -36,6 +36,7 @@ def _run(pcl, p, cls, normals, guesses, upfront, **params):
     c = pcl.Context(0)
     if upfront:
         c.set_int("warm_upfront", upfront)
+        c.set_int("warm_upfront_from", 1)  # every warm launch, also the first one with its large balls
     icp = cls(c)
     icp.setInputSource(p.source)
     icp.setInputTarget(p.target, normals)

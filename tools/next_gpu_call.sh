@@ -14,6 +14,8 @@ for rep in 1 2; do
   python bench.py --steps 5 --warmup 3 --no-single --no-cpu-baseline > gpurun_out/next_bench_default_$rep.json 2> gpurun_out/next_bench_default_$rep.err
   PEB_OPTS=warm_upfront=1 python bench.py --steps 5 --warmup 3 --no-single --no-cpu-baseline > gpurun_out/next_bench_upfront2x2_$rep.json 2> gpurun_out/next_bench_upfront2x2_$rep.err
   PEB_OPTS=warm_upfront=3 python bench.py --steps 5 --warmup 3 --no-single --no-cpu-baseline > gpurun_out/next_bench_upfront3x3_$rep.json 2> gpurun_out/next_bench_upfront3x3_$rep.err
+  PEB_OPTS=warm_upfront=3,warm_upfront_from=1 python bench.py --steps 5 --warmup 3 --no-single --no-cpu-baseline > gpurun_out/next_bench_upfront3x3_from1_$rep.json 2> gpurun_out/next_bench_upfront3x3_from1_$rep.err
+  PEB_OPTS=warm_upfront=3,warm_upfront_from=6 python bench.py --steps 5 --warmup 3 --no-single --no-cpu-baseline > gpurun_out/next_bench_upfront3x3_from6_$rep.json 2> gpurun_out/next_bench_upfront3x3_from6_$rep.err
 done
 python tools/bench_multi_inproc.py --devices 1,2 --same-device --reps 3 > gpurun_out/next_multi_inproc.jsonl 2> gpurun_out/next_multi_inproc.err
 python - <<'PY'
