@@ -248,8 +248,10 @@ def run_ours(args):
         log(f"[bench] warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    park = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        park = dist.new_group(backend="gloo")  # host-side barrier: ranks parked on it leave their GPU idle
     ctx = pcl.Context(local)
     for kv in filter(None, os.environ.get("PEB_OPTS", "").split(",")):  # development: library tuning knobs
         k, v = kv.split("=")
@@ -379,6 +381,19 @@ def run_ours(args):
         barrier()
         e2e_ms = max_over_ranks(e2e_ms)
 
+    # ---- the product's multi-GPU path: ONE process, peb_multi_* over all N devices ---------------------------
+    # (the reference node is a single process, launch/pose_estimation.launch.py:17-35).  Rank 0 drives every GPU
+    # of the box through one peb_multi handle while the other ranks are parked on a HOST barrier (gloo), their
+    # contexts idle; its records must equal the NCCL-gathered records of the one-rank-per-GPU legs byte for byte.
+    inproc = None
+    if not args.no_inproc:
+        ranks_records = (d_all if world > 1 else d_res).cpu().numpy().tobytes()
+        torch.cuda.synchronize()
+        if rank == 0:
+            inproc = inproc_leg(args, torch, pcl, lib, c4, guesses_cm, params, world, H, rec, ranks_records)
+        if park is not None:
+            dist.barrier(group=park)
+
     ms_per_step = total_ms / args.steps
     value = H / (ms_per_step * 1e-3)
     e2e_value = H / (e2e_ms / args.steps * 1e-3)
@@ -432,6 +447,8 @@ def run_ours(args):
         "per_rank_ms_per_step": per_rank_ms,
         "nn_queries_per_s": H * len(c4.source) * ITERATIONS / (ms_per_step * 1e-3),
     }
+    if inproc is not None:
+        line["inproc"] = inproc
 
     if rank == 0 and world == 1:
         if c2 is not None:
@@ -449,6 +466,81 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def inproc_leg(args, torch, pcl, lib, c4, guesses_cm, params, n_dev, H, rec, ranks_records):
+    """peb_multi_create(N) + peb_multi_target_set / _source_set / _icp_align_batch from HOST buffers, results on the
+    host: what the reference's single process would call.  Timed with the host clock around the blocking calls (the
+    caller's view; there is no asynchronous multi-device entry point), L2 of every device flushed before every step."""
+    from pose_estimation_b200 import multi
+
+    m = pcl.MultiContext(list(range(n_dev)))
+    for kv in filter(None, os.environ.get("PEB_OPTS", "").split(",")):
+        k, v = kv.split("=")
+        m.check(lib.peb_multi_set_int(m.handle, k.encode(), int(v)))
+    h_scene = torch.from_numpy(np.ascontiguousarray(c4.target)).pin_memory()
+    h_model = torch.from_numpy(np.ascontiguousarray(c4.source)).pin_memory()
+    h_guess = torch.from_numpy(np.ascontiguousarray(guesses_cm)).pin_memory()
+    results = (pcl.IcpResult * H)()
+    flushes = [torch.empty(256 << 20, dtype=torch.uint8, device=torch.device("cuda", d)) for d in range(n_dev)]
+
+    def flush_all():
+        for f in flushes:
+            f.zero_()
+        for d in range(n_dev):
+            torch.cuda.synchronize(d)
+
+    def setup():
+        m.check(lib.peb_multi_target_set(m.handle, h_scene.data_ptr(), h_scene.shape[0], 16, None, 0))
+        m.check(lib.peb_multi_source_set(m.handle, h_model.data_ptr(), h_model.shape[0], 16))
+
+    def align():
+        m.check(lib.peb_multi_icp_align_batch(m.handle, h_guess.data_ptr(), H, C.byref(params), results))
+
+    def timed(fn, steps):
+        total = 0.0
+        for _ in range(steps):
+            flush_all()
+            t0 = time.perf_counter()
+            fn()
+            total += time.perf_counter() - t0
+        return 1e3 * total / max(steps, 1)
+
+    setup()
+    timed(align, max(args.warmup, 1))
+    launches0 = m.launch_count
+    ms = timed(align, args.steps)
+    launches = m.launch_count - launches0
+    same = bytes(results) == multi.unpack_results(ranks_records, H, n_dev).tobytes()
+
+    def both():
+        setup()
+        align()
+
+    timed(both, max(1, min(args.warmup, 3)))
+    ms_e2e = timed(both, args.steps)
+    # the device's own view of one step: the span of the iteration launches of every device (CUDA events of the library)
+    m.check(lib.peb_multi_set_int(m.handle, b"profile", 1))
+    align()
+    spans = []
+    buf = np.zeros(4, np.float32)
+    cnt = C.c_size_t(0)
+    for d in range(n_dev):
+        lib.peb_profile_read(lib.peb_multi_ctx(m.handle, d), buf.ctypes.data, len(buf), C.byref(cnt))
+        spans.append(round(float(buf[0]), 3) if cnt.value else None)
+    m.close()
+    return {
+        "what": "ONE process, peb_multi_* over all devices (the single-process node's multi-GPU path): "
+                "peb_multi_icp_align_batch from host buffers to host records, scene + model resident",
+        "n_devices": n_dev, "value": H / (ms * 1e-3), "unit": "hypotheses/s", "ms_per_step": ms,
+        "e2e": {"value": H / (ms_e2e * 1e-3), "unit": "hypotheses/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int((h_scene.numel() + h_model.numel()) * 4 + H * 64), "d2h_bytes_per_step": int(H * rec),
+                "what": "peb_multi_target_set + peb_multi_source_set (one upload, device-to-device replicas) + "
+                        "peb_multi_icp_align_batch"},
+        "records_identical_to_ranks": bool(same), "gpu_launches": int(launches),
+        "iteration_span_ms_per_device": spans,
+        "timing": "host clock around the blocking calls, 256 MiB L2 flush of every device before every step",
+    }
 
 
 def single_align(ctx, c2, torch, stream, flush, pcl, lib):
@@ -719,6 +811,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="linear scene scale (1.0 = the 1944x1200 configuration)")
     ap.add_argument("--no-single", action="store_true", help="skip the configs[1] single-align leg")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-inproc", action="store_true", help="skip the single-process peb_multi_* leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("[bench] note: the timing rules ask for >= 3 warm-up steps")

@@ -114,7 +114,9 @@ PEB_API void* peb_ctx_stream(peb_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches claim) */
 PEB_API uint64_t peb_ctx_launch_count(const peb_ctx* ctx);
 /* tuning knobs that change speed, never results (tests/test_gpu_parity.py asserts bit-identical records for
- * every one of them): "nn_group" (lanes per COLD nearest-neighbour query: 1, 2, 4, 8, 16),
+ * every one of them; the exception are the block-count knobs "blocks_factor" / "blocks_factor_cold" — and "nn_group" in
+ * a batch, which changes launch 0's block count —: they change the ORDER in which the per-block partial sums of the
+ * double moments are added, i.e. at most their last bits): "nn_group" (lanes per COLD nearest-neighbour query: 1, 2, 4, 8, 16),
  * "grid_occupancy_x100" (wanted points per occupied target-grid cell x 100, default 350; takes effect at
  * the next peb_target_set), "source_sort_occupancy" (points per cell of the source's own sort grid = patch
  * compactness, default 32), "warm_start" (iterations >= 1 seed their search with the previous match),
@@ -125,9 +127,10 @@ PEB_API uint64_t peb_ctx_launch_count(const peb_ctx* ctx);
  * "flag_deps" (warm launches of a batch wait per hypothesis instead of for the whole previous grid),
  * "pdl" (programmatic dependent launch), "cert_margin_x1000" (search-skipping certificates, off),
  * "profile" (0 / 1 / 2, see peb_profile_read), "debug_timers" (development),
- * "warm_upfront" (experimental, default 0; 1 / 2: warm searches whose ball spans up to 2 x 2 grid rows fetch all
- * row bounds up front, 3: up to 3 x 3 — csrc/nn_upfront.cuh; exact on the CPU checks, never run or measured on
- * a GPU yet; "warm_upfront_from": the first iteration launch that uses it, default 2) */
+ * "warm_upfront" (default 0; 1 / 2: warm searches whose ball spans up to 2 x 2 grid rows fetch all row bounds up
+ * front, 3: up to 3 x 3 — csrc/nn_upfront.cuh; bit-identical results, measured SLOWER on B200 (C4: -4 % and -19 %,
+ * profiles/README.md round 2) and kept only as a recorded experiment; "warm_upfront_from": the first iteration
+ * launch that uses it, default 2) */
 PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value);
 
 /* ---- pcl::VoxelGrid<PointXYZ>::filter  [PCL] filters/.../impl/voxel_grid.hpp -------- */
@@ -199,7 +202,10 @@ PEB_API int peb_sac_plane_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, const 
  * called one after the other, but the cloud crosses PCIe once in each direction instead of seven times.
  * filter: use_sphere / remove_inliers / sphere_* / plane_band are read, its planes are ignored.
  * out_planes (nullable): num_planes x 4 coefficients; a plane that could not be estimated is all zeros and
- * removes nothing (the reference prints an error and goes on). */
+ * removes nothing.  DELIBERATE DEVIATION: the reference's remove_planes applies its band test unconditionally
+ * (pose_estimation.cpp:313-333) — after a failed segment() PCL leaves `coefficients->values` EMPTY, so the
+ * reference indexes an empty vector there (undefined behaviour, there is nothing to reproduce); this library keeps
+ * every point of such a pass (tests/test_sac.py::test_scene_prepare_keeps_everything_when_no_plane_is_found). */
 PEB_API int peb_scene_prepare(peb_ctx* ctx, const void* pts, size_t n, size_t stride, const peb_prefilter_params* filter,
                               int num_planes, const peb_sac_params* sac, float leaf, float* out_xyz4, size_t* out_n,
                               float* out_planes);
@@ -248,6 +254,22 @@ PEB_API int peb_nn_search_bruteforce(peb_ctx* ctx, const void* queries, size_t n
 PEB_API int peb_target_set(peb_ctx* ctx, const void* pts, size_t n, size_t stride,
                            const void* normals, size_t nstride);
 PEB_API int peb_source_set(peb_ctx* ctx, const void* pts, size_t n, size_t stride);
+/* The two halves of peb_target_set / peb_source_set, and the replica of another context's cloud — the building
+ * blocks of peb_multi_target_set / peb_multi_source_set (one host-to-device copy per box, not per device):
+ *   *_stage  uploads the caller's records into the context (asynchronous; nothing is searchable yet),
+ *   *_build  builds the search grid over the staged cloud (peb_target_set = stage + build),
+ *   *_clone  copies src's STAGED cloud device to device into dst (cudaMemcpyPeerAsync, ordered after src's staging by
+ *            an event: NVLink / NVSwitch between peers, through the host otherwise) and builds dst's grid — the build
+ *            is deterministic, so the replica is identical to src's.  dst and src may live on the same device.
+ * peb_ctx_enable_peer: direct peer access from ctx's device to peer's (PEB_E_UNSUPPORTED if the hardware has none —
+ * the clones then still work, staged by the driver). */
+PEB_API int peb_target_stage(peb_ctx* ctx, const void* pts, size_t n, size_t stride, const void* normals, size_t nstride);
+PEB_API int peb_target_build(peb_ctx* ctx);
+PEB_API int peb_target_clone(peb_ctx* dst, peb_ctx* src);
+PEB_API int peb_source_stage(peb_ctx* ctx, const void* pts, size_t n, size_t stride);
+PEB_API int peb_source_build(peb_ctx* ctx);
+PEB_API int peb_source_clone(peb_ctx* dst, peb_ctx* src);
+PEB_API int peb_ctx_enable_peer(peb_ctx* ctx, const peb_ctx* peer);
 
 /* ---- pcl::IterativeClosestPoint::align(output, guess) ------------------------------ */
 /* guess: column-major 4x4 (NULL = identity).  Optional outputs (nullable):
@@ -277,8 +299,14 @@ PEB_API int peb_fitness_score(peb_ctx* ctx, const float T[16], double max_range,
  * Hypotheses are independent: no collective; each device copies its records into `results`.
  * devices: ndev CUDA device indices (NULL = 0 .. ndev-1).  An index may repeat — the contexts are
  * independent, which is how the single-GPU tests exercise the sharding.  Calls on one peb_multi
- * must be serialised by the caller, like calls on one peb_ctx.  Results are identical to
- * peb_icp_align_batch on one device, record for record. */
+ * must be serialised by the caller, like calls on one peb_ctx.  One persistent host thread per extra
+ * device is parked between calls.  The scene and the model are uploaded once (device 0) and replicated
+ * device to device (peb_target_clone).
+ * Results: every hypothesis is refined exactly as by peb_icp_align_batch on one device given the same
+ * block of hypotheses (byte-identical records; it is also what one rank of the one-process-per-GPU path
+ * computes).  Against ONE context refining all H hypotheses the records can differ in the last bits of the
+ * double moment sums: the number of blocks per hypothesis (hence the order in which the per-block partial
+ * sums are added) is chosen from the batch size. */
 typedef struct peb_multi peb_multi;
 PEB_API int peb_multi_create(int ndev, const int* devices, peb_multi** out);
 PEB_API void peb_multi_destroy(peb_multi* m);
@@ -291,7 +319,7 @@ PEB_API peb_ctx* peb_multi_ctx(peb_multi* m, int i);
 PEB_API int peb_multi_set_int(peb_multi* m, const char* key, int value);
 /* [lo, hi) of the n_items hypotheses device i of ndev refines: blocks of ceil(n_items / ndev) */
 PEB_API void peb_multi_shard_range(size_t n_items, int ndev, int i, size_t* lo, size_t* hi);
-/* peb_target_set / peb_source_set on every device (same host buffers, concurrently) */
+/* peb_target_set / peb_source_set for every device: staged once on device 0, cloned to the others, built everywhere */
 PEB_API int peb_multi_target_set(peb_multi* m, const void* pts, size_t n, size_t stride,
                                  const void* normals, size_t nstride);
 PEB_API int peb_multi_source_set(peb_multi* m, const void* pts, size_t n, size_t stride);
@@ -314,6 +342,9 @@ PEB_API int peb_voxel_grid_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, float
                                float leaf_z, unsigned min_pts, void* d_out_xyz4, size_t* out_n);
 PEB_API int peb_normals_knn_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, int k,
                                 const float viewpoint[3], void* d_out_normal8);
+/* waits for everything queued on the context.  PEB_E_CUDA if the last batched align raised its internal-error flag
+ * (PEB_STATE_INTERNAL_ERROR): the asynchronous peb_icp_align_batch_dev cannot report it when it returns, and a
+ * record written before another hypothesis hit the bound does not carry it. */
 PEB_API int peb_sync(peb_ctx* ctx);
 
 /* ---- introspection used by the parity tests ---------------------------------------- */
@@ -327,8 +358,9 @@ typedef struct peb_grid_info {
 PEB_API int peb_target_grid_info(peb_ctx* ctx, peb_grid_info* out);
 /* with peb_ctx_set_int(ctx, "profile", 2): device time (ms, CUDA events on the context's stream)
  * of every ICP kernel launch of the last align — the iteration launches, then the fitness launch.
- * With "profile" = 1: ONE value, the span from the first to the last iteration launch (no events
- * between the launches, so their overlap is not disturbed). */
+ * With "profile" = 1: ONE value, the span from the first to the end of the last ITERATION launch (no events
+ * between the iteration launches, so their overlap is not disturbed; the fitness launch is outside the span;
+ * a batch that runs as several chains of launches reports its slowest chain). */
 PEB_API int peb_profile_read(peb_ctx* ctx, float* out_ms, size_t cap, size_t* out_n);
 /* per-iteration increments of the last peb_icp_align (column-major 4x4 each);
  * copies min(cap, iterations) matrices, returns the count via *out_n */

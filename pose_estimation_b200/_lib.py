@@ -140,6 +140,13 @@ SYMBOLS = {
     "peb_nn_search_bruteforce": (_i, [_vp, _vp, _sz, _sz, _vp, _vp]),
     "peb_target_set": (_i, [_vp, _vp, _sz, _sz, _vp, _sz]),
     "peb_source_set": (_i, [_vp, _vp, _sz, _sz]),
+    "peb_target_stage": (_i, [_vp, _vp, _sz, _sz, _vp, _sz]),
+    "peb_target_build": (_i, [_vp]),
+    "peb_target_clone": (_i, [_vp, _vp]),
+    "peb_source_stage": (_i, [_vp, _vp, _sz, _sz]),
+    "peb_source_build": (_i, [_vp]),
+    "peb_source_clone": (_i, [_vp, _vp]),
+    "peb_ctx_enable_peer": (_i, [_vp, _vp]),
     "peb_icp_align": (_i, [_vp, _vp, _pp(IcpParams), _pp(IcpResult), _vp, _vp, _vp]),
     "peb_icp_align_batch": (_i, [_vp, _vp, _sz, _pp(IcpParams), _vp]),
     "peb_fitness_score": (_i, [_vp, _vp, _d, _pp(_d), _pp(C.c_int32)]),

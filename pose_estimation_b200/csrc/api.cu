@@ -83,6 +83,13 @@ int source_finish(peb_ctx* ctx, size_t n) {
   return PEB_OK;
 }
 
+// records (creating it on first use) the event that orders a replica's copy after this context's staging
+int mark_staged(peb_ctx* ctx, cudaEvent_t* ev) {
+  if (!*ev) PEB_CUDA(ctx, cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+  PEB_CUDA(ctx, cudaEventRecord(*ev, ctx->stream));
+  return PEB_OK;
+}
+
 int upload_guesses(peb_ctx* ctx, const float* guesses, size_t H, const float** d_out) {
   *d_out = nullptr;
   if (!guesses) return PEB_OK;
@@ -197,6 +204,8 @@ PEB_API void peb_ctx_destroy(peb_ctx* ctx) {
   for (cudaEvent_t e : ctx->join_events) cudaEventDestroy(e);
   for (cudaStream_t st : ctx->sub_streams) cudaStreamDestroy(st);
   if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
+  if (ctx->tgt_stage_event) cudaEventDestroy(ctx->tgt_stage_event);
+  if (ctx->src_stage_event) cudaEventDestroy(ctx->src_stage_event);
   ctx->h_stage.release();
   ctx->h_small.release();
   ctx->h_sac.release();
@@ -233,6 +242,7 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
     return PEB_OK;
   }
   if (!strcmp(key, "seed_guard_x10")) {
+    if (value < 0 || value > 100000) return fail(ctx, PEB_E_INVALID_ARG, "seed_guard_x10 out of [0, 100000]");
     ctx->seed_guard = value / 10.0f;
     return PEB_OK;
   }
@@ -287,6 +297,7 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
     return PEB_OK;
   }
   if (!strcmp(key, "profile")) {
+    if (value < 0 || value > 2) return fail(ctx, PEB_E_INVALID_ARG, "profile must be 0, 1 or 2");
     ctx->profile = value != 0;
     ctx->profile_level = value;
     ctx->prof_launches = 0;
@@ -295,10 +306,20 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
   return fail(ctx, PEB_E_INVALID_ARG, "unknown option '%s'", key);
 }
 
+// Waits for everything queued on the context; PEB_E_CUDA if the last batched align raised its internal-error flag
+// (the asynchronous *_dev entry points cannot report it when they return).
 PEB_API int peb_sync(peb_ctx* ctx) {
   if (!ctx) return PEB_E_INVALID_ARG;
   DeviceGuard guard(ctx->device);
-  return sync(ctx);
+  int* h_flag = ctx->h_small.as<int>() + 64;
+  *h_flag = 0;
+  if (ctx->last_err_flag)
+    PEB_CUDA(ctx, cudaMemcpyAsync(h_flag, ctx->last_err_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PEB_TRY(sync(ctx));
+  if (*h_flag != 0)
+    return fail(ctx, PEB_E_CUDA, "a per-hypothesis dependency wait of the last batched align ran into its bound (internal "
+                                 "error; peb_ctx_set_int(ctx, \"flag_deps\", 0) restores whole-grid dependencies)");
+  return PEB_OK;
 }
 
 // ---- VoxelGrid ---------------------------------------------------------------------------------
@@ -508,10 +529,11 @@ PEB_API int peb_normals_knn(peb_ctx* ctx, const void* pts, size_t n, size_t stri
 }
 
 // ---- target / source -----------------------------------------------------------------------------
-PEB_API int peb_target_set(peb_ctx* ctx, const void* pts, size_t n, size_t stride, const void* normals, size_t nstride) {
+PEB_API int peb_target_stage(peb_ctx* ctx, const void* pts, size_t n, size_t stride, const void* normals, size_t nstride) {
   if (!ctx) return PEB_E_INVALID_ARG;
   DeviceGuard guard(ctx->device);
   ctx->tgt_grid.valid = false;
+  ctx->tgt_staged = false;
   PEB_TRY(check_cloud(ctx, "target_set", pts, n, stride));
   if (normals) PEB_TRY(check_cloud(ctx, "target_set(normals)", normals, n, nstride));
   PEB_CUDA(ctx, ctx->tgt_raw.ensure(n * sizeof(float4)));
@@ -520,13 +542,54 @@ PEB_API int peb_target_set(peb_ctx* ctx, const void* pts, size_t n, size_t strid
     PEB_CUDA(ctx, ctx->tgt_nrm_raw.ensure(n * sizeof(float4)));
     PEB_TRY(upload_cloud(ctx, normals, n, nstride, 0.0f, ctx->tgt_nrm_raw.as<float4>()));
   }
-  return target_finish(ctx, n, normals != nullptr);
+  ctx->n_tgt = n;
+  ctx->tgt_has_normals = normals != nullptr;
+  PEB_TRY(mark_staged(ctx, &ctx->tgt_stage_event));
+  ctx->tgt_staged = true;
+  return PEB_OK;
+}
+
+PEB_API int peb_target_build(peb_ctx* ctx) {
+  if (!ctx) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  if (!ctx->tgt_staged) return fail(ctx, PEB_E_NO_TARGET, "target_build: no staged target (peb_target_stage / peb_target_clone)");
+  return target_finish(ctx, ctx->n_tgt, ctx->tgt_has_normals);
+}
+
+PEB_API int peb_target_set(peb_ctx* ctx, const void* pts, size_t n, size_t stride, const void* normals, size_t nstride) {
+  const int rc = peb_target_stage(ctx, pts, n, stride, normals, nstride);
+  return rc != PEB_OK ? rc : peb_target_build(ctx);
+}
+
+// dst's target becomes a replica of src's staged cloud: device-to-device (NVLink between peers), ordered after
+// src's staging by an event, then the same deterministic grid build => the replicas are identical
+PEB_API int peb_target_clone(peb_ctx* dst, peb_ctx* src) {
+  if (!dst || !src) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(dst->device);
+  dst->tgt_grid.valid = false;
+  dst->tgt_staged = false;
+  if (!src->tgt_staged) return fail(dst, PEB_E_NO_TARGET, "target_clone: the source context has no staged target");
+  if (dst == src) return peb_target_build(dst);
+  const size_t n = src->n_tgt;
+  PEB_CUDA(dst, dst->tgt_raw.ensure(n * sizeof(float4)));
+  PEB_CUDA(dst, cudaStreamWaitEvent(dst->stream, src->tgt_stage_event, 0));
+  if (n) PEB_CUDA(dst, cudaMemcpyPeerAsync(dst->tgt_raw.p, dst->device, src->tgt_raw.p, src->device, n * sizeof(float4), dst->stream));
+  if (src->tgt_has_normals) {
+    PEB_CUDA(dst, dst->tgt_nrm_raw.ensure(n * sizeof(float4)));
+    if (n) PEB_CUDA(dst, cudaMemcpyPeerAsync(dst->tgt_nrm_raw.p, dst->device, src->tgt_nrm_raw.p, src->device, n * sizeof(float4), dst->stream));
+  }
+  dst->n_tgt = n;
+  dst->tgt_has_normals = src->tgt_has_normals;
+  PEB_TRY(mark_staged(dst, &dst->tgt_stage_event));
+  dst->tgt_staged = true;
+  return target_finish(dst, n, dst->tgt_has_normals);
 }
 
 PEB_API int peb_target_set_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, const void* d_normal4) {
   if (!ctx) return PEB_E_INVALID_ARG;
   DeviceGuard guard(ctx->device);
   ctx->tgt_grid.valid = false;
+  ctx->tgt_staged = false;
   if (n > 0 && !d_xyz4) return fail(ctx, PEB_E_INVALID_ARG, "target_set_dev: null device pointer");
   if (n > static_cast<size_t>(INT32_MAX) / 2) return fail(ctx, PEB_E_INVALID_ARG, "target_set: too many points");
   PEB_CUDA(ctx, ctx->tgt_raw.ensure(n * sizeof(float4)));
@@ -535,27 +598,83 @@ PEB_API int peb_target_set_dev(peb_ctx* ctx, const void* d_xyz4, size_t n, const
     PEB_CUDA(ctx, ctx->tgt_nrm_raw.ensure(n * sizeof(float4)));
     if (n) PEB_CUDA(ctx, cudaMemcpyAsync(ctx->tgt_nrm_raw.p, d_normal4, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
   }
+  ctx->n_tgt = n;
+  ctx->tgt_has_normals = d_normal4 != nullptr;
+  PEB_TRY(mark_staged(ctx, &ctx->tgt_stage_event));
+  ctx->tgt_staged = true;
   return target_finish(ctx, n, d_normal4 != nullptr);
 }
 
-PEB_API int peb_source_set(peb_ctx* ctx, const void* pts, size_t n, size_t stride) {
+PEB_API int peb_source_stage(peb_ctx* ctx, const void* pts, size_t n, size_t stride) {
   if (!ctx) return PEB_E_INVALID_ARG;
   DeviceGuard guard(ctx->device);
   ctx->src_set = false;
+  ctx->src_staged = false;
   PEB_TRY(check_cloud(ctx, "source_set", pts, n, stride));
   PEB_CUDA(ctx, ctx->src.ensure(n * sizeof(float4)));
   PEB_TRY(upload_cloud(ctx, pts, n, stride, 1.0f, ctx->src.as<float4>()));
-  return source_finish(ctx, n);
+  ctx->n_src = n;
+  PEB_TRY(mark_staged(ctx, &ctx->src_stage_event));
+  ctx->src_staged = true;
+  return PEB_OK;
+}
+
+PEB_API int peb_source_build(peb_ctx* ctx) {
+  if (!ctx) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  if (!ctx->src_staged) return fail(ctx, PEB_E_NO_SOURCE, "source_build: no staged source (peb_source_stage / peb_source_clone)");
+  return source_finish(ctx, ctx->n_src);
+}
+
+PEB_API int peb_source_set(peb_ctx* ctx, const void* pts, size_t n, size_t stride) {
+  const int rc = peb_source_stage(ctx, pts, n, stride);
+  return rc != PEB_OK ? rc : peb_source_build(ctx);
+}
+
+PEB_API int peb_source_clone(peb_ctx* dst, peb_ctx* src) {
+  if (!dst || !src) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(dst->device);
+  dst->src_set = false;
+  dst->src_staged = false;
+  if (!src->src_staged) return fail(dst, PEB_E_NO_SOURCE, "source_clone: the source context has no staged source");
+  if (dst == src) return peb_source_build(dst);
+  const size_t n = src->n_src;
+  PEB_CUDA(dst, dst->src.ensure(n * sizeof(float4)));
+  PEB_CUDA(dst, cudaStreamWaitEvent(dst->stream, src->src_stage_event, 0));
+  if (n) PEB_CUDA(dst, cudaMemcpyPeerAsync(dst->src.p, dst->device, src->src.p, src->device, n * sizeof(float4), dst->stream));
+  dst->n_src = n;
+  PEB_TRY(mark_staged(dst, &dst->src_stage_event));
+  dst->src_staged = true;
+  return source_finish(dst, n);
+}
+
+// direct loads / copies between the two devices where the hardware allows it (NVLink / NVSwitch on a B200 box);
+// without it cudaMemcpyPeerAsync stages through the host and still works
+PEB_API int peb_ctx_enable_peer(peb_ctx* ctx, const peb_ctx* peer) {
+  if (!ctx || !peer) return PEB_E_INVALID_ARG;
+  if (ctx->device == peer->device) return PEB_OK;
+  DeviceGuard guard(ctx->device);
+  int can = 0;
+  if (cudaDeviceCanAccessPeer(&can, ctx->device, peer->device) == cudaSuccess && can) {
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+  }
+  cudaGetLastError();
+  return can ? PEB_OK : PEB_E_UNSUPPORTED;
 }
 
 PEB_API int peb_source_set_dev(peb_ctx* ctx, const void* d_xyz4, size_t n) {
   if (!ctx) return PEB_E_INVALID_ARG;
   DeviceGuard guard(ctx->device);
   ctx->src_set = false;
+  ctx->src_staged = false;
   if (n > 0 && !d_xyz4) return fail(ctx, PEB_E_INVALID_ARG, "source_set_dev: null device pointer");
   if (n > static_cast<size_t>(INT32_MAX) / 2) return fail(ctx, PEB_E_INVALID_ARG, "source_set: too many points");
   PEB_CUDA(ctx, ctx->src.ensure(n * sizeof(float4)));
   if (n) PEB_CUDA(ctx, cudaMemcpyAsync(ctx->src.p, d_xyz4, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  ctx->n_src = n;
+  PEB_TRY(mark_staged(ctx, &ctx->src_stage_event));
+  ctx->src_staged = true;
   return source_finish(ctx, n);
 }
 
@@ -643,8 +762,14 @@ static int icp_align_batch_impl(peb_ctx* ctx, const float* guesses, size_t n_gue
   PEB_TRY(icp_align_device(ctx, d_g, n_guesses, params, ctx->d_results.as<peb_icp_result>(), false));
   PEB_CUDA(ctx, cudaMemcpyAsync(results, ctx->d_results.p, n_guesses * sizeof(peb_icp_result), cudaMemcpyDeviceToHost,
                                 ctx->stream));
+  // the error flag of the dependency waits is read AFTER every launch of the align has finished: a record written
+  // before another hypothesis hit its bound does not carry the error
+  int* h_flag = ctx->h_small.as<int>() + 64;
+  *h_flag = 0;
+  if (ctx->last_err_flag)
+    PEB_CUDA(ctx, cudaMemcpyAsync(h_flag, ctx->last_err_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   PEB_TRY(sync(ctx));
-  if (results[0].state == PEB_STATE_INTERNAL_ERROR)
+  if (*h_flag != 0 || results[0].state == PEB_STATE_INTERNAL_ERROR)
     return fail(ctx, PEB_E_CUDA, "align_batch: a per-hypothesis dependency wait ran into its bound (internal error; "
                                  "peb_ctx_set_int(ctx, \"flag_deps\", 0) restores whole-grid dependencies)");
   return PEB_OK;
@@ -689,6 +814,16 @@ PEB_API int peb_profile_read(peb_ctx* ctx, float* out_ms, size_t cap, size_t* ou
   size_t cnt = static_cast<size_t>(ctx->prof_launches);
   if (cnt > cap) cnt = cap;
   *out_n = cnt;
+  if (ctx->prof_chain_ends > 0 && cnt == 1 && out_ms) {  // chains: the slowest chain's iteration launches
+    float span = 0.0f;
+    for (int c = 0; c < ctx->prof_chain_ends; ++c) {
+      float ms = 0.0f;
+      PEB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->prof_events[0], ctx->prof_events[2 + c]));
+      span = std::max(span, ms);
+    }
+    out_ms[0] = span;
+    return PEB_OK;
+  }
   for (size_t i = 0; i < cnt && out_ms; ++i)
     PEB_CUDA(ctx, cudaEventElapsedTime(&out_ms[i], ctx->prof_events[2 * i], ctx->prof_events[2 * i + 1]));
   return PEB_OK;

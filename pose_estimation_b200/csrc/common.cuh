@@ -116,6 +116,7 @@ struct peb_ctx {
   int blocks_factor_cold = 0;   // the same for launch 0 of a batched align; 0 = like blocks_factor
   bool flag_deps = true;        // warm launches wait per hypothesis (epoch flags) instead of for the whole previous grid
   peb::DevBuf epochs;           // H solved-iteration counters + 1 error flag
+  int* last_err_flag = nullptr; // device address of that flag for the last batched align (nullptr: whole-grid dependencies)
   bool use_pdl = true;          // programmatic dependent launch between the ICP launches of an align
   bool debug_timers = false;    // development: %globaltimer stamps of the phases of every iteration launch
   peb::DevBuf dbg;
@@ -139,12 +140,16 @@ struct peb_ctx {
   peb::DevBuf tgt_nrm_raw;   // float4 normals in original order (if any)
   size_t n_tgt = 0;
   bool tgt_has_normals = false;
+  bool tgt_staged = false;            // tgt_raw (+ normals) holds a cloud; tgt_stage_event orders a replica's copy after it
+  cudaEvent_t tgt_stage_event = nullptr;
   peb::Grid tgt_grid;
 
   // source (model)
   peb::DevBuf src;           // float4 xyz1, original order
   size_t n_src = 0;
   bool src_set = false;
+  bool src_staged = false;
+  cudaEvent_t src_stage_event = nullptr;
   // the finite source points sorted by the cells of a coarse grid over the source itself
   // (~32 points per cell = one warp per compact patch): neighbouring threads get neighbouring
   // queries, i.e. the same grid rows, the same ring counts and L1 hits.  .w = original index.
@@ -169,6 +174,7 @@ struct peb_ctx {
   int prof_launches = 0;
   int profile_level = 0;        // 1: one event pair around all iteration launches, 2: one per launch
   int prof_span_launches = 0;
+  int prof_chain_ends = 0;      // > 0: the last align ran as this many chains; events 2 .. 2 + chains - 1 end their iteration launches
   peb::DevBuf nn_q, nn_idx, nn_d2;   // peb_nn_search staging
 
   // voxel grid / normals scratch

@@ -51,7 +51,9 @@ struct IcpLaunch {
   unsigned long long* dbg;  // nullable: 8 timestamps (ns, %globaltimer) per launch, written by the last block
   int launch_idx;
   IcpState* states;      // H
-  double* partials;      // H x blocks_per_hyp x kAccMax
+  double* partials;      // H x part_stride x kAccMax
+  int part_stride;       // block records per hypothesis: the same for every launch of an align (the cold and the warm
+                         // launches may use different blocks_per_hyp, and chains / launch dependencies let them overlap)
   int32_t* corr_idx;     // nullable, indexed by ORIGINAL source index (single align only)
   float* corr_d2;        // nullable
   Mat4* trace;           // nullable, trace_cap increments (single align only)
@@ -510,7 +512,7 @@ __device__ __forceinline__ void icp_iteration_body(const IcpLaunch& L, const int
 
   if (L.dbg) t_dbg[1] = global_ns();
   const double r = block_reduce_acc<NACC>(acc, sm);
-  double* part = L.partials + (static_cast<size_t>(h) * L.blocks_per_hyp) * kAccMax;
+  double* part = L.partials + (static_cast<size_t>(h) * L.part_stride) * kAccMax;
   if (threadIdx.x < NACC) __stcg(part + static_cast<size_t>(blk) * kAccMax + threadIdx.x, r);
   __threadfence();
   __syncthreads();
@@ -627,7 +629,7 @@ __global__ void __launch_bounds__(kIcpThreads) icp_fitness_kernel(const IcpLaunc
     }
   }
   const double r = block_reduce_acc<2>(acc, sm);
-  double* part = L.partials + (static_cast<size_t>(h) * L.blocks_per_hyp) * kAccMax;
+  double* part = L.partials + (static_cast<size_t>(h) * L.part_stride) * kAccMax;
   if (threadIdx.x < 2) __stcg(part + static_cast<size_t>(blockIdx.x) * kAccMax + threadIdx.x, r);
   __threadfence();
   __syncthreads();
@@ -819,6 +821,7 @@ int prepare_launch(peb_ctx* ctx, size_t H, const peb_icp_params* prm, IcpLaunch&
   L.margin = ctx->cert_margin * L.grid.h;
   L.states = ctx->state.as<IcpState>();
   L.partials = ctx->partials.as<double>();
+  L.part_stride = max_bph;
   L.crit.max_iterations = prm->max_iterations;
   L.crit.min_correspondences = prm->min_correspondences;
   L.crit.max_similar = prm->max_iterations_similar;
@@ -894,10 +897,12 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
   //  one thread everybody waits for — measured 0.74 -> 0.78 ms on C2)
   const bool flag_deps = ctx->flag_deps && ctx->use_pdl && !per_launch && !ctx->debug_timers && !single_mode && H >= 16 &&
                          launches < kEpochStopped;
+  ctx->last_err_flag = nullptr;
   if (flag_deps) {
     PEB_CUDA(ctx, ctx->epochs.ensure((H + 1) * sizeof(int)));
     L.epochs = ctx->epochs.as<int>();
     L.err_flag = L.epochs + H;
+    ctx->last_err_flag = L.err_flag;
   }
   PEB_LAUNCH(ctx, icp_init_kernel, ceil_div(static_cast<long long>(H + 1), 128), 128, 0, L.states, d_guesses,
              static_cast<int>(H), L.epochs);
@@ -920,6 +925,7 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
   Lw.blocks_per_hyp = blocks_for(n, H, g_warm, ctx->blocks_factor);
   Lw.warm = ctx->warm_start ? 1 : 0;
   ctx->prof_launches = 0;
+  ctx->prof_chain_ends = 0;
   if (ctx->debug_timers) {
     PEB_CUDA(ctx, ctx->dbg.ensure(static_cast<size_t>(launches) * 8 * sizeof(unsigned long long)));
     PEB_CUDA(ctx, cudaMemsetAsync(ctx->dbg.p, 0, static_cast<size_t>(launches) * 8 * sizeof(unsigned long long), ctx->stream));
@@ -959,7 +965,7 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
       C.states += h0;
       C.work += h0 * static_cast<size_t>(n);
       C.slack += h0 * static_cast<size_t>(n);
-      C.partials += h0 * static_cast<size_t>(base.blocks_per_hyp) * kAccMax;
+      C.partials += h0 * static_cast<size_t>(base.part_stride) * kAccMax;
       C.results += h0;
       if (C.anchors) C.anchors += h0 * static_cast<size_t>(C.n_anchor);
       if (C.epochs) C.epochs += h0;
@@ -978,16 +984,19 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
         } else if (it < launches) {
           PEB_TRY(launch_one_iteration_g(ctx, g_warm, false, chunk_of(Lw, h0), h1 - h0, prm->estimator));
         } else {
+          // profile 1: the span ends with the last ITERATION launch of the slowest chain, as in the single-chain path
+          // (peb_profile_read takes the maximum over the chains)
+          PEB_TRY(prof_mark(ctx, 2 + c));
           PEB_TRY(launch_fitness_g(ctx, g_warm, chunk_of(Lw, h0), h1 - h0));
           PEB_CUDA(ctx, cudaEventRecord(ctx->join_events[c], ctx->stream));
         }
       }
     }
     for (int c = 0; c < S; ++c) PEB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->join_events[c], 0));
-    PEB_TRY(prof_mark(ctx, 1));
     if (ctx->profile) {
-      ctx->prof_launches = 1;  // one record: the span of all chains (iterations + fitness)
+      ctx->prof_launches = 1;  // one record: from the fork to the end of the last iteration launch of the slowest chain
       ctx->prof_span_launches = launches;
+      ctx->prof_chain_ends = static_cast<int>(std::min<size_t>(S, (H + per - 1) / per));  // chains that hold hypotheses
     }
     return PEB_OK;
   }

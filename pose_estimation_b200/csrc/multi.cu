@@ -8,16 +8,95 @@
 // independent: no collective; every device copies its block of result records straight into the
 // caller's `results` array.
 //
-// Host code only (no kernel of its own): one short-lived host thread per extra device drives the
-// blocking single-device entry points of api.cu, so every device runs the tested path unchanged.
+// Host code only (no kernel of its own):
+//   * one PERSISTENT host thread per extra device (created with the handle, parked on a condition variable between
+//     calls) drives the blocking single-device entry points of api.cu, so every device runs the tested path unchanged
+//     and a call costs two wake-ups instead of thread creation;
+//   * the scene and the model cross PCIe ONCE: device 0 stages the caller's host buffer (peb_target_stage), every other
+//     device copies the staged cloud device-to-device (peb_target_clone: NVLink / NVSwitch between peers) while
+//     device 0 already builds its grid; every device then runs the same deterministic grid build on the same bytes,
+//     so the replicas are identical.
 #include <algorithm>
+#include <condition_variable>
 #include <exception>
+#include <functional>
+#include <mutex>
 #include <thread>
 
 #include "common.cuh"
 
+namespace {
+
+// One parked host thread per extra device.  post() hands it a job, wait() collects the job's status.
+class Worker {
+ public:
+  Worker() : thread_([this]() { run(); }) {}
+  ~Worker() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      quit_ = true;
+    }
+    cv_.notify_all();
+    if (thread_.joinable()) thread_.join();
+  }
+  Worker(const Worker&) = delete;
+  Worker& operator=(const Worker&) = delete;
+
+  void post(const std::function<int()>* job) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      job_ = job;
+      done_ = false;
+    }
+    cv_.notify_all();
+  }
+  int wait() {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [this]() { return done_; });
+    return rc_;
+  }
+
+ private:
+  void run() {
+    for (;;) {
+      const std::function<int()>* job = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [this]() { return quit_ || job_ != nullptr; });
+        if (quit_) return;
+        job = job_;
+        job_ = nullptr;
+      }
+      int rc = PEB_E_CUDA;
+      try {
+        rc = (*job)();
+      } catch (const std::bad_alloc&) {
+        rc = PEB_E_OOM;
+      } catch (...) {
+      }
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        rc_ = rc;
+        done_ = true;
+      }
+      cv_.notify_all();
+    }
+  }
+
+  std::mutex mu_;
+  std::condition_variable cv_;
+  const std::function<int()>* job_ = nullptr;
+  bool done_ = true;
+  bool quit_ = false;
+  int rc_ = PEB_OK;
+  std::thread thread_;  // last: starts when everything above exists
+};
+
+}  // namespace
+
 struct peb_multi {
   std::vector<peb_ctx*> ctx;
+  std::vector<Worker*> workers;  // workers[i - 1] drives ctx[i]; ctx[0] runs on the calling thread
   std::string err;
 };
 
@@ -36,20 +115,21 @@ int on_all_devices(peb_multi* m, const char* what, Fn fn) {
   const size_t n = m->ctx.size();
   std::vector<int> rc(n, PEB_OK);
   try {
-    std::vector<std::thread> workers;
-    workers.reserve(n);
+    std::vector<std::function<int()>> jobs;
+    jobs.reserve(n);
+    for (size_t i = 0; i < n; ++i) jobs.emplace_back([&fn, i]() { return fn(i); });
+    for (size_t i = 1; i < n; ++i) m->workers[i - 1]->post(&jobs[i]);
     try {
-      for (size_t i = 1; i < n; ++i) workers.emplace_back([&rc, &fn, i]() { rc[i] = fn(i); });
+      rc[0] = jobs[0]();
     } catch (...) {
-      for (std::thread& t : workers) t.join();
+      for (size_t i = 1; i < n; ++i) m->workers[i - 1]->wait();  // the jobs reference this frame
       throw;
     }
-    rc[0] = fn(0);
-    for (std::thread& t : workers) t.join();
+    for (size_t i = 1; i < n; ++i) rc[i] = m->workers[i - 1]->wait();
   } catch (const std::exception& e) {
     return multi_fail(m, PEB_E_OOM, std::string(what) + ": " + e.what());
   } catch (...) {
-    return multi_fail(m, PEB_E_OOM, std::string(what) + ": could not start the per-device host threads");
+    return multi_fail(m, PEB_E_OOM, std::string(what) + ": host-side failure");
   }
   for (size_t i = 0; i < n; ++i)
     if (rc[i] != PEB_OK)
@@ -73,6 +153,7 @@ PEB_API int peb_multi_create(int ndev, const int* devices, peb_multi** out) {
   try {
     m = new peb_multi();
     m->ctx.reserve(static_cast<size_t>(ndev));
+    m->workers.reserve(static_cast<size_t>(ndev));
   } catch (...) {
     delete m;
     g_multi_create_error = "peb_multi_create: out of host memory";
@@ -90,12 +171,25 @@ PEB_API int peb_multi_create(int ndev, const int* devices, peb_multi** out) {
     }
     m->ctx.push_back(c);
   }
+  try {
+    for (int i = 1; i < ndev; ++i) m->workers.push_back(new Worker());
+  } catch (...) {
+    g_multi_create_error = "peb_multi_create: could not start the per-device host threads";
+    peb_multi_destroy(m);
+    return PEB_E_OOM;
+  }
+  // replicas are copied device to device from context 0 (peb_multi_target_set): direct where the hardware allows it
+  for (int i = 1; i < ndev; ++i) {
+    peb_ctx_enable_peer(m->ctx[static_cast<size_t>(i)], m->ctx[0]);
+    peb_ctx_enable_peer(m->ctx[0], m->ctx[static_cast<size_t>(i)]);
+  }
   *out = m;
   return PEB_OK;
 }
 
 PEB_API void peb_multi_destroy(peb_multi* m) {
   if (!m) return;
+  for (Worker* w : m->workers) delete w;  // joins the parked thread
   for (peb_ctx* c : m->ctx) peb_ctx_destroy(c);
   delete m;
 }
@@ -126,16 +220,27 @@ PEB_API void peb_multi_shard_range(size_t n_items, int ndev, int i, size_t* lo, 
   if (hi) *hi = b;
 }
 
-// every device builds its grid from the same host buffer: deterministic, so the replicas are identical
+// One host-to-device copy (context 0), device-to-device replicas, the same grid build on every device.
 PEB_API int peb_multi_target_set(peb_multi* m, const void* pts, size_t n, size_t stride, const void* normals, size_t nstride) {
   if (!m) return PEB_E_INVALID_ARG;
-  return on_all_devices(m, "peb_multi_target_set",
-                        [&](size_t i) { return peb_target_set(m->ctx[i], pts, n, stride, normals, nstride); });
+  const int rc = peb_target_stage(m->ctx[0], pts, n, stride, normals, nstride);
+  if (rc != PEB_OK)
+    return multi_fail(m, rc, std::string("peb_multi_target_set [context 0, device ") + std::to_string(m->ctx[0]->device) +
+                                 "]: " + peb_last_error(m->ctx[0]));
+  return on_all_devices(m, "peb_multi_target_set", [&](size_t i) {
+    return i == 0 ? peb_target_build(m->ctx[0]) : peb_target_clone(m->ctx[i], m->ctx[0]);
+  });
 }
 
 PEB_API int peb_multi_source_set(peb_multi* m, const void* pts, size_t n, size_t stride) {
   if (!m) return PEB_E_INVALID_ARG;
-  return on_all_devices(m, "peb_multi_source_set", [&](size_t i) { return peb_source_set(m->ctx[i], pts, n, stride); });
+  const int rc = peb_source_stage(m->ctx[0], pts, n, stride);
+  if (rc != PEB_OK)
+    return multi_fail(m, rc, std::string("peb_multi_source_set [context 0, device ") + std::to_string(m->ctx[0]->device) +
+                                 "]: " + peb_last_error(m->ctx[0]));
+  return on_all_devices(m, "peb_multi_source_set", [&](size_t i) {
+    return i == 0 ? peb_source_build(m->ctx[0]) : peb_source_clone(m->ctx[i], m->ctx[0]);
+  });
 }
 
 PEB_API int peb_multi_icp_align_batch(peb_multi* m, const float* guesses, size_t n_guesses, const peb_icp_params* params,

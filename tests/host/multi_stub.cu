@@ -14,8 +14,11 @@ std::atomic<int> g_live{0};
 std::atomic<int> g_created{0};
 std::atomic<int> g_concurrent{0};
 std::atomic<int> g_max_concurrent{0};
+std::atomic<int> g_uploads{0};  // host -> device stagings
+std::atomic<int> g_clones{0};   // device -> device replicas
 int g_fail_ordinal = -1;  // the context with this ordinal fails its next align
 thread_local std::string g_err;
+unsigned long long stub_thread_id() { return static_cast<unsigned long long>(std::hash<std::thread::id>{}(std::this_thread::get_id())); }
 }  // namespace
 
 extern "C" {
@@ -58,6 +61,62 @@ PEB_API int peb_source_set(peb_ctx* c, const void*, size_t n, size_t) {
   c->launches += 1;
   return PEB_OK;
 }
+// the halves of the two setters and the replicas (api.cu): staged -> built; a clone needs a staged original
+PEB_API int peb_target_stage(peb_ctx* c, const void*, size_t n, size_t, const void*, size_t) {
+  c->n_tgt = n;
+  c->tgt_staged = true;
+  c->launches += 1;
+  ++g_uploads;
+  return PEB_OK;
+}
+PEB_API int peb_target_build(peb_ctx* c) {
+  if (!c->tgt_staged) {
+    c->err = "stub: nothing staged";
+    return PEB_E_NO_TARGET;
+  }
+  c->tgt_grid.valid = true;
+  return PEB_OK;
+}
+PEB_API int peb_target_clone(peb_ctx* dst, peb_ctx* src) {
+  if (!src->tgt_staged) {
+    dst->err = "stub: the original has nothing staged";
+    return PEB_E_NO_TARGET;
+  }
+  dst->n_tgt = src->n_tgt;
+  dst->tgt_staged = true;
+  dst->tgt_grid.valid = true;
+  dst->launches += 1;
+  ++g_clones;
+  return PEB_OK;
+}
+PEB_API int peb_source_stage(peb_ctx* c, const void*, size_t n, size_t) {
+  c->n_src = n;
+  c->src_staged = true;
+  c->launches += 1;
+  ++g_uploads;
+  return PEB_OK;
+}
+PEB_API int peb_source_build(peb_ctx* c) {
+  if (!c->src_staged) {
+    c->err = "stub: nothing staged";
+    return PEB_E_NO_SOURCE;
+  }
+  c->src_set = true;
+  return PEB_OK;
+}
+PEB_API int peb_source_clone(peb_ctx* dst, peb_ctx* src) {
+  if (!src->src_staged) {
+    dst->err = "stub: the original has nothing staged";
+    return PEB_E_NO_SOURCE;
+  }
+  dst->n_src = src->n_src;
+  dst->src_staged = true;
+  dst->src_set = true;
+  dst->launches += 1;
+  ++g_clones;
+  return PEB_OK;
+}
+PEB_API int peb_ctx_enable_peer(peb_ctx*, const peb_ctx*) { return PEB_OK; }
 PEB_API int peb_icp_align_batch(peb_ctx* c, const float* guesses, size_t n, const peb_icp_params* p, peb_icp_result* results) {
   const int now = ++g_concurrent;
   int seen = g_max_concurrent.load();
@@ -65,6 +124,7 @@ PEB_API int peb_icp_align_batch(peb_ctx* c, const float* guesses, size_t n, cons
   }
   std::this_thread::sleep_for(std::chrono::milliseconds(30));  // long enough for the shards to overlap
   int rc = PEB_OK;
+  c->coop_max_rows = static_cast<int>(stub_thread_id() & 0x7FFFFFFF);  // which host thread drove this context (a field the stub does not otherwise use)
   if (c->nn_group == g_fail_ordinal) {
     c->err = "stub: injected failure";
     rc = PEB_E_CUDA;
@@ -84,10 +144,14 @@ PEB_API int peb_icp_align_batch(peb_ctx* c, const float* guesses, size_t n, cons
 }
 
 // test controls
+PEB_API int stub_uploads() { return g_uploads.exchange(0); }
+PEB_API int stub_clones() { return g_clones.exchange(0); }
 PEB_API int stub_live_contexts() { return g_live.load(); }
 PEB_API int stub_max_concurrent() { return g_max_concurrent.exchange(0); }
 PEB_API void stub_fail_ordinal(int k) { g_fail_ordinal = k; }
 PEB_API void stub_reset_ordinals() { g_created = 0; }
 PEB_API int stub_ctx_batch_streams(peb_ctx* c) { return c->batch_streams; }
+PEB_API int stub_ctx_thread(peb_ctx* c) { return c->coop_max_rows; }
+PEB_API int stub_ctx_ready(peb_ctx* c) { return (c->tgt_grid.valid ? 1 : 0) + (c->src_set ? 2 : 0); }
 
 }  // extern "C"

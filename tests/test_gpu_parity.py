@@ -382,6 +382,43 @@ def test_speed_options_never_change_results(pcl, oracle, scene_small, option, va
     assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
 
 
+@pytest.mark.parametrize("options,H", [({"blocks_factor_cold": 128}, 400), ({"blocks_factor_cold": 8, "blocks_factor": 64}, 400),
+                                       ({"nn_group": 8, "batch_streams": 2}, 32), ({"nn_group": 8, "batch_streams": 4}, 96)])
+def test_cold_and_warm_launches_with_different_block_counts_do_not_share_partial_records(pcl, scene_small, options, H):
+    """The per-block partial sums of a hypothesis live at a stride that does not depend on the launch: launch 0 (cold) and
+    the warm launches may use different numbers of blocks per hypothesis (blocks_factor_cold, or a lane-group width > 1
+    in launch 0 only), and chains / per-hypothesis launch dependencies let a warm launch of one hypothesis run while the
+    cold launch of another still sums.  A different block count changes the ORDER of the double sums (last bits), so the
+    check is against single aligns at a tolerance far below any corruption."""
+    p = scene_small
+    rng = np.random.default_rng(17)
+    guesses = np.stack([synth.perturb_pose(p.gt_pose, rng, 5.0, 0.006) for _ in range(H)])
+    prm = default_params(max_iterations=12, max_corr_dist=0.02, abs_mse_threshold=-1.0)
+    c = pcl.Context(0)
+    for k, v in options.items():
+        c.set_int(k, v)
+    icp = pcl.IterativeClosestPoint(c)
+    icp.setInputSource(p.source)
+    icp.setInputTarget(p.target)
+    _set_params(icp, prm)
+    runs = [[bytes(r) for r in icp.alignBatch(guesses)] for _ in range(3)]
+    assert runs[0] == runs[1] == runs[2]  # deterministic (an overlap of partial records would depend on timing)
+    res = icp.alignBatch(guesses)
+    plain = pcl.Context(0)
+    ref = pcl.IterativeClosestPoint(plain)
+    ref.setInputSource(p.source)
+    ref.setInputTarget(p.target)
+    _set_params(ref, prm)
+    for h in range(0, H, max(1, H // 24)):
+        ref.align(guesses[h], want_output=False)
+        rot, tr = pose_delta(pcl.result_matrix(res[h]), pcl.result_matrix(ref.result))
+        assert rot < 2e-6 and tr < 2e-6, (h, rot, tr)
+        assert res[h].iterations == ref.result.iterations and res[h].state == ref.result.state
+        assert abs(res[h].fitness - ref.result.fitness) <= 1e-5 * ref.result.fitness
+    c.close()
+    plain.close()
+
+
 def test_batch_with_hypotheses_that_stop_at_different_iterations(pcl, scene_small):
     """Convergence criteria on: hypotheses stop after different numbers of iterations, some never get a correspondence.
     The launches of a batch depend on each other per hypothesis (epoch flags, a sentinel when a hypothesis stops): the
