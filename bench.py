@@ -405,26 +405,20 @@ def run_ours(args):
         peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
-    persistent = False  # (a persistent cooperative variant was measured slower and removed: profiles/README.md)
-    if persistent:
-        # one cooperative launch per batch: anchors + ITERATIONS iterations (40 B/query each) + fitness (32 B/query)
-        kernel_name = ("icp_persistent_kernel (batched: one launch = anchors, all ICP iterations and the fitness pass "
-                       "of this rank's hypotheses)")
-        alg_bytes = h_local * len(c4.source) * (ALG_BYTES_PER_QUERY * ITERATIONS + 32)
-        avg_kernel_ms = sum(span_ms) / max(len(span_ms), 1)  # live, inside the timed steps
-        launches_timed = len(span_ms)
-    else:
-        kernel_name = "icp_iteration_kernel (batched, one launch = one ICP iteration of this rank's hypotheses)"
-        alg_bytes = h_local * len(c4.source) * ALG_BYTES_PER_QUERY
-        avg_kernel_ms = sum(span_ms) / max(len(span_ms) * ITERATIONS, 1)
-        launches_timed = len(span_ms) * ITERATIONS
+    kernel_name = "icp_iteration_kernel (batched, one launch = one ICP iteration of this rank's hypotheses)"
+    alg_bytes = h_local * len(c4.source) * ALG_BYTES_PER_QUERY
+    avg_kernel_ms = sum(span_ms) / max(len(span_ms) * ITERATIONS, 1)
+    launches_timed = len(span_ms) * ITERATIONS
     achieved = alg_bytes / (avg_kernel_ms * 1e-3) / 1e9 if avg_kernel_ms > 0 else 0.0
+    # traffic: dram__bytes_read + dram__bytes_write of one launch from an `ncu --set full` capture of THIS configuration
+    # (profiles/roofline_traffic.json names the launch size it was captured at); any other launch size -> null
     traffic = None
     tf = ROOT / "profiles" / "roofline_traffic.json"
     if tf.exists():
         try:
-            traffic = json.loads(tf.read_text()).get(
-                "icp_persistent_kernel_bytes_per_launch" if persistent else "icp_iteration_kernel_batch_bytes_per_launch")
+            t = json.loads(tf.read_text())
+            if int(t.get("hypotheses_per_launch", -1)) == h_local and int(t.get("n_source", -1)) == len(c4.source):
+                traffic = t.get("icp_iteration_kernel_batch_bytes_per_launch")
         except (ValueError, OSError):
             traffic = None
     roofline = {"bound": "hbm", "kernel": kernel_name,
@@ -454,7 +448,12 @@ def run_ours(args):
         if c2 is not None:
             with torch.cuda.stream(stream):
                 line["align_ms"] = single_align(ctx, c2, torch, stream, flush, pcl, lib)
+                line["align_ms"]["c1"] = c1_leg(ctx, torch, stream, flush, pcl, lib)
                 line["align_ms"]["cvicp_reference_call"] = cvicp_leg(ctx, c2, pcl, not args.no_cpu_baseline)
+            stage_fractions(line["align_ms"], peak)
+            if not args.no_cpu_baseline:
+                # SURVEY.md 8d / BASELINE.md section 4: the CPU port beside EVERY GPU number, same run, same host
+                line["align_ms"]["cpu_baseline"] = cpu_stage_baselines(c2)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(c4)
     if rank == 0:
@@ -588,6 +587,109 @@ def single_align(ctx, c2, torch, stream, flush, pcl, lib):
             "e2e_host_buffers": {"median": statistics.median(e2e), "min": min(e2e),
                                  "what": "peb_target_set + peb_source_set + peb_icp_align, L2 flushed"},
             "unit": "ms", "target_ms": 2.0, "stages": stages}
+
+
+def c1_leg(ctx, torch, stream, flush, pcl, lib):
+    """configs[0] (C1): 20k-pt model vs its rigidly moved, 1 mm-noise copy, 30 point-to-point iterations — the
+    reference's CPU-runnable case, here on the GPU (device-resident and from host buffers)."""
+    from pose_estimation_b200.testing import synth
+
+    c1 = synth.make_c1(20000, seed=1)
+    params = pcl.IcpParams()
+    lib.peb_icp_params_default(C.byref(params))
+    params.max_iterations = ITERATIONS
+    params.abs_mse_threshold = -1.0
+    h_t = torch.from_numpy(np.ascontiguousarray(c1.target)).pin_memory()
+    h_s = torch.from_numpy(np.ascontiguousarray(c1.source)).pin_memory()
+    d_res = torch.zeros(C.sizeof(pcl.IcpResult), dtype=torch.uint8, device=flush.device)
+    res = pcl.IcpResult()
+
+    def setup():
+        ctx.check(lib.peb_target_set(ctx.handle, h_t.data_ptr(), h_t.shape[0], 16, None, 0))
+        ctx.check(lib.peb_source_set(ctx.handle, h_s.data_ptr(), h_s.shape[0], 16))
+
+    def run(host: bool, reps: int):
+        out = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            if host:
+                setup()
+                ctx.check(lib.peb_icp_align(ctx.handle, None, C.byref(params), C.byref(res), None, None, None))
+            else:
+                ctx.check(lib.peb_icp_align_dev(ctx.handle, None, C.byref(params), d_res.data_ptr()))
+            b.record(stream)
+            stream.synchronize()
+            out.append(a.elapsed_time(b))
+        return out
+
+    setup()
+    run(False, 5)
+    dev = run(False, 20)
+    e2e = run(True, 10)
+    alg = ALG_BYTES_PER_QUERY * len(c1.source) * ITERATIONS
+    return {"workload": "C1 (BASELINE.json configs[0]): 20k-pt model vs its moved 1 mm-noise copy, 30 point-to-point iterations",
+            "device_resident_cold_l2": {"median": statistics.median(dev), "min": min(dev)},
+            "e2e_host_buffers": {"median": statistics.median(e2e), "min": min(e2e)},
+            "iterations": int(res.iterations), "fitness": float(res.fitness), "algorithmic_bytes": alg,
+            "achieved_gbs": alg / (statistics.median(dev) * 1e-3) / 1e9, "unit": "ms"}
+
+
+def stage_fractions(align, peak):
+    """achieved GB/s and fraction of the measured HBM peak for every stage that has algorithmic bytes."""
+    n_src = align["n_source"]
+    align["algorithmic_bytes"] = ALG_BYTES_PER_QUERY * n_src * ITERATIONS
+    align["achieved_gbs"] = align["algorithmic_bytes"] / (align["device_resident_cold_l2"]["median"] * 1e-3) / 1e9
+    align["frac"] = align["achieved_gbs"] / peak
+    st = align["stages"]
+    n_t = align["n_target"]
+    st["c3_point_to_plane_align"]["algorithmic_bytes"] = 56 * n_src * ITERATIONS
+    st["c5_end_to_end"]["algorithmic_bytes"] = (st["voxel_grid"]["algorithmic_bytes"] + st["normals_k30"]["algorithmic_bytes"]
+                                                + 36 * n_t + 56 * n_src * 50)
+    for k in ("c3_point_to_plane_align", "c5_end_to_end"):
+        st[k]["achieved_gbs"] = st[k]["algorithmic_bytes"] / (st[k]["ms_median"] * 1e-3) / 1e9
+    for v in list(st.values()) + [align["c1"]]:
+        if isinstance(v, dict) and "achieved_gbs" in v:
+            v["frac"] = v["achieved_gbs"] / peak
+
+
+def cpu_stage_baselines(c2):
+    """The CPU port (oracle timing build, the PCL 1.10 restatement: single kd-tree, leaf 15, exact search) on this box's
+    host cores for every stage bench.py times on the GPU.  PCL 1.10's ICP loop, VoxelGrid and NormalEstimation are serial
+    (1 thread); NormalEstimationOMP is the all-cores figure."""
+    from oracle import Oracle, build, default_params
+    from pose_estimation_b200.testing import synth
+
+    build()
+    orc = Oracle(fast=True)
+    cores = host_threads()
+
+    def timed(fn):
+        t0 = time.perf_counter()
+        out = fn()
+        return 1e3 * (time.perf_counter() - t0), out
+
+    out = {"kind": "port", "cores": cores, "unit": "ms",
+           "what": "oracle timing build (-O3 AVX2/FMA) of the PCL 1.10 restatement, wall clock, kd-tree build included"}
+    c1 = synth.make_c1(20000, seed=1)
+    prm = default_params(max_iterations=ITERATIONS, abs_mse_threshold=-1.0)
+    out["c1_align_1_thread"], _ = timed(lambda: orc.icp(c1.target).align(c1.source, None, prm))
+    out["c2_align_1_thread"], _ = timed(lambda: orc.icp(c2.target).align(c2.source, c2.guess, prm))
+    out["voxel_grid_1_thread"], (ds, _u) = timed(lambda: orc.voxel_grid(c2.organized, c2.leaf))
+    out["normals_k30_1_thread"], nrm = timed(lambda: orc.normals(ds, 30, threads=1))
+    out["normals_k30_all_cores"], _ = timed(lambda: orc.normals(ds, 30, threads=cores))
+    p3 = default_params(max_iterations=ITERATIONS, abs_mse_threshold=-1.0, estimator=1)
+    out["c3_point_to_plane_align_1_thread"], _ = timed(lambda: orc.icp(ds, nrm[:, :3].copy()).align(c2.source, c2.guess, p3))
+    p5 = default_params(max_iterations=50, abs_mse_threshold=-1.0, estimator=1)
+
+    def c5():
+        d, _ = orc.voxel_grid(c2.organized, c2.leaf)
+        n = orc.normals(d, 30, threads=1)
+        return orc.icp(d, n[:, :3].copy()).align(c2.source, c2.guess, p5)
+
+    out["c5_end_to_end_1_thread"], _ = timed(c5)
+    return out
 
 
 def cvicp_leg(ctx, c2, pcl, with_cpu: bool):

@@ -189,8 +189,10 @@ PEB_API void peb_ctx_destroy(peb_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->d_small, &ctx->d_scratch, &ctx->d_stage, &ctx->tgt_raw, &ctx->tgt_nrm_raw, &ctx->src, &ctx->work, &ctx->slack, &ctx->anchors, &ctx->dbg,
                     &ctx->corr_idx, &ctx->corr_d2, &ctx->partials, &ctx->state, &ctx->trace, &ctx->d_guesses,
                     &ctx->d_results, &ctx->d_aligned, &ctx->vg_in, &ctx->vg_out, &ctx->vg_flags, &ctx->vg_scan,
-                    &ctx->vg_starts, &ctx->nrm_in, &ctx->nrm_out, &ctx->nn_q, &ctx->nn_idx, &ctx->nn_d2, &ctx->epochs, &ctx->cv_arena};
+                    &ctx->vg_starts, &ctx->nrm_in, &ctx->nrm_out, &ctx->nrm_left, &ctx->nn_q, &ctx->nn_idx, &ctx->nn_d2, &ctx->epochs, &ctx->cv_arena};
   for (DevBuf* b : bufs) b->release();
+  ctx->sort_scratch.release();
+  for (DevBuf& b : ctx->scan_scratch) b.release();
   for (Grid* g : {&ctx->tgt_grid, &ctx->aux_grid, &ctx->src_grid}) {
     g->pts.release();
     g->normals.release();
@@ -841,6 +843,47 @@ extern "C" PEB_API int peb_debug_timers_read(peb_ctx* ctx, unsigned long long* o
     PEB_TRY(sync(ctx));
   }
   return PEB_OK;
+}
+
+// development aids (not in the public header): the radix sort and the scan on host arrays, for tests/test_gpu_sort_scan.py
+extern "C" PEB_API int peb_debug_sort_pairs(peb_ctx* ctx, uint32_t* keys, uint32_t* vals, size_t n, int key_bits) {
+  if (!ctx || (n && (!keys || !vals)) || n > (1u << 30)) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  DevBuf b[4];
+  int rc = PEB_OK;
+  for (DevBuf& x : b)
+    if (x.ensure(std::max<size_t>(n, 1) * 4) != cudaSuccess) rc = fail(ctx, PEB_E_OOM, "debug_sort_pairs: out of device memory");
+  uint32_t *ko = nullptr, *vo = nullptr;
+  if (rc == PEB_OK && n) {
+    cudaMemcpyAsync(b[0].p, keys, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(b[1].p, vals, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    rc = sort_pairs(ctx, b[0].as<uint32_t>(), b[1].as<uint32_t>(), b[2].as<uint32_t>(), b[3].as<uint32_t>(), static_cast<int>(n),
+                    key_bits, &ko, &vo);
+    if (rc == PEB_OK) {
+      cudaMemcpyAsync(keys, ko, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+      cudaMemcpyAsync(vals, vo, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+      rc = sync(ctx);
+    }
+  }
+  for (DevBuf& x : b) x.release();
+  return rc;
+}
+
+extern "C" PEB_API int peb_debug_exclusive_scan(peb_ctx* ctx, const uint32_t* in, uint32_t* out, size_t n, uint32_t* out_total) {
+  if (!ctx || (n && (!in || !out)) || n > (1u << 30)) return PEB_E_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  DevBuf b;
+  if (b.ensure(std::max<size_t>(n, 1) * 4 + 4) != cudaSuccess) return fail(ctx, PEB_E_OOM, "debug_exclusive_scan: out of device memory");
+  uint32_t* d = b.as<uint32_t>();
+  if (n) cudaMemcpyAsync(d, in, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+  int rc = exclusive_scan_u32(ctx, d, d, static_cast<int>(n), d + n);  // in place
+  if (rc == PEB_OK) {
+    if (n) cudaMemcpyAsync(out, d, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (out_total) cudaMemcpyAsync(out_total, d + n, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    rc = sync(ctx);
+  }
+  b.release();
+  return rc;
 }
 
 PEB_API int peb_icp_trace(peb_ctx* ctx, float* out_T, size_t cap, size_t* out_n) {

@@ -132,7 +132,9 @@ struct peb_ctx {
   peb::PinnedBuf h_stage;    // host repack / readback staging
   peb::PinnedBuf h_small;    // small results (bbox, counters, peb_icp_result)
   peb::DevBuf d_small;       // device side of h_small
-  peb::DevBuf d_scratch;     // sort histograms, scan block sums, ...
+  peb::DevBuf d_scratch;     // plane RANSAC staging
+  peb::DevBuf sort_scratch;  // radix sort: digit histograms, tile tickets, look-back words (sort_scan.cuh : SortPlan)
+  peb::DevBuf scan_scratch[4];  // single-pass scans: look-back words + ticket + total per slot (sort_scan.cuh : ScanState)
   peb::DevBuf d_stage;       // raw host records before the repack kernel
 
   // target (scene)
@@ -181,6 +183,7 @@ struct peb_ctx {
   peb::Grid aux_grid;
   peb::DevBuf vg_in, vg_out, vg_flags, vg_scan, vg_starts;
   peb::DevBuf nrm_in, nrm_out;
+  peb::DevBuf nrm_left;      // normals: count + sorted positions of the queries the warp kernel left to the general one
   peb::DevBuf cv_arena;      // cv::ppf_match_3d::ICP mode: all device buffers of a call
   peb::PinnedBuf h_cv;       // cv ICP mode: pose tables (two, alternating) + accumulator read-back
   peb::PinnedBuf h_sac;      // plane RANSAC: sample indices / coordinates, candidate planes, counts, moment records

@@ -3,12 +3,19 @@
 //
 // Like KdTreeFLANN, non-finite points are left out and results are reported as ORIGINAL indices.
 //   bbox        : finite min/max + count, one pass, float4 loads, ordered-int atomics
-//   cell ids    : key = (z * dy + y) * dx + x (x fastest); non-finite points get key = n_cells
-//   radix sort  : (key, original index), stable
+//   cell ids    : key = (z * dy + y) * dx + x (x fastest); non-finite points get key = n_cells; the same kernel
+//                 counts the digits of every sort pass (sort_scan.cuh)
+//   radix sort  : (key, original index), stable, one kernel per 8-bit digit (radix_sort.cu)
 //   gather      : sorted float4 records with the original index in .w (and sorted normals)
-//   cell_start  : lower_bound of every cell id in the sorted keys (one thread per cell)
+//   cell_start  : every boundary between two sorted keys writes the table entries of the cells in between
+//                 (warp-cooperative, coalesced): one streaming write of the table instead of a binary search per cell
 // HBM traffic is N * (16 read + 16 write + 4 idx) + 4 * cells, plus the sort passes.
+// Host round trips: the bounding box (the cell size and the table size depend on it) and, after everything has been
+// queued, the measured occupancy (a rebuild with another cell size happens only for unusual clouds).
+#include <algorithm>
+
 #include "core_math.cuh"
+#include "sort_scan.cuh"
 
 namespace peb {
 
@@ -84,19 +91,32 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float4* __restrict__ pt
 
 __global__ void __launch_bounds__(256) cell_key_kernel(const float4* __restrict__ pts, int n, GridView g,
                                                        uint32_t n_cells, uint32_t* __restrict__ keys,
-                                                       uint32_t* __restrict__ vals) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float4 p = pts[i];
-  uint32_t key = n_cells;
-  if (finite3(p.x, p.y, p.z)) {
-    const int cx = grid_coord(p.x, g.ox, g.inv_h, g.dx);
-    const int cy = grid_coord(p.y, g.oy, g.inv_h, g.dy);
-    const int cz = grid_coord(p.z, g.oz, g.inv_h, g.dz);
-    key = static_cast<uint32_t>((static_cast<long long>(cz) * g.dy + cy) * g.dx + cx);
+                                                       uint32_t* __restrict__ vals, int passes,
+                                                       uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[kSortMaxPasses][kSortRadix];
+  for (int i = threadIdx.x; i < kSortMaxPasses * kSortRadix; i += 256) (&sh[0][0])[i] = 0;
+  __syncthreads();
+  const int stride = gridDim.x * 256;
+  const int rounds = (n + stride - 1) / stride;  // every lane runs every round (warp votes in sort_hist_add)
+  for (int r = 0; r < rounds; ++r) {
+    const int i = r * stride + blockIdx.x * 256 + threadIdx.x;
+    const bool in = i < n;
+    uint32_t key = n_cells;
+    if (in) {
+      const float4 p = pts[i];
+      if (finite3(p.x, p.y, p.z)) {
+        const int cx = grid_coord(p.x, g.ox, g.inv_h, g.dx);
+        const int cy = grid_coord(p.y, g.oy, g.inv_h, g.dy);
+        const int cz = grid_coord(p.z, g.oz, g.inv_h, g.dz);
+        key = static_cast<uint32_t>((static_cast<long long>(cz) * g.dy + cy) * g.dx + cx);
+      }
+      keys[i] = key;
+      vals[i] = static_cast<uint32_t>(i);
+    }
+    sort_hist_add(sh, key, in, passes);
   }
-  keys[i] = key;
-  vals[i] = static_cast<uint32_t>(i);
+  __syncthreads();
+  sort_hist_flush(sh, hist, passes);
 }
 
 __global__ void __launch_bounds__(256) gather_sorted_kernel(const float4* __restrict__ pts,
@@ -113,28 +133,35 @@ __global__ void __launch_bounds__(256) gather_sorted_kernel(const float4* __rest
   if (normals) out_normals[j] = normals[src];
 }
 
-// cell_start[c] = first sorted position whose key >= c, for c in [0, n_cells]
-__global__ void __launch_bounds__(256) cell_start_kernel(const uint32_t* __restrict__ sorted_keys, int n_finite,
-                                                         uint32_t n_cells, uint32_t* __restrict__ cell_start) {
-  const long long c = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (c > n_cells) return;
-  int lo = 0, hi = n_finite;
-  const uint32_t want = static_cast<uint32_t>(c);
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (sorted_keys[mid] < want)
-      lo = mid + 1;
-    else
-      hi = mid;
-  }
-  cell_start[c] = static_cast<uint32_t>(lo);
-}
-
-__global__ void count_occupied_kernel(const uint32_t* __restrict__ sorted_keys, int n_finite, unsigned* out) {
+// cell_start[c] = first sorted position whose key >= c, for c in [0, n_cells].  Thread j looks at the boundary between
+// sorted positions j - 1 and j (j = n_finite: the end): every cell id in (key[j-1], key[j]] starts at j.  Gaps of more
+// than two cells are filled by the whole warp (consecutive cells -> consecutive addresses).  Also counts the occupied
+// cells (*occupied += number of boundaries with key[j] != key[j-1]).
+__global__ void __launch_bounds__(256) cell_start_fill_kernel(const uint32_t* __restrict__ sorted_keys, int n_finite,
+                                                              uint32_t n_cells, uint32_t* __restrict__ cell_start,
+                                                              unsigned* __restrict__ occupied) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  bool head = j < n_finite && (j == 0 || sorted_keys[j] != sorted_keys[j - 1]);
-  unsigned b = __ballot_sync(0xFFFFFFFFu, head);
-  if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, __popc(b));
+  const int lane = threadIdx.x & 31;
+  const bool in = j <= n_finite;
+  long long prev = -1, cur = -1;
+  if (in) {
+    prev = j > 0 ? static_cast<long long>(sorted_keys[j - 1]) : -1;
+    cur = j < n_finite ? static_cast<long long>(sorted_keys[j]) : static_cast<long long>(n_cells);
+  }
+  const long long gap = cur - prev;
+  const unsigned heads = __ballot_sync(0xFFFFFFFFu, in && j < n_finite && gap > 0);
+  if (lane == 0 && heads) atomicAdd(occupied, static_cast<unsigned>(__popc(heads)));
+  if (in && gap >= 1 && gap <= 2)
+    for (long long c = prev + 1; c <= cur; ++c) cell_start[c] = static_cast<uint32_t>(j);
+  unsigned big = __ballot_sync(0xFFFFFFFFu, in && gap > 2);
+  while (big) {
+    const int src = __ffs(big) - 1;
+    big &= big - 1;
+    const long long p = __shfl_sync(0xFFFFFFFFu, prev, src);
+    const long long e = __shfl_sync(0xFFFFFFFFu, cur, src);
+    const uint32_t jj = static_cast<uint32_t>(__shfl_sync(0xFFFFFFFFu, j, src));
+    for (long long c = p + 1 + lane; c <= e; c += 32) cell_start[c] = jj;
+  }
 }
 
 }  // namespace
@@ -229,15 +256,22 @@ int grid_build(peb_ctx* ctx, Grid* g, const float4* d_pts, const float4* d_norma
     g->n_cells = cells;
     int key_bits = 1;
     while ((1ll << key_bits) <= cells) ++key_bits;  // keys run 0..cells (cells = non-finite)
-    PEB_LAUNCH(ctx, cell_key_kernel, ceil_div(n, 256), 256, 0, d_pts, n, v, static_cast<uint32_t>(cells),
-               g->keys.as<uint32_t>(), g->vals.as<uint32_t>());
-    PEB_TRY(sort_pairs(ctx, g->keys.as<uint32_t>(), g->vals.as<uint32_t>(), g->keys_tmp.as<uint32_t>(),
-                       g->vals_tmp.as<uint32_t>(), n, key_bits, &sk, &sv));
-    // measured occupancy
+    SortPlan plan;
+    PEB_TRY(sort_prepare(ctx, n, key_bits, &plan));
+    const int key_blocks = std::min(ceil_div(n, 256 * 8), kSmCount * 8);
+    PEB_LAUNCH(ctx, cell_key_kernel, key_blocks, 256, 0, d_pts, n, v, static_cast<uint32_t>(cells),
+               g->keys.as<uint32_t>(), g->vals.as<uint32_t>(), plan.passes, plan.hist);
+    PEB_TRY(sort_pairs_counted(ctx, plan, g->keys.as<uint32_t>(), g->vals.as<uint32_t>(), g->keys_tmp.as<uint32_t>(),
+                               g->vals_tmp.as<uint32_t>(), n, &sk, &sv));
+    // the rest of the build is queued before the occupancy comes back: the usual cloud needs no second attempt
+    PEB_CUDA(ctx, g->cell_start.ensure(static_cast<size_t>(g->n_cells + 1) * sizeof(uint32_t)));
     unsigned* d_occ = ctx->d_small.as<unsigned>() + 16;
     unsigned* h_occ = ctx->h_small.as<unsigned>() + 16;
     PEB_CUDA(ctx, cudaMemsetAsync(d_occ, 0, sizeof(unsigned), ctx->stream));
-    PEB_LAUNCH(ctx, count_occupied_kernel, ceil_div(n_finite, 256), 256, 0, sk, n_finite, d_occ);
+    PEB_LAUNCH(ctx, gather_sorted_kernel, ceil_div(n_finite, 256), 256, 0, d_pts, d_normals, sv, n_finite,
+               g->pts.as<float4>(), d_normals ? g->normals.as<float4>() : nullptr);
+    PEB_LAUNCH(ctx, cell_start_fill_kernel, ceil_div(n_finite + 1, 256), 256, 0, sk, n_finite,
+               static_cast<uint32_t>(g->n_cells), g->cell_start.as<uint32_t>(), d_occ);
     PEB_CUDA(ctx, cudaMemcpyAsync(h_occ, d_occ, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
     PEB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const float occ = static_cast<float>(n_finite) / static_cast<float>(*h_occ > 0 ? *h_occ : 1);
@@ -249,11 +283,6 @@ int grid_build(peb_ctx* ctx, Grid* g, const float4* d_pts, const float4* d_norma
     if (h_new < h && cells * 1.0 / (scale * scale * scale) > static_cast<double>(kMaxCells)) break;
     h = h_new;
   }
-  PEB_CUDA(ctx, g->cell_start.ensure(static_cast<size_t>(g->n_cells + 1) * sizeof(uint32_t)));
-  PEB_LAUNCH(ctx, gather_sorted_kernel, ceil_div(n_finite, 256), 256, 0, d_pts, d_normals, sv, n_finite,
-             g->pts.as<float4>(), d_normals ? g->normals.as<float4>() : nullptr);
-  PEB_LAUNCH(ctx, cell_start_kernel, ceil_div(g->n_cells + 1, 256), 256, 0, sk, n_finite,
-             static_cast<uint32_t>(g->n_cells), g->cell_start.as<uint32_t>());
   v.pts = g->pts.as<float4>();
   v.normals = d_normals ? g->normals.as<float4>() : nullptr;
   v.cell_start = g->cell_start.as<uint32_t>();

@@ -1,193 +1,202 @@
-// radix_sort.cu — stable LSD radix sort of (uint32 key, uint32 value) pairs and a device-wide
-// exclusive scan.  These feed VoxelGrid (sort by voxel id, [PCL] filters/impl/voxel_grid.hpp
-// "second pass") and the uniform-grid build that replaces the kd-tree (SURVEY.md 8a-2').
+// radix_sort.cu — stable LSD radix sort of (uint32 key, uint32 value) pairs ("one sweep": ONE kernel per 8-bit digit)
+// and a single-pass device-wide exclusive scan.  They feed VoxelGrid (sort by voxel id, [PCL]
+// filters/impl/voxel_grid.hpp "second pass") and the uniform-grid build that replaces the kd-tree (SURVEY.md 8a-2').
 //
-// Layout: 8-bit digits, only ceil(key_bits / 8) passes.  One pass = three launches:
-//   digit_histogram : each CTA histograms its 4096-key tile                     (16 B / lane loads)
-//   exclusive scan  : over the digit-major (digit, CTA) table -> global offsets
-//   scatter         : each CTA re-reads its tile, ranks keys stably with warp match_any and a
-//                     per-warp digit counter table in shared memory, writes to out[offset+rank]
-// Stability keeps equal keys in ascending original index, which is what fixes the float
-// summation order of the voxel centroids.  Sort traffic is overhead on top of the
-// algorithmic bytes of its callers; at 2.3 M pairs every pass stays inside the 126 MB L2.
-#include "common.cuh"
+//   digit counts   the histograms of ALL passes are taken in one pass over the keys — by the kernel that produces the
+//                  keys (sort_scan.cuh : sort_hist_add) or, for keys that already exist, by sort_hist_kernel
+//   one pass       onesweep_kernel: a CTA takes a tile (ticket order), ranks its keys stably (warp match_any + per-warp
+//                  digit counters), publishes the tile's digit counts, obtains the counts of all earlier tiles by
+//                  decoupled look-back (256 chains, one per digit and thread), reorders the tile through shared memory
+//                  and writes runs of equal digits to consecutive addresses — coalesced stores, one read of the input
+// Only ceil(key_bits / 8) passes run.  Stability keeps equal keys in ascending original index, which fixes the float
+// summation order of the voxel centroids.
+// Round 1 ran five launches per pass (histogram, three-kernel scan, scatter from registers): 20 launches for the 25-bit
+// voxel ids of the 2.33 M-point scene; this version: memset + 4.
+#include "sort_scan.cuh"
 
 namespace peb {
 
 namespace {
 
 constexpr int kSortThreads = 256;
-constexpr int kSortItems = 16;
-constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 keys per CTA
 constexpr int kWarps = kSortThreads / 32;
-constexpr int kRadix = 256;
 
-__global__ void __launch_bounds__(kSortThreads) digit_histogram_kernel(const uint32_t* __restrict__ keys, int n,
-                                                                       int shift, uint32_t* __restrict__ hist,
-                                                                       int n_tiles) {
-  __shared__ uint32_t sh[kRadix];
-  sh[threadIdx.x] = 0;
+// digit histograms of all passes for keys that already exist (the debug entry point; the library's own producers count
+// while they write the keys)
+__global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const uint32_t* __restrict__ keys, int n, int passes,
+                                                                 uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[kSortMaxPasses][kSortRadix];
+  for (int i = threadIdx.x; i < kSortMaxPasses * kSortRadix; i += kSortThreads) (&sh[0][0])[i] = 0;
   __syncthreads();
-  const int tile = blockIdx.x;
-  const int base = tile * kSortTile;
-  // 4 x uint4 per thread, coalesced 16-byte loads
-  const int end = min(base + kSortTile, n);
-  for (int i = base + threadIdx.x * 4; i < end; i += kSortThreads * 4) {
-    if (i + 3 < end) {
-      uint4 k = *reinterpret_cast<const uint4*>(keys + i);
-      atomicAdd(&sh[(k.x >> shift) & 0xFF], 1u);
-      atomicAdd(&sh[(k.y >> shift) & 0xFF], 1u);
-      atomicAdd(&sh[(k.z >> shift) & 0xFF], 1u);
-      atomicAdd(&sh[(k.w >> shift) & 0xFF], 1u);
-    } else {
-      for (int j = i; j < end; ++j) atomicAdd(&sh[(keys[j] >> shift) & 0xFF], 1u);
-    }
+  const int stride = gridDim.x * kSortThreads;
+  const int rounds = (n + stride - 1) / stride;  // every lane runs every round: the warp votes need all 32
+  for (int r = 0; r < rounds; ++r) {
+    const int i = r * stride + blockIdx.x * kSortThreads + threadIdx.x;
+    const bool ok = i < n;
+    sort_hist_add(sh, ok ? keys[i] : 0u, ok, passes);
   }
   __syncthreads();
-  hist[static_cast<size_t>(threadIdx.x) * n_tiles + tile] = sh[threadIdx.x];
+  sort_hist_flush(sh, hist, passes);
 }
 
-__global__ void __launch_bounds__(kSortThreads) scatter_kernel(const uint32_t* __restrict__ keys_in,
-                                                               const uint32_t* __restrict__ vals_in,
-                                                               uint32_t* __restrict__ keys_out,
-                                                               uint32_t* __restrict__ vals_out, int n, int shift,
-                                                               const uint32_t* __restrict__ offsets, int n_tiles) {
-  __shared__ uint32_t warp_cnt[kWarps][kRadix];  // per-warp running digit counters
-  __shared__ uint32_t digit_base[kRadix];        // global offset of (digit, this tile)
-  const int tile = blockIdx.x;
+template <int ITEMS>
+__global__ void __launch_bounds__(kSortThreads) onesweep_kernel(const uint32_t* __restrict__ keys_in,
+                                                                const uint32_t* __restrict__ vals_in,
+                                                                uint32_t* __restrict__ keys_out,
+                                                                uint32_t* __restrict__ vals_out, int n, int shift,
+                                                                const uint32_t* __restrict__ hist,  // this pass: [256]
+                                                                uint32_t* __restrict__ tile_state,  // this pass: [n_tiles][256]
+                                                                uint32_t* __restrict__ ticket) {
+  constexpr int kTile = kSortThreads * ITEMS;
+  __shared__ uint32_t warp_cnt[kWarps][kSortRadix];  // per-warp running digit counters -> exclusive over the warps
+  __shared__ uint32_t local_start[kSortRadix];       // first position of a digit inside the reordered tile
+  __shared__ uint32_t dst_base[kSortRadix];          // global address of position 0 of a digit's run, minus local_start
+  __shared__ uint32_t sk[kTile], sv[kTile];          // the reordered tile
+  __shared__ uint32_t s_scan[kWarps];
+  __shared__ int s_tile;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < kWarps * kRadix; i += kSortThreads) (&warp_cnt[0][0])[i] = 0;
-  digit_base[threadIdx.x] = offsets[static_cast<size_t>(threadIdx.x) * n_tiles + tile];
+  if (threadIdx.x == 0) s_tile = static_cast<int>(atomicAdd(ticket, 1u));
+  for (int i = threadIdx.x; i < kWarps * kSortRadix; i += kSortThreads) (&warp_cnt[0][0])[i] = 0;
   __syncthreads();
+  const int tile = s_tile;
+  const int tile_n = min(kTile, n - tile * kTile);
 
-  // warp w owns the contiguous chunk [base + w*512, +512): item r of lane l is element r*32 + l,
-  // so consecutive rounds and lanes walk the chunk in index order (stability).
-  const int chunk = tile * kSortTile + warp * (32 * kSortItems);
-  uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
+  // warp w owns the contiguous chunk [w * 32 * ITEMS, + 32 * ITEMS) of the tile: item r of lane l is element r * 32 + l,
+  // so consecutive rounds and lanes walk the chunk in index order (stability)
+  const int chunk = tile * kTile + warp * (32 * ITEMS);
+  uint32_t key[ITEMS], val[ITEMS], rank[ITEMS];
 #pragma unroll
-  for (int r = 0; r < kSortItems; ++r) {
+  for (int r = 0; r < ITEMS; ++r) {
     const int i = chunk + r * 32 + lane;
     const bool ok = i < n;
     key[r] = ok ? keys_in[i] : 0xFFFFFFFFu;
     val[r] = ok ? vals_in[i] : 0u;
-    const uint32_t digit = (key[r] >> shift) & 0xFF;
-    // lanes past the end take part in the ballot with a digit nobody else can rank against
-    const uint32_t active = __ballot_sync(0xFFFFFFFFu, ok);
-    uint32_t peers = __match_any_sync(0xFFFFFFFFu, ok ? digit : (0x100u + lane)) & active;
+  }
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) {
+    const bool ok = chunk + r * 32 + lane < n;
+    const uint32_t digit = (key[r] >> shift) & 0xFFu;
+    // lanes past the end take part in the vote with a digit nobody else can rank against
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, ok ? digit : (0x100u + lane));
     const uint32_t lower = peers & ((1u << lane) - 1u);
     uint32_t before = 0;
     if (ok) before = warp_cnt[warp][digit];
     __syncwarp();
-    if (ok && lower == 0) warp_cnt[warp][digit] = before + __popc(peers);  // first peer bumps the counter
+    if (ok && lower == 0) warp_cnt[warp][digit] = before + __popc(peers);  // the first peer bumps the counter
     __syncwarp();
     rank[r] = before + __popc(lower);
   }
   __syncthreads();
-  // exclusive scan over warps, per digit: warp_cnt[w][d] becomes the number of keys with digit d in warps < w
-  {
-    const int d = threadIdx.x;
-    uint32_t run = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      uint32_t c = warp_cnt[w][d];
-      warp_cnt[w][d] = run;
-      run += c;
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < kSortItems; ++r) {
-    const int i = chunk + r * 32 + lane;
-    if (i < n) {
-      const uint32_t digit = (key[r] >> shift) & 0xFF;
-      const uint32_t dst = digit_base[digit] + warp_cnt[warp][digit] + rank[r];
-      keys_out[dst] = key[r];
-      vals_out[dst] = val[r];
-    }
-  }
-}
 
-// ---- exclusive scan (three phases) ------------------------------------------------------------
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
-constexpr int kScanTile = kScanThreads * kScanItems;
+  // thread d: digit d.  Counters -> exclusive over the warps; the tile's count of d goes to the look-back chain at once
+  const int d = threadIdx.x;
+  uint32_t count = 0;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) {
+    const uint32_t c = warp_cnt[w][d];
+    warp_cnt[w][d] = count;
+    count += c;
+  }
+  uint32_t* word = tile_state + static_cast<size_t>(tile) * kSortRadix + d;
+  st_relaxed_u32(word, (tile == 0 ? kFlagInclusive : kFlagAggregate) | count);
 
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
-  __shared__ uint32_t warp_sums[kScanThreads / 32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t inc = v;
+  // exclusive scans over the digits: of the tile's counts (positions inside the tile) and of the global histogram
+  // (where a digit's run starts in the output)
+  uint32_t inc_local = count, inc_global = hist[d];
+  const uint32_t hist_d = inc_global;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) warp_sums[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t w = lane < kScanThreads / 32 ? warp_sums[lane] : 0;
-    uint32_t winc = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(0xFFFFFFFFu, winc, o);
-      if (lane >= o) winc += t;
+    const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, inc_local, o);
+    const uint32_t b = __shfl_up_sync(0xFFFFFFFFu, inc_global, o);
+    if (lane >= o) {
+      inc_local += a;
+      inc_global += b;
     }
-    if (lane < kScanThreads / 32) warp_sums[lane] = winc - w;
-    if (lane == 31 && total) *total = winc;
+  }
+  __shared__ uint32_t s_scan_g[kWarps];
+  if (lane == 31) {
+    s_scan[warp] = inc_local;
+    s_scan_g[warp] = inc_global;
   }
   __syncthreads();
-  uint32_t res = warp_sums[warp] + inc - v;
-  __syncthreads();
-  return res;
-}
-
-__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const uint32_t* __restrict__ in, int n,
-                                                                      uint32_t* __restrict__ tile_sums) {
-  __shared__ uint32_t total;
-  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-  uint32_t s = 0;
+  uint32_t off_local = 0, off_global = 0;
 #pragma unroll
-  for (int i = 0; i < kScanItems; ++i)
-    if (base + i < n) s += in[base + i];
-  block_exclusive_scan(s, &total);
-  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
-}
-
-// single CTA: exclusive scan of the tile sums in place; writes the grand total
-__global__ void __launch_bounds__(kScanThreads) scan_spine_kernel(uint32_t* __restrict__ tile_sums, int n_tiles,
-                                                                  uint32_t* __restrict__ d_total) {
-  __shared__ uint32_t total;
-  uint32_t carry = 0;
-  for (int base = 0; base < n_tiles; base += kScanThreads) {
-    const int i = base + threadIdx.x;
-    uint32_t v = i < n_tiles ? tile_sums[i] : 0;
-    uint32_t ex = block_exclusive_scan(v, &total);
-    if (i < n_tiles) tile_sums[i] = carry + ex;
-    carry += total;
-    __syncthreads();
+  for (int w = 0; w < kWarps; ++w) {
+    if (w < warp) {
+      off_local += s_scan[w];
+      off_global += s_scan_g[w];
+    }
   }
-  if (threadIdx.x == 0 && d_total) *d_total = carry;
+  const uint32_t start_local = off_local + inc_local - count;
+  const uint32_t start_global = off_global + inc_global - hist_d;
+
+  uint32_t before_tiles = 0;
+  if (tile > 0) {
+    before_tiles = lookback_exclusive(tile_state + d, tile, kSortRadix);
+    st_relaxed_u32(word, kFlagInclusive | (before_tiles + count));
+  }
+  local_start[d] = start_local;
+  dst_base[d] = start_global + before_tiles - start_local;
+  __syncthreads();
+
+  // reorder through shared memory: position = start of the digit + keys of the digit in earlier warps + rank in the warp
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) {
+    if (chunk + r * 32 + lane < n) {
+      const uint32_t digit = (key[r] >> shift) & 0xFFu;
+      const uint32_t pos = local_start[digit] + warp_cnt[warp][digit] + rank[r];
+      sk[pos] = key[r];
+      sv[pos] = val[r];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < tile_n; i += kSortThreads) {
+    const uint32_t k = sk[i];
+    const uint32_t dst = dst_base[(k >> shift) & 0xFFu] + static_cast<uint32_t>(i);
+    keys_out[dst] = k;
+    vals_out[dst] = sv[i];
+  }
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t* __restrict__ in,
-                                                                  uint32_t* __restrict__ out, int n,
-                                                                  const uint32_t* __restrict__ tile_sums) {
-  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+// ---- exclusive scan of an array: one launch (block scan + decoupled look-back) ------------------------------------
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanBlock * kScanItems;
+
+__global__ void __launch_bounds__(kScanBlock) scan_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n,
+                                                          ScanState st, int n_tiles, uint32_t* __restrict__ d_total) {
+  const int tile = scan_take_ticket(st);
+  const int base = tile * kScanTile + threadIdx.x * kScanItems;
   uint32_t v[kScanItems];
   uint32_t s = 0;
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) {
-    v[i] = (base + i < n) ? in[base + i] : 0;
+    v[i] = (base + i < n) ? in[base + i] : 0u;
     s += v[i];
   }
-  uint32_t ex = block_exclusive_scan(s, nullptr) + tile_sums[blockIdx.x];
+  uint32_t ex = scan_exclusive(s, st, tile, n_tiles);
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) {
     if (base + i < n) out[base + i] = ex;
     ex += v[i];
   }
+  if (d_total && tile == n_tiles - 1 && threadIdx.x == kScanBlock - 1) *d_total = ex;
 }
 
 }  // namespace
+
+// ctx->scan_scratch holds kScanSlots areas of look-back words; each prepare zeroes its area with one memset
+int scan_state_prepare(peb_ctx* ctx, int n_blocks, ScanState* st, int slot) {
+  constexpr int kScanSlots = 4;
+  if (slot < 0 || slot >= kScanSlots) return fail(ctx, PEB_E_INVALID_ARG, "scan_state_prepare: slot %d", slot);
+  const size_t words = static_cast<size_t>(n_blocks) + 2;
+  DevBuf& buf = ctx->scan_scratch[slot];
+  PEB_CUDA(ctx, buf.ensure(words * sizeof(uint32_t)));
+  PEB_CUDA(ctx, cudaMemsetAsync(buf.p, 0, words * sizeof(uint32_t), ctx->stream));
+  st->words = buf.as<uint32_t>();
+  st->ticket = st->words + n_blocks;
+  st->total = st->words + n_blocks + 1;
+  return PEB_OK;
+}
 
 // out may alias in.  d_total (nullable) receives the sum of all elements.
 int exclusive_scan_u32(peb_ctx* ctx, const uint32_t* in, uint32_t* out, int n, uint32_t* d_total) {
@@ -196,15 +205,41 @@ int exclusive_scan_u32(peb_ctx* ctx, const uint32_t* in, uint32_t* out, int n, u
     return PEB_OK;
   }
   const int n_tiles = ceil_div(n, kScanTile);
-  // tile sums live at the tail of d_scratch so that callers may keep using its head
-  static_assert(sizeof(uint32_t) == 4, "");
-  PEB_CUDA(ctx, ctx->d_small.ensure(1 << 20));
-  uint32_t* tile_sums = ctx->d_small.as<uint32_t>() + (1 << 16);  // d_small: [0,256KB) results, [256KB, ...) spine
-  if (static_cast<size_t>(n_tiles) * 4 + (1 << 18) > ctx->d_small.cap)
-    return fail(ctx, PEB_E_INVALID_ARG, "exclusive_scan_u32: %d elements exceed the scan spine", n);
-  PEB_LAUNCH(ctx, scan_tile_sums_kernel, n_tiles, kScanThreads, 0, in, n, tile_sums);
-  PEB_LAUNCH(ctx, scan_spine_kernel, 1, kScanThreads, 0, tile_sums, n_tiles, d_total);
-  PEB_LAUNCH(ctx, scan_apply_kernel, n_tiles, kScanThreads, 0, in, out, n, tile_sums);
+  ScanState st;
+  PEB_TRY(scan_state_prepare(ctx, n_tiles, &st, 3));
+  PEB_LAUNCH(ctx, scan_kernel, n_tiles, kScanBlock, 0, in, out, n, st, n_tiles, d_total);
+  return PEB_OK;
+}
+
+int sort_prepare(peb_ctx* ctx, int n, int key_bits, SortPlan* plan) {
+  plan->passes = std::min(kSortMaxPasses, std::max(1, (key_bits + 7) / 8));
+  plan->items = n >= (1 << 20) ? 16 : 4;  // small inputs: more, smaller tiles so that the launch still fills the SMs
+  plan->n_tiles = std::max(1, ceil_div(n, kSortThreads * plan->items));
+  const size_t head = static_cast<size_t>(kSortMaxPasses) * kSortRadix + kSortMaxPasses;  // histograms + tickets
+  const size_t words = head + static_cast<size_t>(plan->passes) * plan->n_tiles * kSortRadix;
+  PEB_CUDA(ctx, ctx->sort_scratch.ensure(words * sizeof(uint32_t)));
+  PEB_CUDA(ctx, cudaMemsetAsync(ctx->sort_scratch.p, 0, words * sizeof(uint32_t), ctx->stream));
+  plan->hist = ctx->sort_scratch.as<uint32_t>();
+  plan->tickets = plan->hist + static_cast<size_t>(kSortMaxPasses) * kSortRadix;
+  plan->tile_state = plan->hist + head;
+  return PEB_OK;
+}
+
+int sort_pairs_counted(peb_ctx* ctx, const SortPlan& plan, uint32_t* keys, uint32_t* vals, uint32_t* keys_tmp,
+                       uint32_t* vals_tmp, int n, uint32_t** keys_out, uint32_t** vals_out) {
+  uint32_t *ki = keys, *vi = vals, *ko = keys_tmp, *vo = vals_tmp;
+  for (int p = 0; p < plan.passes && n > 1; ++p) {
+    const uint32_t* hist = plan.hist + static_cast<size_t>(p) * kSortRadix;
+    uint32_t* state = plan.tile_state + static_cast<size_t>(p) * plan.n_tiles * kSortRadix;
+    if (plan.items == 16)
+      PEB_LAUNCH(ctx, onesweep_kernel<16>, plan.n_tiles, kSortThreads, 0, ki, vi, ko, vo, n, 8 * p, hist, state, plan.tickets + p);
+    else
+      PEB_LAUNCH(ctx, onesweep_kernel<4>, plan.n_tiles, kSortThreads, 0, ki, vi, ko, vo, n, 8 * p, hist, state, plan.tickets + p);
+    std::swap(ki, ko);
+    std::swap(vi, vo);
+  }
+  *keys_out = ki;
+  *vals_out = vi;
   return PEB_OK;
 }
 
@@ -215,27 +250,11 @@ int sort_pairs(peb_ctx* ctx, uint32_t* keys, uint32_t* vals, uint32_t* keys_tmp,
   *keys_out = keys;
   *vals_out = vals;
   if (n <= 1) return PEB_OK;
-  const int passes = (key_bits + 7) / 8;
-  const int n_tiles = ceil_div(n, kSortTile);
-  const size_t hist_bytes = static_cast<size_t>(kRadix) * n_tiles * sizeof(uint32_t);
-  PEB_CUDA(ctx, ctx->d_scratch.ensure(hist_bytes));
-  uint32_t* hist = ctx->d_scratch.as<uint32_t>();
-  uint32_t *ki = keys, *vi = vals, *ko = keys_tmp, *vo = vals_tmp;
-  for (int p = 0; p < passes; ++p) {
-    const int shift = 8 * p;
-    PEB_LAUNCH(ctx, digit_histogram_kernel, n_tiles, kSortThreads, 0, ki, n, shift, hist, n_tiles);
-    PEB_TRY(exclusive_scan_u32(ctx, hist, hist, kRadix * n_tiles, nullptr));
-    PEB_LAUNCH(ctx, scatter_kernel, n_tiles, kSortThreads, 0, ki, vi, ko, vo, n, shift, hist, n_tiles);
-    uint32_t* t = ki;
-    ki = ko;
-    ko = t;
-    t = vi;
-    vi = vo;
-    vo = t;
-  }
-  *keys_out = ki;
-  *vals_out = vi;
-  return PEB_OK;
+  SortPlan plan;
+  PEB_TRY(sort_prepare(ctx, n, key_bits, &plan));
+  const int blocks = std::min(ceil_div(n, kSortThreads * 8), kSmCount * 4);
+  PEB_LAUNCH(ctx, sort_hist_kernel, blocks, kSortThreads, 0, keys, n, plan.passes, plan.hist);
+  return sort_pairs_counted(ctx, plan, keys, vals, keys_tmp, vals_tmp, n, keys_out, vals_out);
 }
 
 }  // namespace peb

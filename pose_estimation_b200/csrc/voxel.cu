@@ -4,17 +4,21 @@
 //
 //   bbox            finite min/max                                            (grid.cu)
 //   host            inv_leaf, the int64 overflow guard, min_b / div_b / divb_mul — PCL's scalars
-//   voxel_key       idx = ijk . divb_mul per finite point (float floor arithmetic of PCL);
-//                   non-finite points get a key above every voxel id
-//   radix sort      (idx, point index), stable => within a voxel the points stay in ascending
-//                   original index, the summation order the oracle defines
-//   run heads       flag + exclusive scan -> voxel ordinal -> run start table
-//   (min_pts >= 2)  keep flag + scan -> output slot
-//   centroid        one thread per voxel adds its run SEQUENTIALLY in float (bit-exact with
-//                   CentroidPoint's Vector3f += ... / n), writes (cx, cy, cz, 1)
+//   voxel_key       idx = ijk . divb_mul per finite point (float floor arithmetic of PCL); non-finite points get a key
+//                   above every voxel id; the same kernel counts the digits of every sort pass (sort_scan.cuh)
+//   radix sort      (idx, point index), stable, one kernel per 8-bit digit => within a voxel the points stay in
+//                   ascending original index, the summation order the oracle defines
+//   centroid        ONE kernel: the thread at the head of a run of equal keys adds the run SEQUENTIALLY in float
+//                   (bit-exact with CentroidPoint's Vector3f += ... / n), runs with >= min_pts points get their output
+//                   slot from a single-pass scan (block scan + decoupled look-back) in the same launch
 // Output order = ascending voxel index (x fastest) like PCL.  Algorithmic HBM bytes:
 // 16 * N_in + 16 * M_out; the sort passes are overhead on top (L2 resident at 2.3 M points).
+// Launches for the 2.33 M-point scene: 1 + 2 memsets + 1 + 4 + 1 = 9 (round 1: 31) and two host round trips (bounding
+// box for PCL's scalars, the output count).
+#include <algorithm>
+
 #include "core_math.cuh"
+#include "sort_scan.cuh"
 
 namespace peb {
 
@@ -28,64 +32,67 @@ struct VoxelParams {
 };
 
 __global__ void __launch_bounds__(256) voxel_key_kernel(const float4* __restrict__ pts, int n, VoxelParams vp,
-                                                        uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float4 p = pts[i];
-  uint32_t key = vp.sentinel;
-  if (finite3(p.x, p.y, p.z)) {
-    const int ijk0 = static_cast<int>(floorf(p.x * vp.inv[0]) - vp.min_b[0]);
-    const int ijk1 = static_cast<int>(floorf(p.y * vp.inv[1]) - vp.min_b[1]);
-    const int ijk2 = static_cast<int>(floorf(p.z * vp.inv[2]) - vp.min_b[2]);
-    key = static_cast<uint32_t>(ijk0) * vp.mul[0] + static_cast<uint32_t>(ijk1) * vp.mul[1] +
-          static_cast<uint32_t>(ijk2) * vp.mul[2];
+                                                        uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                        int passes, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[kSortMaxPasses][kSortRadix];
+  for (int i = threadIdx.x; i < kSortMaxPasses * kSortRadix; i += 256) (&sh[0][0])[i] = 0;
+  __syncthreads();
+  const int stride = gridDim.x * 256;
+  const int rounds = (n + stride - 1) / stride;  // every lane runs every round (warp votes in sort_hist_add)
+  for (int r = 0; r < rounds; ++r) {
+    const int i = r * stride + blockIdx.x * 256 + threadIdx.x;
+    const bool in = i < n;
+    uint32_t key = vp.sentinel;
+    if (in) {
+      const float4 p = pts[i];
+      if (finite3(p.x, p.y, p.z)) {
+        const int ijk0 = static_cast<int>(floorf(p.x * vp.inv[0]) - vp.min_b[0]);
+        const int ijk1 = static_cast<int>(floorf(p.y * vp.inv[1]) - vp.min_b[1]);
+        const int ijk2 = static_cast<int>(floorf(p.z * vp.inv[2]) - vp.min_b[2]);
+        key = static_cast<uint32_t>(ijk0) * vp.mul[0] + static_cast<uint32_t>(ijk1) * vp.mul[1] +
+              static_cast<uint32_t>(ijk2) * vp.mul[2];
+      }
+      keys[i] = key;
+      vals[i] = static_cast<uint32_t>(i);
+    }
+    sort_hist_add(sh, key, in, passes);
   }
-  keys[i] = key;
-  vals[i] = static_cast<uint32_t>(i);
+  __syncthreads();
+  sort_hist_flush(sh, hist, passes);
 }
 
-__global__ void __launch_bounds__(256) run_head_kernel(const uint32_t* __restrict__ sorted_keys, int n_finite,
-                                                       uint32_t* __restrict__ flags) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_finite) return;
-  flags[j] = (j == 0 || sorted_keys[j] != sorted_keys[j - 1]) ? 1u : 0u;
-}
-
-// starts[ordinal] = j for every run head; the last element also writes the end sentinel starts[n_runs]
-__global__ void __launch_bounds__(256) run_start_kernel(const uint32_t* __restrict__ flags,
-                                                        const uint32_t* __restrict__ ordinal, int n_finite,
-                                                        uint32_t* __restrict__ starts) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_finite) return;
-  if (flags[j]) starts[ordinal[j]] = static_cast<uint32_t>(j);
-  if (j == n_finite - 1) starts[ordinal[j] + flags[j]] = static_cast<uint32_t>(n_finite);  // = starts[n_runs]
-}
-
-__global__ void __launch_bounds__(256) run_keep_kernel(const uint32_t* __restrict__ starts, int n_runs, unsigned min_pts,
-                                                       uint32_t* __restrict__ keep) {
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= n_runs) return;
-  keep[v] = (starts[v + 1] - starts[v] >= min_pts) ? 1u : 0u;
-}
-
-// slot == nullptr: every run is kept and slot = v
-__global__ void __launch_bounds__(128) centroid_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ sorted_vals,
-                                                       const uint32_t* __restrict__ starts, int n_runs,
-                                                       const uint32_t* __restrict__ keep, const uint32_t* __restrict__ slot,
-                                                       float4* __restrict__ out) {
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= n_runs) return;
-  if (keep && !keep[v]) return;
-  const uint32_t s = starts[v], e = starts[v + 1];
+// One thread per sorted position (tiles in ticket order).  The thread at the head of a run of equal voxel ids walks
+// the run: count, and the SEQUENTIAL float sum of its points in sorted order = ascending original index.  A run with
+// at least min_pts points is an output point; its slot is the number of such runs before it (single-pass scan).
+__global__ void __launch_bounds__(kScanBlock) voxel_centroid_kernel(const float4* __restrict__ pts,
+                                                                    const uint32_t* __restrict__ sorted_keys,
+                                                                    const uint32_t* __restrict__ sorted_vals, int n_finite,
+                                                                    unsigned min_pts, float4* __restrict__ out,
+                                                                    ScanState st, int n_tiles) {
+  const int tile = scan_take_ticket(st);
+  const int j = tile * kScanBlock + threadIdx.x;
   float sx = 0.0f, sy = 0.0f, sz = 0.0f;
-  for (uint32_t j = s; j < e; ++j) {
-    const float4 p = pts[sorted_vals[j]];
-    sx += p.x;
-    sy += p.y;
-    sz += p.z;
+  uint32_t len = 0;
+  if (j < n_finite) {
+    const uint32_t key = sorted_keys[j];
+    if (j == 0 || sorted_keys[j - 1] != key) {
+      int e = j;
+      do {
+        const float4 p = pts[sorted_vals[e]];
+        sx += p.x;
+        sy += p.y;
+        sz += p.z;
+        ++e;
+      } while (e < n_finite && sorted_keys[e] == key);
+      len = static_cast<uint32_t>(e - j);
+    }
   }
-  const float cnt = static_cast<float>(e - s);
-  out[slot ? slot[v] : static_cast<uint32_t>(v)] = make_float4(sx / cnt, sy / cnt, sz / cnt, 1.0f);
+  const uint32_t keep = (len > 0 && len >= min_pts) ? 1u : 0u;
+  const uint32_t slot = scan_exclusive(keep, st, tile, n_tiles);
+  if (keep) {
+    const float cnt = static_cast<float>(len);
+    out[slot] = make_float4(sx / cnt, sy / cnt, sz / cnt, 1.0f);
+  }
 }
 
 __global__ void __launch_bounds__(256) copy_xyz1_kernel(const float4* __restrict__ in, int n, float4* __restrict__ out) {
@@ -142,40 +149,22 @@ int voxel_grid_device(peb_ctx* ctx, const float4* d_in, int n, float lx, float l
   PEB_CUDA(ctx, g.vals.ensure(static_cast<size_t>(n) * 4));
   PEB_CUDA(ctx, g.keys_tmp.ensure(static_cast<size_t>(n) * 4));
   PEB_CUDA(ctx, g.vals_tmp.ensure(static_cast<size_t>(n) * 4));
-  PEB_LAUNCH(ctx, voxel_key_kernel, ceil_div(n, 256), 256, 0, d_in, n, vp, g.keys.as<uint32_t>(), g.vals.as<uint32_t>());
+  SortPlan plan;
+  PEB_TRY(sort_prepare(ctx, n, key_bits, &plan));
+  const int key_blocks = std::min(ceil_div(n, 256 * 8), kSmCount * 8);
+  PEB_LAUNCH(ctx, voxel_key_kernel, key_blocks, 256, 0, d_in, n, vp, g.keys.as<uint32_t>(), g.vals.as<uint32_t>(),
+             plan.passes, plan.hist);
   uint32_t *sk = nullptr, *sv = nullptr;
-  PEB_TRY(sort_pairs(ctx, g.keys.as<uint32_t>(), g.vals.as<uint32_t>(), g.keys_tmp.as<uint32_t>(),
-                     g.vals_tmp.as<uint32_t>(), n, key_bits, &sk, &sv));
-
-  PEB_CUDA(ctx, ctx->vg_flags.ensure(static_cast<size_t>(n_finite) * 4));
-  PEB_CUDA(ctx, ctx->vg_scan.ensure(static_cast<size_t>(n_finite) * 4));
-  PEB_CUDA(ctx, ctx->vg_starts.ensure((static_cast<size_t>(n_finite) + 1) * 4));
-  uint32_t* flags = ctx->vg_flags.as<uint32_t>();
-  uint32_t* ordinal = ctx->vg_scan.as<uint32_t>();
-  uint32_t* starts = ctx->vg_starts.as<uint32_t>();
-  uint32_t* d_total = ctx->d_small.as<uint32_t>() + 32;
+  PEB_TRY(sort_pairs_counted(ctx, plan, g.keys.as<uint32_t>(), g.vals.as<uint32_t>(), g.keys_tmp.as<uint32_t>(),
+                             g.vals_tmp.as<uint32_t>(), n, &sk, &sv));
+  const int n_tiles = ceil_div(n_finite, kScanBlock);
+  ScanState st;
+  PEB_TRY(scan_state_prepare(ctx, n_tiles, &st, 0));
+  PEB_LAUNCH(ctx, voxel_centroid_kernel, n_tiles, kScanBlock, 0, d_in, sk, sv, n_finite, min_pts, d_out, st, n_tiles);
   uint32_t* h_total = ctx->h_small.as<uint32_t>() + 32;
-  PEB_LAUNCH(ctx, run_head_kernel, ceil_div(n_finite, 256), 256, 0, sk, n_finite, flags);
-  PEB_TRY(exclusive_scan_u32(ctx, flags, ordinal, n_finite, d_total));
-  PEB_LAUNCH(ctx, run_start_kernel, ceil_div(n_finite, 256), 256, 0, flags, ordinal, n_finite, starts);
-  PEB_CUDA(ctx, cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  PEB_CUDA(ctx, cudaMemcpyAsync(h_total, st.total, 4, cudaMemcpyDeviceToHost, ctx->stream));
   PEB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  const int n_runs = static_cast<int>(*h_total);
-  size_t n_out = static_cast<size_t>(n_runs);
-  const uint32_t* keep = nullptr;
-  const uint32_t* slot = nullptr;
-  if (min_pts >= 2) {
-    // flags / ordinal are free again: reuse them as keep / slot
-    PEB_LAUNCH(ctx, run_keep_kernel, ceil_div(n_runs, 256), 256, 0, starts, n_runs, min_pts, flags);
-    PEB_TRY(exclusive_scan_u32(ctx, flags, ordinal, n_runs, d_total));
-    PEB_CUDA(ctx, cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PEB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    n_out = static_cast<size_t>(*h_total);
-    keep = flags;
-    slot = ordinal;
-  }
-  PEB_LAUNCH(ctx, centroid_kernel, ceil_div(n_runs, 128), 128, 0, d_in, sv, starts, n_runs, keep, slot, d_out);
-  *out_n = n_out;
+  *out_n = static_cast<size_t>(*h_total);
   return PEB_OK;
 }
 
