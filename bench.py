@@ -779,6 +779,38 @@ def preprocessing_stages(ctx, c2, torch, stream, flush, pcl, lib):
     tset()
     t_set = timed(tset)
 
+    # ---- the brute-force FP32 validator (north star (2)) and the grid search on the same queries (C2: the model under
+    # the initial guess against the down-sampled scene), through the host-buffer C ABI (uploads / downloads inside)
+    g4 = np.asarray(c2.guess, np.float64)
+    q_host = np.ascontiguousarray(c2.source, np.float32).copy()
+    q_host[:, :3] = (c2.source[:, :3].astype(np.float64) @ g4[:3, :3].T + g4[:3, 3]).astype(np.float32)
+    h_q = torch.from_numpy(q_host).pin_memory()
+    nq = h_q.shape[0]
+    h_idx = [torch.empty(nq, dtype=torch.int32).pin_memory() for _ in range(2)]
+    h_d2 = [torch.empty(nq, dtype=torch.float32).pin_memory() for _ in range(2)]
+
+    def nn_brute():
+        ctx.check(lib.peb_nn_search_bruteforce(ctx.handle, h_q.data_ptr(), nq, 16, h_idx[0].data_ptr(), h_d2[0].data_ptr()))
+
+    def nn_grid():
+        ctx.check(lib.peb_nn_search(ctx.handle, h_q.data_ptr(), nq, 16, h_idx[1].data_ptr(), h_d2[1].data_ptr()))
+
+    nn_brute()
+    nn_grid()
+    t_brute = timed(nn_brute, 5)
+    t_grid = timed(nn_grid, 5)
+    nn_same = bool(torch.equal(h_d2[0], h_d2[1]) and torch.equal(h_idx[0], h_idx[1]))
+    pairs = float(nq) * float(n_ds)
+    fp32_instr_peak = 148 * 128 * 1.965e9  # one FADD / FMUL per lane and clock (no FMA: the distance is PCL's unfused expression)
+    brute_stage = {
+        "what": "nn_bruteforce_kernel, every query against every target point (8 FP32 instructions per pair: 3 FADD + 3 FMUL + "
+                "2 FADD, unfused, + 1 FMNMX), host buffers in and out",
+        "n_queries": int(nq), "n_target": int(n_ds), "ms_median": statistics.median(t_brute), "ms_min": min(t_brute),
+        "fp32_instr_per_s": 8.0 * pairs / (statistics.median(t_brute) * 1e-3),
+        "fp32_pipe_frac": 8.0 * pairs / (statistics.median(t_brute) * 1e-3) / fp32_instr_peak,
+        "fp32_pipe_peak": "148 SMs x 128 lanes x 1.965 GHz = 3.72e13 FADD|FMUL per s",
+        "grid_search_same_queries_ms": statistics.median(t_grid), "identical_to_grid_search": nn_same}
+
     # ---- configs[2] (C3) and configs[4] (C5): point-to-plane aligns with the normals estimated on the device ----
     d_nrm4 = torch.zeros((n_ds, 4), dtype=torch.float32, device=dev)
     d_model = torch.from_numpy(np.ascontiguousarray(c2.source)).to(dev)
@@ -862,6 +894,7 @@ def preprocessing_stages(ctx, c2, torch, stream, flush, pcl, lib):
                         "algorithmic_bytes": nb, "achieved_gbs": nb / (statistics.median(t_nrm) * 1e-3) / 1e9},
         "target_grid_build": {"n": int(n_ds), "ms_median": statistics.median(t_set), "ms_min": min(t_set),
                               "algorithmic_bytes": gb, "achieved_gbs": gb / (statistics.median(t_set) * 1e-3) / 1e9},
+        "nn_validator_bruteforce": brute_stage,
         "nan_removal": {"n_in": int(n_in), "n_out": int(n_clean), "ms_median": statistics.median(t_clean), "ms_min": min(t_clean),
                         "algorithmic_bytes": 16 * (n_in + n_clean),
                         "achieved_gbs": 16 * (n_in + n_clean) / (statistics.median(t_clean) * 1e-3) / 1e9},

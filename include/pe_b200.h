@@ -230,6 +230,57 @@ PEB_API int peb_cvicp_register(peb_ctx* ctx, const float* model_xyzn, size_t n_m
                                size_t n_scene, const peb_cvicp_params* params, double* poses, size_t n_poses,
                                double* out_residuals);
 
+/* ---- cv::ppf_match_3d::PPF3DDetector: trainModel / match (coarse matching) -------------
+ * What the reference runs in front of the refinement slot:
+ *   detectors_[name] = cv::ppf_match_3d::PPF3DDetector(0.03, 0.03, 40); detectors_[name].trainModel(model)
+ *                                                     (pose_estimation/src/opencv_surface_match.cpp:37-51)
+ *   detectors_[object].match(pc_scene_normals, results, 1.0, 0.03)   (pose_estimation/src/opencv_surface_match.cpp:65)
+ * [CV] opencv_contrib/modules/surface_matching/src/ppf_match_3d.cpp, ppf_helpers.cpp, pose_3d.cpp (not in the
+ * reference tree nor in this image: restated from recollection, parity unpinned — DESIGN.md section 11).
+ * train: both clouds are n x 6 float rows (x y z nx ny nz).  The model is sampled on a 1/step lattice of its bounding
+ * box (samplePCByQuantization), every ordered pair of sampled points gives a four-component point-pair feature
+ * (three angles quantised by 2 pi / num_angles, the distance by step * diameter) and the pair's planar angle alpha.
+ * match: the scene is sampled the same way (relative_scene_distance); every 1/relative_scene_sample_step-th sampled
+ * point is a reference point whose pairs with all other sampled points vote for (model reference, alpha bin); the
+ * winner gives one pose per reference point, the poses are clustered greedily (position / rotation thresholds) and
+ * averaged.  results: clustered poses, most votes first.
+ * ONE DELIBERATE DIFFERENCE from OpenCV: a scene pair votes for the model pairs with the SAME quantised feature;
+ * OpenCV additionally counts the pairs that merely share a bucket of its MurmurHash table (hash-collision votes,
+ * walked without a key comparison) — noise that depends on the hash variant and cannot be restated. */
+typedef struct peb_ppf_params {
+  double relative_sampling_step;  /* PPF3DDetector(0.03, ., .)                                         */
+  double relative_distance_step;  /* PPF3DDetector(., 0.03, .) — stored and never used by OpenCV either */
+  double num_angles;              /* PPF3DDetector(., ., 40)                                            */
+  double position_threshold;      /* setSearchParams: < 0 -> relative_sampling_step (an ABSOLUTE length, as upstream) */
+  double rotation_threshold;      /* setSearchParams: < 0 -> (360 / angle_step) / 180 * pi              */
+  int32_t use_weighted_avg;       /* setSearchParams(., ., useWeightedClustering)                       */
+  int32_t reserved;
+} peb_ppf_params;
+/* cv::ppf_match_3d::Pose3D */
+typedef struct peb_ppf_pose {
+  double pose[16];       /* row-major 4 x 4 (cv::Matx44d::val): model -> scene */
+  double q[4];           /* w x y z */
+  double t[3];
+  double angle;          /* rotation angle of pose (from the trace) */
+  double alpha;          /* the winning alpha bin's angle           */
+  double residual;       /* filled by the ICP afterwards            */
+  uint64_t num_votes;
+  uint64_t model_index;  /* the winning model reference point       */
+} peb_ppf_pose;
+typedef struct peb_ppf_model peb_ppf_model;
+PEB_API void peb_ppf_params_default(peb_ppf_params* p); /* (0.03, 0.03, 40), thresholds -1, plain average */
+/* trainModel: the trained detector lives on ctx's device and belongs to ctx (destroy it before the context) */
+PEB_API int peb_ppf_train(peb_ctx* ctx, const float* model_xyzn, size_t n_model, const peb_ppf_params* params,
+                          peb_ppf_model** out);
+PEB_API void peb_ppf_model_destroy(peb_ppf_model* m);
+/* sampled model points (rows of 6 floats, lattice order); out6 nullable */
+PEB_API int peb_ppf_model_sampled(const peb_ppf_model* m, float* out6, size_t cap, size_t* out_n);
+/* match: at most cap clustered poses are copied to results, *out_n = how many there are.
+ * raw / cap_raw / out_n_raw (nullable): the un-clustered pose of every scene reference point, in reference order. */
+PEB_API int peb_ppf_match(peb_ctx* ctx, const peb_ppf_model* m, const float* scene_xyzn, size_t n_scene,
+                          double relative_scene_sample_step, double relative_scene_distance, peb_ppf_pose* results,
+                          size_t cap, size_t* out_n, peb_ppf_pose* raw, size_t cap_raw, size_t* out_n_raw);
+
 /* ---- pcl::NormalEstimation<PointXYZ,Normal>::compute  [PCL] features/.../impl/normal_3d.hpp */
 /* out_normal8: n x 8 floats = pcl::Normal memory image (nx ny nz 0 | curvature 0 0 0). */
 PEB_API int peb_normals_knn(peb_ctx* ctx, const void* pts, size_t n, size_t stride, int k,

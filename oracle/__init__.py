@@ -111,6 +111,32 @@ def cvicp_params(iterations=250, tolerance=0.005, rejection_scale=2.5, num_level
     return CvIcpParams(int(iterations), int(num_levels), float(tolerance), float(rejection_scale))
 
 
+class PpfParams(C.Structure):
+    """peb_ppf_params (include/pe_b200.h)."""
+
+    _fields_ = [("relative_sampling_step", C.c_double), ("relative_distance_step", C.c_double), ("num_angles", C.c_double),
+                ("position_threshold", C.c_double), ("rotation_threshold", C.c_double), ("use_weighted_avg", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class PpfPose(C.Structure):
+    """peb_ppf_pose = cv::ppf_match_3d::Pose3D (include/pe_b200.h)."""
+
+    _fields_ = [("pose", C.c_double * 16), ("q", C.c_double * 4), ("t", C.c_double * 3), ("angle", C.c_double),
+                ("alpha", C.c_double), ("residual", C.c_double), ("num_votes", C.c_uint64), ("model_index", C.c_uint64)]
+
+    @property
+    def matrix(self) -> np.ndarray:
+        return np.array(self.pose, np.float64).reshape(4, 4)
+
+
+def ppf_params(relative_sampling_step=0.03, relative_distance_step=0.03, num_angles=40.0, position_threshold=-1.0,
+               rotation_threshold=-1.0, use_weighted_avg=False) -> PpfParams:
+    """cv::ppf_match_3d::PPF3DDetector(0.03, 0.03, 40) as the reference constructs it (opencv_surface_match.cpp:45)."""
+    return PpfParams(float(relative_sampling_step), float(relative_distance_step), float(num_angles), float(position_threshold),
+                     float(rotation_threshold), int(bool(use_weighted_avg)), 0)
+
+
 DBL_MAX = float(np.finfo(np.float64).max)
 
 
@@ -209,6 +235,24 @@ class Oracle:
         L.orc_sac_plane.restype = C.c_int
         L.orc_sac_plane.argtypes = [_vp, _sz, _sz, _vp, C.c_int, _vp, _vp, _vp, _vp]
         L.orc_cvicp_register.argtypes = [_vp, _sz, _vp, _sz, _vp, _vp, _sz, _vp]
+        L.orc_ppf_train.restype = _vp
+        L.orc_ppf_train.argtypes = [_vp, _sz, _vp]
+        L.orc_ppf_destroy.argtypes = [_vp]
+        L.orc_ppf_model_size.restype = _sz
+        L.orc_ppf_model_size.argtypes = [_vp]
+        L.orc_ppf_model_sampled.argtypes = [_vp, _vp]
+        L.orc_ppf_distance_step.restype = C.c_double
+        L.orc_ppf_distance_step.argtypes = [_vp]
+        L.orc_ppf_table_size.restype = _sz
+        L.orc_ppf_table_size.argtypes = [_vp]
+        L.orc_ppf_match.restype = _sz
+        L.orc_ppf_match.argtypes = [_vp, _vp, _sz, C.c_double, C.c_double, _vp, _sz, _vp, _vp, _sz, _vp, _sz, _vp]
+        L.orc_ppf_feature.argtypes = [_vp] * 6
+        L.orc_ppf_transform_rt.argtypes = [_vp] * 4
+        L.orc_ppf_sample.restype = _sz
+        L.orc_ppf_sample.argtypes = [_vp, _sz, C.c_float, _vp, _sz]
+        L.orc_ppf_cluster.restype = _sz
+        L.orc_ppf_cluster.argtypes = [_vp, _vp, _sz, _vp, _sz]
         L.orc_mt19937_nth.restype = C.c_uint32
         L.orc_mt19937_nth.argtypes = [C.c_uint32, C.c_uint32]
 
@@ -274,6 +318,32 @@ class Oracle:
                                   P.shape[0], res.ctypes.data)
         return P.reshape(-1, 4, 4), res
 
+    # ---- cv::ppf_match_3d::PPF3DDetector ------------------------------------------------------
+    def ppf_train(self, model6: np.ndarray, params: "PpfParams | None" = None) -> "OraclePpf":
+        return OraclePpf(self, model6, params or ppf_params())
+
+    def ppf_sample(self, pc6: np.ndarray, step: float) -> np.ndarray:
+        """samplePCByQuantization over the cloud's own bounding box."""
+        p = np.ascontiguousarray(pc6, np.float32)
+        out = np.empty((p.shape[0], 6), np.float32)
+        n = self.L.orc_ppf_sample(p.ctypes.data, p.shape[0], float(step), out.ctypes.data, out.shape[0])
+        return out[:n].copy()
+
+    def ppf_feature(self, p1, n1, p2, n2):
+        """(f[4], alpha) of the ordered pair, double."""
+        a = [np.ascontiguousarray(v, np.float64) for v in (p1, n1, p2, n2)]
+        f = np.zeros(4, np.float64)
+        al = C.c_double(0)
+        self.L.orc_ppf_feature(a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data, f.ctypes.data, C.byref(al))
+        return f, al.value
+
+    def ppf_transform_rt(self, p1, n1):
+        a = [np.ascontiguousarray(v, np.float64) for v in (p1, n1)]
+        R = np.zeros(9, np.float64)
+        t = np.zeros(3, np.float64)
+        self.L.orc_ppf_transform_rt(a[0].ctypes.data, a[1].ctypes.data, R.ctypes.data, t.ctypes.data)
+        return R.reshape(3, 3), t
+
     def mt19937_nth(self, seed: int, nth: int) -> int:
         return int(self.L.orc_mt19937_nth(seed, nth))
 
@@ -293,6 +363,59 @@ class Oracle:
 
     def max_threads(self) -> int:
         return int(self.L.orc_max_threads())
+
+
+class OraclePpf:
+    """A trained detector (PPF3DDetector::trainModel)."""
+
+    def __init__(self, orc: Oracle, model6: np.ndarray, params: "PpfParams"):
+        self.o = orc
+        m = np.ascontiguousarray(model6, np.float32)
+        assert m.ndim == 2 and m.shape[1] == 6
+        self.params = params
+        self.h = orc.L.orc_ppf_train(m.ctypes.data, m.shape[0], C.byref(params))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.o.L.orc_ppf_destroy(self.h)
+            self.h = None
+
+    @property
+    def n(self) -> int:
+        return int(self.o.L.orc_ppf_model_size(self.h))
+
+    @property
+    def distance_step(self) -> float:
+        return float(self.o.L.orc_ppf_distance_step(self.h))
+
+    @property
+    def table_size(self) -> int:
+        return int(self.o.L.orc_ppf_table_size(self.h))
+
+    def sampled(self) -> np.ndarray:
+        out = np.empty((self.n, 6), np.float32)
+        self.o.L.orc_ppf_model_sampled(self.h, out.ctypes.data)
+        return out
+
+    def match(self, scene6: np.ndarray, relative_scene_sample_step: float = 1.0, relative_scene_distance: float = 0.03):
+        """-> (clustered poses, raw per-reference poses, sampled scene)."""
+        sc = np.ascontiguousarray(scene6, np.float32)
+        cap = sc.shape[0]
+        raw = (PpfPose * cap)()
+        res = (PpfPose * cap)()
+        samp = np.empty((cap, 6), np.float32)
+        n_raw = C.c_size_t(0)
+        n_s = C.c_size_t(0)
+        n = self.o.L.orc_ppf_match(self.h, sc.ctypes.data, sc.shape[0], float(relative_scene_sample_step),
+                                   float(relative_scene_distance), raw, cap, C.byref(n_raw), res, cap, samp.ctypes.data, cap,
+                                   C.byref(n_s))
+        return list(res[:n]), list(raw[: n_raw.value]), samp[: n_s.value].copy()
+
+    def cluster(self, poses):
+        arr = (PpfPose * len(poses))(*poses)
+        out = (PpfPose * max(len(poses), 1))()
+        n = self.o.L.orc_ppf_cluster(self.h, arr, len(poses), out, len(poses))
+        return list(out[:n])
 
 
 class OracleIcp:

@@ -189,7 +189,7 @@ PEB_API void peb_ctx_destroy(peb_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->d_small, &ctx->d_scratch, &ctx->d_stage, &ctx->tgt_raw, &ctx->tgt_nrm_raw, &ctx->src, &ctx->work, &ctx->slack, &ctx->anchors, &ctx->dbg,
                     &ctx->corr_idx, &ctx->corr_d2, &ctx->partials, &ctx->state, &ctx->trace, &ctx->d_guesses,
                     &ctx->d_results, &ctx->d_aligned, &ctx->vg_in, &ctx->vg_out, &ctx->vg_flags, &ctx->vg_scan,
-                    &ctx->vg_starts, &ctx->nrm_in, &ctx->nrm_out, &ctx->nrm_left, &ctx->nn_q, &ctx->nn_idx, &ctx->nn_d2, &ctx->epochs, &ctx->cv_arena};
+                    &ctx->vg_starts, &ctx->nrm_in, &ctx->nrm_out, &ctx->brute_keys, &ctx->nn_q, &ctx->nn_idx, &ctx->nn_d2, &ctx->epochs, &ctx->cv_arena};
   for (DevBuf* b : bufs) b->release();
   ctx->sort_scratch.release();
   for (DevBuf& b : ctx->scan_scratch) b.release();

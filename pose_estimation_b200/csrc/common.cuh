@@ -183,7 +183,7 @@ struct peb_ctx {
   peb::Grid aux_grid;
   peb::DevBuf vg_in, vg_out, vg_flags, vg_scan, vg_starts;
   peb::DevBuf nrm_in, nrm_out;
-  peb::DevBuf nrm_left;      // normals: count + sorted positions of the queries the warp kernel left to the general one
+  peb::DevBuf brute_keys;    // brute-force validator: one 64-bit (distance, index) key per query, merged over the target segments with atomicMin
   peb::DevBuf cv_arena;      // cv::ppf_match_3d::ICP mode: all device buffers of a call
   peb::PinnedBuf h_cv;       // cv ICP mode: pose tables (two, alternating) + accumulator read-back
   peb::PinnedBuf h_sac;      // plane RANSAC: sample indices / coordinates, candidate planes, counts, moment records

@@ -155,141 +155,141 @@ __global__ void normals_knn_kernel(const GridView g, int k, float vx, float vy, 
   reinterpret_cast<float4*>(o)[1] = make_float4(res[4], res[5], res[6], res[7]);
 }
 
-// ---- k <= 32: a warp per query --------------------------------------------------------------------------------
-constexpr int kNrmWarps = 4;  // warps per block
+// ---- k <= 32: one thread per query, the candidate list in REGISTERS ----------------------------------------------
+// K slots (d2, position), ascending.  An insertion is branch-free — every slot takes its left neighbour, the new
+// candidate or itself (one compare + four selects per slot, all slots independent) — so the 32 queries of a warp, which
+// are neighbours in the cell-sorted cloud and walk the same grid rows, stay in lock-step where the shared-memory
+// insertion sort of the general kernel serialises their different shift lengths.  A list for k < K neighbours keeps
+// K - k sentinels (d2 = -1, never displaced) in front, so that the k-th neighbour is always slot K - 1.
+template <int K>
+struct RegList {
+  float d[K];
+  int j[K];
+};
 
-__device__ __forceinline__ unsigned long long warp_sort32(unsigned long long key, int lane) {
+// candidates arrive in ascending position (ring 1: rows in ascending (z, y), cells in ascending x), so a candidate that
+// ties with a listed one has the larger position and goes behind it: strict < on the distance is the (d2, position) order
+template <int K>
+__device__ __forceinline__ void reglist_insert_ascending(RegList<K>& l, float x, int xj) {
+  if (!(x < l.d[K - 1])) return;
 #pragma unroll
-  for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
-    for (int j = size >> 1; j > 0; j >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, j);
-      const bool up = (lane & size) == 0;  // (size == 32: always ascending)
-      const bool low = (lane & j) == 0;
-      key = (low == up) ? (other < key ? other : key) : (other > key ? other : key);
-    }
+  for (int i = K - 1; i >= 1; --i) {
+    const bool shift = x < l.d[i - 1];
+    const bool here = x < l.d[i];
+    l.j[i] = shift ? l.j[i - 1] : (here ? xj : l.j[i]);
+    l.d[i] = shift ? l.d[i - 1] : (here ? x : l.d[i]);
   }
-  return key;
+  const bool here = x < l.d[0];
+  l.j[0] = here ? xj : l.j[0];
+  l.d[0] = here ? x : l.d[0];
 }
 
-// best (ascending over the lanes) <- the 32 smallest of best and chunk (ascending over the lanes), ascending
-__device__ __forceinline__ unsigned long long warp_merge32(unsigned long long best, unsigned long long chunk, int lane) {
-  const unsigned long long rev = __shfl_sync(0xFFFFFFFFu, chunk, 31 - lane);
-  unsigned long long m = rev < best ? rev : best;  // a bitonic sequence holding the 32 smallest
+// any arrival order (shells of ring >= 2): the full (d2, position) comparison
+template <int K>
+__device__ __forceinline__ void reglist_insert_any(RegList<K>& l, float x, int xj) {
+  auto less = [](float a, int aj, float b, int bj) { return a < b || (a == b && static_cast<unsigned>(aj) < static_cast<unsigned>(bj)); };
+  if (!less(x, xj, l.d[K - 1], l.j[K - 1])) return;
 #pragma unroll
-  for (int j = 16; j > 0; j >>= 1) {
-    const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, m, j);
-    m = ((lane & j) == 0) ? (other < m ? other : m) : (other > m ? other : m);
+  for (int i = K - 1; i >= 1; --i) {
+    const bool shift = less(x, xj, l.d[i - 1], l.j[i - 1]);
+    const bool here = less(x, xj, l.d[i], l.j[i]);
+    l.j[i] = shift ? l.j[i - 1] : (here ? xj : l.j[i]);
+    l.d[i] = shift ? l.d[i - 1] : (here ? x : l.d[i]);
   }
-  return m;
+  const bool here = less(x, xj, l.d[0], l.j[0]);
+  l.j[0] = here ? xj : l.j[0];
+  l.d[0] = here ? x : l.d[0];
 }
 
-__global__ void __launch_bounds__(32 * kNrmWarps) normals_warp_kernel(const GridView g, int k, float vx, float vy, float vz,
-                                                                    float* __restrict__ out8, int32_t* __restrict__ out_nn,
-                                                                    int* __restrict__ left, int* __restrict__ left_n) {
-  __shared__ float s_accu[kNrmWarps][32][9];
-  __shared__ uint32_t s_row_start[kNrmWarps][9];
-  __shared__ uint32_t s_row_prefix[kNrmWarps][10];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int q0 = (blockIdx.x * kNrmWarps + warp) * 32;
-  if (q0 >= g.n) return;
-  const int nq = min(32, g.n - q0);
-  // lane a < 9 owns covariance sum a: xx xy xz yy yz zz x y z = u * v with u, v picked from (x, y, z, 1)
-  const int sel_u = lane < 3 ? 0 : (lane < 5 ? 1 : (lane == 5 ? 2 : lane - 6));
-  const int sel_v = lane < 3 ? lane : (lane < 5 ? lane - 2 : (lane == 5 ? 2 : 3));
-  bool mine_ok = false;  // lane q: query q0 + q was finished here
-  int last_cx = -1, last_cy = -1, last_cz = -1;
-  uint32_t total = 0;
-  for (int qi = 0; qi < nq; ++qi) {
-    const int q = q0 + qi;
-    const float4 p = g.pts[q];
-    const int cx = grid_coord(p.x, g.ox, g.inv_h, g.dx);
-    const int cy = grid_coord(p.y, g.oy, g.inv_h, g.dy);
-    const int cz = grid_coord(p.z, g.oz, g.inv_h, g.dz);
-    if (cx != last_cx || cy != last_cy || cz != last_cz) {  // (warp-uniform) the 9 grid rows of the 3 x 3 x 3 block
-      last_cx = cx;
-      last_cy = cy;
-      last_cz = cz;
-      uint32_t rs = 0, len = 0;
-      if (lane < 9) {
-        const int y = cy + lane % 3 - 1, z = cz + lane / 3 - 1;
-        if (y >= 0 && y < g.dy && z >= 0 && z < g.dz) {
-          const long long base = (static_cast<long long>(z) * g.dy + y) * g.dx;
-          rs = g.cell_start[base + max(cx - 1, 0)];
-          len = g.cell_start[base + min(cx + 1, g.dx - 1) + 1] - rs;
-        }
-      }
-      uint32_t inc = len;
+template <int K, bool ASC>
+__device__ __forceinline__ void reglist_scan_range(const GridView& g, uint32_t s, uint32_t e, float qx, float qy, float qz,
+                                                   RegList<K>& l) {
+  for (uint32_t j = s; j < e; ++j) {
+    const float4 p = g.pts[j];
+    const float d2 = l2_simple(qx, qy, qz, p.x, p.y, p.z);
+    if (ASC) reglist_insert_ascending<K>(l, d2, static_cast<int>(j));
+    else reglist_insert_any<K>(l, d2, static_cast<int>(j));
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(128, 4) normals_reglist_kernel(const GridView g, int k, float vx, float vy, float vz,
+                                                                 float* __restrict__ out8, int32_t* __restrict__ out_nn) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= g.n) return;
+  const float4 p = g.pts[q];
+  const int orig = __float_as_int(p.w);
+  const int kk = min(k, g.n);  // neighbours wanted
+  RegList<K> l;
 #pragma unroll
-      for (int o = 1; o < 16; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-        if (lane >= o) inc += t;
+  for (int i = 0; i < K; ++i) {
+    const bool sentinel = i < K - kk;
+    l.d[i] = sentinel ? -1.0f : pos_inf();
+    l.j[i] = -1;
+  }
+  const int cx = grid_coord(p.x, g.ox, g.inv_h, g.dx);
+  const int cy = grid_coord(p.y, g.oy, g.inv_h, g.dy);
+  const int cz = grid_coord(p.z, g.oz, g.inv_h, g.dz);
+  {  // ring 1: the 3 x 3 x 3 block, rows in ascending position
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
+    for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dz - 1); ++z)
+      for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dy - 1); ++y) {
+        const long long base = (static_cast<long long>(z) * g.dy + y) * g.dx;
+        reglist_scan_range<K, true>(g, g.cell_start[base + x0], g.cell_start[base + x1 + 1], p.x, p.y, p.z, l);
       }
-      __syncwarp();
-      if (lane < 9) {
-        s_row_start[warp][lane] = rs;
-        s_row_prefix[warp][lane] = inc - len;
-      }
-      if (lane == 8) s_row_prefix[warp][9] = inc;
-      total = __shfl_sync(0xFFFFFFFFu, inc, 8);
-      __syncwarp();
-    }
-    unsigned long long best = ~0ull;  // lane i: the i-th nearest so far
-    unsigned long long kth = ~0ull;   // the k-th nearest so far (lane k - 1), known to every lane
-    for (uint32_t c0 = 0; c0 < total; c0 += 32) {
-      const uint32_t c = c0 + lane;
-      unsigned long long key = ~0ull;
-      if (c < total) {
-        int r = 0;
-#pragma unroll
-        for (int t = 1; t < 9; ++t) r += (c >= s_row_prefix[warp][t]) ? 1 : 0;
-        const uint32_t j = s_row_start[warp][r] + (c - s_row_prefix[warp][r]);
-        const float4 t4 = g.pts[j];
-        key = knn_key(l2_simple(p.x, p.y, p.z, t4.x, t4.y, t4.z), static_cast<int>(j));
-      }
-      if (!__any_sync(0xFFFFFFFFu, key < kth)) continue;
-      best = warp_merge32(best, warp_sort32(key, lane), lane);
-      kth = __shfl_sync(0xFFFFFFFFu, best, k - 1);
-    }
+  }
+  for (int r = 1;; ++r) {
     bool covers_all;
-    const float b2 = grid_ring_bound2(g, p.x, p.y, p.z, cx, cy, cz, 1, covers_all);
-    const bool full = kth != ~0ull;
-    if (!(full && (covers_all || __uint_as_float(static_cast<unsigned>(kth >> 32)) <= b2))) {
-      // not proven by the 3 x 3 x 3 block (or fewer than k points in it): the general kernel finishes this query
-      if (lane == 0) left[atomicAdd(left_n, 1)] = q;
-      continue;
+    const float b2 = grid_ring_bound2(g, p.x, p.y, p.z, cx, cy, cz, r, covers_all);
+    if (covers_all || (l.j[K - 1] >= 0 && l.d[K - 1] <= b2)) break;
+    // the shell of ring r + 1 (sparse borders only)
+    const int rr = r + 1, w = 2 * rr + 1;
+    const int x0 = max(cx - rr, 0), x1 = min(cx + rr, g.dx - 1);
+    for (int row = 0; row < w * w; ++row) {
+      const int oy = row % w - rr, oz = row / w - rr;
+      const int y = cy + oy, z = cz + oz;
+      if (y < 0 || y >= g.dy || z < 0 || z >= g.dz) continue;
+      const long long base = (static_cast<long long>(z) * g.dy + y) * g.dx;
+      if (oy == -rr || oy == rr || oz == -rr || oz == rr) {
+        reglist_scan_range<K, false>(g, g.cell_start[base + x0], g.cell_start[base + x1 + 1], p.x, p.y, p.z, l);
+      } else {
+        if (cx - rr >= 0) reglist_scan_range<K, false>(g, g.cell_start[base + cx - rr], g.cell_start[base + cx - rr + 1], p.x, p.y, p.z, l);
+        if (cx + rr < g.dx) reglist_scan_range<K, false>(g, g.cell_start[base + cx + rr], g.cell_start[base + cx + rr + 1], p.x, p.y, p.z, l);
+      }
     }
-    // the neighbours in list order: lane i < k holds neighbour i
-    float nx = 0.f, ny = 0.f, nz = 0.f;
-    if (lane < k) {
-      const float4 c4 = g.pts[knn_key_pos(best)];
-      nx = c4.x;
-      ny = c4.y;
-      nz = c4.z;
-      if (out_nn) out_nn[static_cast<size_t>(__float_as_int(p.w)) * k + lane] = __float_as_int(c4.w);
-    }
-    float acc = 0.0f;
-    for (int i = 0; i < k; ++i) {
-      const float x = __shfl_sync(0xFFFFFFFFu, nx, i), y = __shfl_sync(0xFFFFFFFFu, ny, i), z = __shfl_sync(0xFFFFFFFFu, nz, i);
-      const float u = sel_u == 0 ? x : (sel_u == 1 ? y : z);
-      const float v = sel_v == 0 ? x : (sel_v == 1 ? y : (sel_v == 2 ? z : 1.0f));
-      acc += u * v;  // (a product with 1.0f is exact: sums 6..8 add the coordinate itself, like accu[6] += x)
-    }
-    if (lane < 9) s_accu[warp][qi][lane] = acc;
-    if (lane == qi) mine_ok = true;
   }
-  __syncwarp();
-  if (mine_ok) {  // one query per lane: covariance -> eigen33 -> flip -> pcl::Normal
-    const float4 p = g.pts[q0 + lane];
-    float accu[9];
+  // the neighbours in list order: slots K - kk .. K - 1 ([PCL] normal_3d.hpp: computePointNormal over nn_indices)
+  int count = 0;
+  float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int a = 0; a < 9; ++a) accu[a] = s_accu[warp][lane][a];
-    float res[8];
-    normal_from_accu(accu, k, p.x, p.y, p.z, vx, vy, vz, res);
-    float4* o = reinterpret_cast<float4*>(out8 + 8 * static_cast<size_t>(__float_as_int(p.w)));
-    o[0] = make_float4(res[0], res[1], res[2], res[3]);
-    o[1] = make_float4(res[4], res[5], res[6], res[7]);
+  for (int s = 0; s < K; ++s) {
+    if (l.j[s] >= 0) {
+      const float4 c = g.pts[l.j[s]];
+      if (out_nn) out_nn[static_cast<size_t>(orig) * k + (s - (K - kk))] = __float_as_int(c.w);
+      accu[0] += c.x * c.x;
+      accu[1] += c.x * c.y;
+      accu[2] += c.x * c.z;
+      accu[3] += c.y * c.y;
+      accu[4] += c.y * c.z;
+      accu[5] += c.z * c.z;
+      accu[6] += c.x;
+      accu[7] += c.y;
+      accu[8] += c.z;
+      ++count;
+    }
   }
+  if (count < 3) return;  // stays NaN ([PCL] normal_3d.h: computePointNormal fails below 3 points)
+  float res[8];
+  normal_from_accu(accu, count, p.x, p.y, p.z, vx, vy, vz, res);
+  float4* o = reinterpret_cast<float4*>(out8 + 8 * static_cast<size_t>(orig));
+  o[0] = make_float4(res[0], res[1], res[2], res[3]);
+  o[1] = make_float4(res[4], res[5], res[6], res[7]);
+}
+
+template <int K>
+int launch_reglist(peb_ctx* ctx, const GridView& g, int k, const float vp[3], float* d_out8, int32_t* d_out_nn) {
+  PEB_LAUNCH(ctx, normals_reglist_kernel<K>, ceil_div(g.n, 128), 128, 0, g, k, vp[0], vp[1], vp[2], d_out8, d_out_nn);
+  return PEB_OK;
 }
 
 }  // namespace
@@ -301,24 +301,19 @@ int normals_knn_device(peb_ctx* ctx, const float4* d_in, int n, int k, const flo
   if (n == 0) return PEB_OK;
   PEB_LAUNCH(ctx, normals_fill_nan_kernel, ceil_div(n, 256), 256, 0, d_out8, n);
   if (d_out_nn) PEB_CUDA(ctx, cudaMemsetAsync(d_out_nn, 0xFF, static_cast<size_t>(n) * k * sizeof(int32_t), ctx->stream));
-  const float occupancy = fmaxf(2.0f, static_cast<float>(k) / 3.0f);
+  // cell edge: the k-th neighbour of a surface point lies sqrt(k / (pi * occupancy)) cells away and the 3 x 3 x 3 block
+  // proves everything within one cell of the query's own cell, so k / 2.4 points per occupied cell (0.87 cells) lets
+  // ring 1 settle all but the border queries at ~9 * k / 2.4 candidates each
+  const float occupancy = fmaxf(2.0f, static_cast<float>(k) / 2.4f);
   PEB_TRY(grid_build(ctx, &ctx->aux_grid, d_in, nullptr, n, occupancy));
   const GridView& g = ctx->aux_grid.view;
   if (g.n == 0) return PEB_OK;
+  if (k <= 8) return launch_reglist<8>(ctx, g, k, vp, d_out8, d_out_nn);
+  if (k <= 16) return launch_reglist<16>(ctx, g, k, vp, d_out8, d_out_nn);
+  if (k <= 24) return launch_reglist<24>(ctx, g, k, vp, d_out8, d_out_nn);
+  if (k <= 32) return launch_reglist<32>(ctx, g, k, vp, d_out8, d_out_nn);
   const int T = k <= 48 ? 128 : (k <= 96 ? 64 : 32);
   const size_t smem = static_cast<size_t>(k) * T * 8;
-  if (k <= 32 && k >= 3 && g.n >= k) {
-    // queries the warp kernel could not prove: sorted positions + their count (index 0)
-    PEB_CUDA(ctx, ctx->nrm_left.ensure((static_cast<size_t>(g.n) + 1) * sizeof(int)));
-    int* left_n = ctx->nrm_left.as<int>();
-    int* left = left_n + 1;
-    PEB_CUDA(ctx, cudaMemsetAsync(left_n, 0, sizeof(int), ctx->stream));
-    PEB_LAUNCH(ctx, normals_warp_kernel, ceil_div(g.n, 32 * kNrmWarps), 32 * kNrmWarps, 0, g, k, vp[0], vp[1], vp[2],
-               d_out8, d_out_nn, left, left_n);
-    // (sized for the worst case; blocks beyond the count return at once)
-    PEB_LAUNCH(ctx, normals_knn_kernel, ceil_div(g.n, T), T, smem, g, k, vp[0], vp[1], vp[2], d_out8, d_out_nn, left, left_n);
-    return PEB_OK;
-  }
   PEB_LAUNCH(ctx, normals_knn_kernel, ceil_div(g.n, T), T, smem, g, k, vp[0], vp[1], vp[2], d_out8, d_out_nn,
              static_cast<const int*>(nullptr), static_cast<const int*>(nullptr));
   return PEB_OK;

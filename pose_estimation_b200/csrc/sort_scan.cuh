@@ -49,6 +49,31 @@ __device__ __forceinline__ uint32_t lookback_exclusive(const uint32_t* state, in
   return excl;
 }
 
+// The same for ONE chain walked by a whole warp (all 32 lanes call it): 32 predecessors per step — lane l looks at
+// tile - 1 - l — instead of one dependent L2 round trip per predecessor.  The words of the step are usable up to the
+// nearest inclusive sum; if a nearer word is not published yet the step is read again.
+__device__ __forceinline__ uint32_t lookback_exclusive_warp(const uint32_t* state, int tile, int lane) {
+  uint32_t excl = 0;
+  for (int t = tile - 1;; t -= 32) {
+    const int idx = t - lane;
+    uint32_t s, upto, incl;
+    for (;;) {
+      s = idx >= 0 ? ld_relaxed_u32(state + idx) : kFlagInclusive;  // (before tile 0: an inclusive sum of zero)
+      incl = __ballot_sync(0xFFFFFFFFu, (s & kFlagMask) == kFlagInclusive);
+      const uint32_t none = __ballot_sync(0xFFFFFFFFu, (s & kFlagMask) == 0u);
+      upto = incl ? ((2u << (__ffs(incl) - 1)) - 1u) : 0xFFFFFFFFu;  // the lanes up to the nearest inclusive word
+      if ((none & upto) == 0u) break;
+      __nanosleep(20);
+    }
+    uint32_t v = ((upto >> lane) & 1u) ? (s & kCountMask) : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    excl += v;
+    if (incl) break;
+  }
+  return excl;
+}
+
 // ---- digit histograms of all passes, accumulated by the kernel that produces the keys ---------------------------
 // sh: [passes][256] in shared memory, zeroed by the caller.  Warp-aggregated: one shared-memory atomic per distinct
 // digit and warp (the high digits of cell ids are nearly constant: 32 lanes on one counter otherwise).
@@ -97,13 +122,13 @@ __device__ __forceinline__ int scan_take_ticket(const ScanState& st) {
   return s_tile;
 }
 
-// Exclusive prefix of v over every element before this thread's (all earlier tiles + the earlier threads of this
-// tile); blockDim.x == kScanBlock, every thread of the block calls it.  The last tile leaves the grand total in
-// *st.total.  block_total (nullable) receives this tile's own sum.
-__device__ __forceinline__ uint32_t scan_exclusive(uint32_t v, const ScanState& st, int tile, int n_tiles,
-                                                   uint32_t* block_total = nullptr) {
+// The two halves of a single-pass scan, for kernels whose tile is several block-sized rounds:
+// block_exclusive_scan: prefix of v inside the block (shared memory only); *block_total = the block's sum.
+// tile_lookback: the sum of the totals of every earlier tile (publishes this tile's total first; decoupled look-back by
+// warp 0; the last tile leaves the grand total in *st.total).  blockDim.x == kScanBlock, every thread calls them.
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* block_total) {
   __shared__ uint32_t s_warp[kScanBlock / 32];
-  __shared__ uint32_t s_base, s_total;
+  __shared__ uint32_t s_total;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t inc = v;
 #pragma unroll
@@ -122,27 +147,46 @@ __device__ __forceinline__ uint32_t scan_exclusive(uint32_t v, const ScanState& 
       if (lane >= o) winc += t;
     }
     if (lane < kScanBlock / 32) s_warp[lane] = winc - w;
-    const uint32_t total = __shfl_sync(0xFFFFFFFFu, winc, 31);
+    if (lane == 31) s_total = winc;
+  }
+  __syncthreads();
+  const uint32_t res = s_warp[warp] + inc - v;
+  *block_total = s_total;
+  __syncthreads();  // the shared words are reused by the next call
+  return res;
+}
+__device__ __forceinline__ uint32_t tile_lookback(uint32_t total, const ScanState& st, int tile, int n_tiles) {
+  __shared__ uint32_t s_base;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    uint32_t* word = st.words + tile;
+    uint32_t excl = 0;
+    if (tile > 0) {
+      if (lane == 0) st_relaxed_u32(word, kFlagAggregate | total);
+      excl = lookback_exclusive_warp(st.words, tile, lane);
+    }
     if (lane == 0) {
-      uint32_t* word = st.words + tile;
-      uint32_t excl = 0;
-      if (tile == 0) {
-        st_relaxed_u32(word, kFlagInclusive | total);
-      } else {
-        st_relaxed_u32(word, kFlagAggregate | total);
-        excl = lookback_exclusive(st.words, tile, 1);
-        st_relaxed_u32(word, kFlagInclusive | (excl + total));
-      }
+      st_relaxed_u32(word, kFlagInclusive | (excl + total));
       if (tile == n_tiles - 1) *st.total = excl + total;
       s_base = excl;
-      s_total = total;
     }
   }
   __syncthreads();
-  const uint32_t res = s_base + s_warp[warp] + inc - v;
-  if (block_total) *block_total = s_total;
-  __syncthreads();  // the shared words may be reused by the caller's next scan
-  return res;
+  const uint32_t base = s_base;
+  __syncthreads();
+  return base;
+}
+
+// Exclusive prefix of v over every element before this thread's (all earlier tiles + the earlier threads of this
+// tile); blockDim.x == kScanBlock, every thread of the block calls it.  The last tile leaves the grand total in
+// *st.total.  block_total (nullable) receives this tile's own sum.
+__device__ __forceinline__ uint32_t scan_exclusive(uint32_t v, const ScanState& st, int tile, int n_tiles,
+                                                   uint32_t* block_total = nullptr) {
+  uint32_t total;
+  const uint32_t local = block_exclusive_scan(v, &total);
+  const uint32_t base = tile_lookback(total, st, tile, n_tiles);
+  if (block_total) *block_total = total;
+  return base + local;
 }
 
 }  // namespace peb

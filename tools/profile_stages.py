@@ -38,6 +38,8 @@ def main():
         icp.getConvergeCriteria().setAbsoluteMSE(-1.0)
         icp.align(prob.guess, want_output=False)
         f1 = icp.getFitnessScore()
+        if rep == 1:  # the brute-force validator on the model's points (target = the down-sampled scene)
+            ctx.nn_search(prob.source, bruteforce=True)
         icpn = pcl.IterativeClosestPointWithNormals(ctx)
         icpn.setInputSource(prob.source)
         icpn.setInputTarget(tgt, nrm)
