@@ -450,6 +450,7 @@ def run_ours(args):
                 line["align_ms"] = single_align(ctx, c2, torch, stream, flush, pcl, lib)
                 line["align_ms"]["c1"] = c1_leg(ctx, torch, stream, flush, pcl, lib)
                 line["align_ms"]["cvicp_reference_call"] = cvicp_leg(ctx, c2, pcl, not args.no_cpu_baseline)
+                line["align_ms"]["ppf_reference_call"] = ppf_leg(ctx, c2, pcl, not args.no_cpu_baseline)
             stage_fractions(line["align_ms"], peak)
             if not args.no_cpu_baseline:
                 # SURVEY.md 8d / BASELINE.md section 4: the CPU port beside EVERY GPU number, same run, same host
@@ -731,6 +732,63 @@ def cvicp_leg(ctx, c2, pcl, with_cpu: bool):
         out["cpu_port_ms"] = 1e3 * (time.perf_counter() - t0)
         out["cpu_port_threads"] = min(6, host_threads())
         out["vs_cpu_port_rad_max"] = float(max(synth.pose_error(a, b)[0] for a, b in zip(got, ref)))
+    return out
+
+
+def ppf_leg(ctx, c2, pcl, with_cpu: bool):
+    """The reference's coarse matcher in front of the refinement slot (opencv_surface_match.cpp:45-46, :65):
+    PPF3DDetector(0.03, 0.03, 40).trainModel(model) once, then match(scene with normals, results, 1.0, 0.03) per frame, on
+    the C2 clouds (background plane cut off like remove_planes does), through the host-buffer C ABI, wall clock."""
+    import time
+
+    from pose_estimation_b200.testing import synth
+
+    def with_normals(cloud, viewpoint):
+        ne = pcl.NormalEstimation(ctx)
+        ne.setInputCloud(cloud)
+        ne.setKSearch(20)
+        ne.setViewPoint(*viewpoint)
+        nrm = ne.compute()
+        ok = np.isfinite(nrm[:, :3]).all(1) & np.isfinite(cloud[:, :3]).all(1)
+        return np.ascontiguousarray(np.concatenate([cloud[ok, :3], nrm[ok, :3]], 1), np.float32)
+
+    scene = c2.target[c2.target[:, 2] < 0.735]
+    scene6 = with_normals(scene, (0.0, 0.0, 0.0))
+    model6 = with_normals(c2.source, (0.0, 0.0, 1.0))  # the model's outward side (object frame), consistently
+    det = pcl.PPF3DDetector(0.03, 0.03, 40, ctx=ctx)
+
+    def timed(fn, reps):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            r = fn()
+            ts.append(1e3 * (time.perf_counter() - t0))
+        return statistics.median(ts), min(ts), r
+
+    t_train, t_train_min, _ = timed(lambda: det.trainModel(model6), 3)
+    t_match, t_match_min, res = timed(lambda: det.match(scene6, 1.0, 0.03, return_raw=True), 5)
+    clustered, raw = res
+    rot, trans = synth.pose_error(clustered[0].matrix, c2.gt_pose)
+    out = {"workload": "cv::ppf_match_3d::PPF3DDetector(0.03, 0.03, 40): trainModel(model) and match(scene, 1.0, 0.03), C2 clouds "
+                       "with k = 20 normals, plane cut off",
+           "n_model": int(len(model6)), "n_scene": int(len(scene6)), "n_model_sampled": int(len(det.sampled_model())),
+           "n_scene_reference_points": int(len(raw)), "n_clusters": int(len(clustered)),
+           "train_ms_median": t_train, "train_ms_min": t_train_min, "match_ms_median": t_match, "match_ms_min": t_match_min,
+           "top_votes": int(clustered[0].num_votes), "top_pose_error_rad": rot, "top_pose_error_m": trans}
+    if with_cpu:
+        from oracle import Oracle
+        orc = Oracle(fast=True)
+        t0 = time.perf_counter()
+        ref = orc.ppf_train(model6)
+        out["cpu_port_train_ms"] = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        ores, oraw, _ = ref.match(scene6, 1.0, 0.03)
+        out["cpu_port_match_ms"] = 1e3 * (time.perf_counter() - t0)
+        out["cpu_port_threads"] = host_threads()
+        out["raw_poses_identical_to_cpu_port"] = float(np.mean([(a.num_votes, a.model_index) == (b.num_votes, b.model_index)
+                                                                for a, b in zip(raw, oraw)]))
+    det.close()
     return out
 
 

@@ -389,6 +389,55 @@ class CvIcp {
   peb_cvicp_params p_;
 };
 
+// cv::ppf_match_3d::PPF3DDetector as the reference constructs and calls it
+// (pose_estimation/src/opencv_surface_match.cpp:45-46: detectors_[name] = PPF3DDetector(0.03, 0.03, 40);
+// detectors_[name].trainModel(models_[name]); :65: detectors_[object].match(pc_scene_normals, results, 1.0, 0.03)).
+// Clouds are the N x 6 CV_32F rows of OpenCV; a result is peb_ppf_pose = cv::ppf_match_3d::Pose3D (pose row-major like
+// cv::Matx44d::val, q = w x y z, t, angle, numVotes, modelIndex, residual), clustered, most votes first — the vector the
+// reference truncates to six poses and hands to ICP::registerModelToScene (CvIcp above).
+class PPF3DDetector {
+ public:
+  explicit PPF3DDetector(Context& c, double relativeSamplingStep = 0.05, double relativeDistanceStep = 0.05, double numAngles = 30)
+      : c_(c) {
+    peb_ppf_params_default(&p_);
+    p_.relative_sampling_step = relativeSamplingStep;
+    p_.relative_distance_step = relativeDistanceStep;
+    p_.num_angles = numAngles;
+  }
+  ~PPF3DDetector() { peb_ppf_model_destroy(m_); }
+  PPF3DDetector(const PPF3DDetector&) = delete;
+  PPF3DDetector& operator=(const PPF3DDetector&) = delete;
+  void setSearchParams(double positionThreshold = -1, double rotationThreshold = -1, bool useWeightedClustering = false) {
+    p_.position_threshold = positionThreshold;
+    p_.rotation_threshold = rotationThreshold;
+    p_.use_weighted_avg = useWeightedClustering ? 1 : 0;
+  }
+  void trainModel(const float* model_xyzn, size_t n_model) {
+    peb_ppf_model_destroy(m_);
+    m_ = nullptr;
+    c_.check(peb_ppf_train(c_.get(), model_xyzn, n_model, &p_, &m_));
+  }
+  void match(const float* scene_xyzn, size_t n_scene, std::vector<peb_ppf_pose>& results, double relativeSceneSampleStep = 1.0 / 5.0,
+             double relativeSceneDistance = 0.03) {
+    if (!m_) throw Error(PEB_E_INVALID_ARG, "PPF3DDetector::match: the model is not trained");
+    size_t n = 0;
+    results.resize(64);
+    c_.check(peb_ppf_match(c_.get(), m_, scene_xyzn, n_scene, relativeSceneSampleStep, relativeSceneDistance, results.data(),
+                           results.size(), &n, nullptr, 0, nullptr));
+    if (n > results.size()) {  // more clusters than the first guess: ask again with room for all of them
+      results.resize(n);
+      c_.check(peb_ppf_match(c_.get(), m_, scene_xyzn, n_scene, relativeSceneSampleStep, relativeSceneDistance, results.data(),
+                             results.size(), &n, nullptr, 0, nullptr));
+    }
+    results.resize(n);
+  }
+
+ private:
+  Context& c_;
+  peb_ppf_params p_;
+  peb_ppf_model* m_ = nullptr;
+};
+
 // The manager's side of the pose (pose_estimation_manager/src/pose_transformer.cpp:78-121, PoseTransformer::obj_in_base_frame):
 // the published {x, y, z, qx, qy, qz, qw} (camera frame) -> hand-eye calibration (row-major 4x4, he_calibration_mat_) -> the
 // grasp frame sent to the robot: the object's y axis is kept, z is the base's -z (or +x when y is more than ~37 degrees out of

@@ -27,6 +27,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <unordered_map>
 #include <vector>
@@ -50,13 +51,18 @@ static inline double norm(const V3& a) { return std::sqrt(dot(a, a)); }
 
 // [CV] ppf_helpers.cpp : computeBboxStd — min / max per axis (float)
 static void bbox(const float* pc, size_t n, size_t cols, float lo[3], float hi[3]) {
-  for (int a = 0; a < 3; ++a) lo[a] = hi[a] = pc[a];
-  for (size_t i = 0; i < n; ++i)
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = std::numeric_limits<float>::infinity();
+    hi[a] = -std::numeric_limits<float>::infinity();
+  }
+  for (size_t i = 0; i < n; ++i) {
+    const float* p = pc + i * cols;
+    if (!(std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]))) continue;
     for (int a = 0; a < 3; ++a) {
-      const float v = pc[i * cols + a];
-      if (v < lo[a]) lo[a] = v;
-      if (v > hi[a]) hi[a] = v;
+      if (p[a] < lo[a]) lo[a] = p[a];
+      if (p[a] > hi[a]) hi[a] = p[a];
     }
+  }
 }
 
 // [CV] ppf_helpers.cpp : samplePCByQuantization(pc, xrange, yrange, zrange, sampleStep, weightByCenter = 0)
@@ -72,6 +78,7 @@ static void sample_by_quantization(const float* pc, size_t n, size_t cols, const
   std::vector<std::vector<int>> map(cells);
   for (size_t i = 0; i < n; ++i) {
     const float* p = pc + i * cols;
+    if (!(std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]))) continue;  // (upstream expects clean clouds)
     const int xc = static_cast<int>(static_cast<float>(nsd) * (p[0] - lo[0]) / xr);
     const int yc = static_cast<int>(static_cast<float>(nsd) * (p[1] - lo[1]) / yr);
     const int zc = static_cast<int>(static_cast<float>(nsd) * (p[2] - lo[2]) / zr);
@@ -132,12 +139,13 @@ static bool ppf_features(const V3& p1, const V3& n1, const V3& p2, const V3& n2,
 }
 
 // the four quantised components ([CV] hashPPF: (int)(f / step)); the hash of upstream is replaced by the key itself
+// A NaN component (acos of a dot product that rounding pushed past 1) would be undefined behaviour in upstream's
+// cast; here such a pair gets a negative component and is left out of the table and of the voting (valid_key).
 static inline void ppf_key(const double f[4], double angle_step, double distance_step, int key[4]) {
-  key[0] = static_cast<int>(f[0] / angle_step);
-  key[1] = static_cast<int>(f[1] / angle_step);
-  key[2] = static_cast<int>(f[2] / angle_step);
-  key[3] = static_cast<int>(f[3] / distance_step);
+  const double q[4] = {f[0] / angle_step, f[1] / angle_step, f[2] / angle_step, f[3] / distance_step};
+  for (int k = 0; k < 4; ++k) key[k] = (q[k] == q[k] && q[k] < 32767.0) ? static_cast<int>(q[k]) : -1;
 }
+static inline bool valid_key(const int key[4]) { return key[0] >= 0 && key[1] >= 0 && key[2] >= 0 && key[3] >= 0; }
 static inline uint64_t pack_key(const int key[4]) {
   return (static_cast<uint64_t>(static_cast<uint16_t>(key[0])) << 48) | (static_cast<uint64_t>(static_cast<uint16_t>(key[1])) << 32) |
          (static_cast<uint64_t>(static_cast<uint16_t>(key[2])) << 16) | static_cast<uint64_t>(static_cast<uint16_t>(key[3]));
@@ -230,6 +238,7 @@ static void train(Detector& d, const float* model6, size_t n_model, const peb_pp
       ppf_features(p1, n1, p2, n2, f);  // (coincident sampled points keep f = 0 and are inserted like upstream)
       int key[4];
       ppf_key(f, d.angle_step, d.distance_step, key);
+      if (!valid_key(key)) continue;
       d.table[pack_key(key)].push_back({i, static_cast<float>(alpha_of(R, t, p2))});
     }
   }
@@ -410,13 +419,16 @@ static void match(const Detector& d, const float* scene6, size_t n_scene, double
       ppf_features(p1, n1, p2, n2, f);
       int key[4];
       ppf_key(f, d.angle_step, d.distance_step, key);
+      if (!valid_key(key)) continue;
       const double alpha_scene = alpha_of(Rsg, tsg, p2);
       const auto it = d.table.find(pack_key(key));
       if (it == d.table.end()) continue;
       for (const Node& nd : it->second) {
         const double alpha = static_cast<double>(nd.alpha) - alpha_scene;
         const int alpha_index = static_cast<int>(num_angles * (alpha + 2 * M_PI) / (4 * M_PI));
-        acc[static_cast<size_t>(nd.i) * num_angles + alpha_index]++;
+        // (alpha == 2 pi exactly would index one past the row upstream: it goes to the last bin here and on the device)
+        const int a_idx = alpha_index < num_angles ? alpha_index : num_angles - 1;
+        acc[static_cast<size_t>(nd.i) * num_angles + a_idx]++;
       }
     }
     uint32_t max_votes = 0;

@@ -104,6 +104,27 @@ class CvIcpParams(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("num_levels", C.c_int32), ("tolerance", C.c_float), ("rejection_scale", C.c_float)]
 
 
+class PpfParams(C.Structure):
+    """peb_ppf_params."""
+
+    _fields_ = [("relative_sampling_step", C.c_double), ("relative_distance_step", C.c_double), ("num_angles", C.c_double),
+                ("position_threshold", C.c_double), ("rotation_threshold", C.c_double), ("use_weighted_avg", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class PpfPose(C.Structure):
+    """peb_ppf_pose = cv::ppf_match_3d::Pose3D."""
+
+    _fields_ = [("pose", C.c_double * 16), ("q", C.c_double * 4), ("t", C.c_double * 3), ("angle", C.c_double),
+                ("alpha", C.c_double), ("residual", C.c_double), ("num_votes", C.c_uint64), ("model_index", C.c_uint64)]
+
+    @property
+    def matrix(self):
+        import numpy as np
+
+        return np.array(self.pose, np.float64).reshape(4, 4)
+
+
 class GridInfo(C.Structure):
     _fields_ = [
         ("origin", C.c_float * 3),
@@ -134,6 +155,11 @@ SYMBOLS = {
     "peb_sac_plane_dev": (_i, [_vp, _vp, _sz, _pp(SacParams), _vp, _vp, _pp(_sz), _pp(C.c_int32)]),
     "peb_scene_prepare": (_i, [_vp, _vp, _sz, _sz, _pp(PrefilterParams), _i, _pp(SacParams), _f, _vp, _pp(_sz), _vp]),
     "peb_cvicp_register": (_i, [_vp, _vp, _sz, _vp, _sz, _pp(CvIcpParams), _vp, _sz, _vp]),
+    "peb_ppf_params_default": (None, [_pp(PpfParams)]),
+    "peb_ppf_train": (_i, [_vp, _vp, _sz, _pp(PpfParams), _pp(_vp)]),
+    "peb_ppf_model_destroy": (None, [_vp]),
+    "peb_ppf_model_sampled": (_i, [_vp, _vp, _sz, _pp(_sz)]),
+    "peb_ppf_match": (_i, [_vp, _vp, _vp, _sz, _d, _d, _vp, _sz, _pp(_sz), _vp, _sz, _pp(_sz)]),
     "peb_normals_knn": (_i, [_vp, _vp, _sz, _sz, _i, _vp, _vp]),
     "peb_normals_knn_ex": (_i, [_vp, _vp, _sz, _sz, _i, _vp, _vp, _vp]),
     "peb_nn_search": (_i, [_vp, _vp, _sz, _sz, _vp, _vp]),

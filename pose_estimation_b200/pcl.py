@@ -17,7 +17,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import CvIcpParams, IcpParams, IcpResult, GridInfo, PrefilterParams, SacParams, lib
+from ._lib import CvIcpParams, IcpParams, IcpResult, GridInfo, PpfParams, PpfPose, PrefilterParams, SacParams, lib
 
 DBL_MAX = float(np.finfo(np.float64).max)
 
@@ -389,6 +389,70 @@ class CvIcp:
         self.ctx.check(lib.peb_cvicp_register(self.ctx.handle, m.ctypes.data, m.shape[0], sc.ctypes.data, sc.shape[0],
                                               C.byref(self.params), P.ctypes.data, P.shape[0], res.ctypes.data))
         return P.reshape(-1, 4, 4), res[: P.shape[0]]
+
+
+class PPF3DDetector:
+    """cv::ppf_match_3d::PPF3DDetector as the reference constructs and calls it
+    (pose_estimation/src/opencv_surface_match.cpp:45-46: PPF3DDetector(0.03, 0.03, 40).trainModel(model); :65:
+    match(scene_with_normals, results, 1.0, 0.03)).  Clouds are N x 6 float (points + normals); match returns the
+    clustered poses (PpfPose = Pose3D: pose, q, t, angle, numVotes, modelIndex), most votes first."""
+
+    def __init__(self, relativeSamplingStep: float = 0.05, relativeDistanceStep: float = 0.05, numAngles: float = 30,
+                 ctx: Context | None = None):
+        # (defaults of cv::ppf_match_3d::PPF3DDetector; the reference passes 0.03, 0.03, 40)
+        self.ctx = ctx or default_context()
+        self.params = PpfParams()
+        lib.peb_ppf_params_default(C.byref(self.params))
+        self.params.relative_sampling_step = float(relativeSamplingStep)
+        self.params.relative_distance_step = float(relativeDistanceStep)
+        self.params.num_angles = float(numAngles)
+        self._model = C.c_void_p()
+
+    def setSearchParams(self, positionThreshold: float = -1.0, rotationThreshold: float = -1.0, useWeightedClustering: bool = False):
+        self.params.position_threshold = float(positionThreshold)
+        self.params.rotation_threshold = float(rotationThreshold)
+        self.params.use_weighted_avg = int(bool(useWeightedClustering))
+
+    def trainModel(self, model6):
+        m = np.ascontiguousarray(model6, np.float32)
+        if m.ndim != 2 or m.shape[1] != 6:
+            raise PebError(-1, "PPF3DDetector.trainModel: the model must be N x 6 float (points + normals)")
+        self.close()
+        self.ctx.check(lib.peb_ppf_train(self.ctx.handle, m.ctypes.data, m.shape[0], C.byref(self.params), C.byref(self._model)))
+
+    def sampled_model(self) -> np.ndarray:
+        n = C.c_size_t(0)
+        self.ctx.check(lib.peb_ppf_model_sampled(self._model, None, 0, C.byref(n)))
+        out = np.empty((n.value, 6), np.float32)
+        self.ctx.check(lib.peb_ppf_model_sampled(self._model, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def match(self, scene6, relativeSceneSampleStep: float = 1.0 / 5.0, relativeSceneDistance: float = 0.03, return_raw: bool = False):
+        if not self._model:
+            raise PebError(-1, "PPF3DDetector.match: the model is not trained")
+        sc = np.ascontiguousarray(scene6, np.float32)
+        if sc.ndim != 2 or sc.shape[1] != 6:
+            raise PebError(-1, "PPF3DDetector.match: the scene must be N x 6 float (points + normals)")
+        cap = max(sc.shape[0], 1)
+        res = (PpfPose * cap)()
+        raw = (PpfPose * cap)()
+        n = C.c_size_t(0)
+        n_raw = C.c_size_t(0)
+        self.ctx.check(lib.peb_ppf_match(self.ctx.handle, self._model, sc.ctypes.data, sc.shape[0], float(relativeSceneSampleStep),
+                                         float(relativeSceneDistance), res, cap, C.byref(n), raw, cap, C.byref(n_raw)))
+        out = list(res[: n.value])
+        return (out, list(raw[: n_raw.value])) if return_raw else out
+
+    def close(self):
+        if self._model:
+            lib.peb_ppf_model_destroy(self._model)
+            self._model = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class VoxelGrid:
