@@ -767,8 +767,8 @@ def ppf_leg(ctx, c2, pcl, with_cpu: bool):
         return statistics.median(ts), min(ts), r
 
     t_train, t_train_min, _ = timed(lambda: det.trainModel(model6), 3)
-    t_match, t_match_min, res = timed(lambda: det.match(scene6, 1.0, 0.03, return_raw=True), 5)
-    clustered, raw = res
+    t_match, t_match_min, clustered = timed(lambda: det.match(scene6, 1.0, 0.03), 5)
+    _, raw = det.match(scene6, 1.0, 0.03, return_raw=True)
     rot, trans = synth.pose_error(clustered[0].matrix, c2.gt_pose)
     out = {"workload": "cv::ppf_match_3d::PPF3DDetector(0.03, 0.03, 40): trainModel(model) and match(scene, 1.0, 0.03), C2 clouds "
                        "with k = 20 normals, plane cut off",

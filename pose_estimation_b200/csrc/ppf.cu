@@ -14,9 +14,13 @@
 //              parameters) built by counting sort: count, scan, fill.  OpenCV's chained MurmurHash table is replaced
 //              by the key itself: a scene pair votes for the model pairs with the same quantised feature and for no
 //              hash-collision neighbours (pe_b200.h / DESIGN.md section 11: the one deliberate difference).
-//   voting     one block per scene reference point, its accumulator (model reference x alpha bin, uint32) in global
-//              memory (L2-resident), threads over the scene points, atomicAdd per vote; block argmax with upstream's
-//              first-maximum rule; the slab is cleared on the way
+//   voting     one block per scene reference point.  Its accumulator (model reference x alpha bin) lives in SHARED
+//              memory, a range of model reference points at a time: the pairs of a feature bin are stored sorted by
+//              that range, so a pass walks exactly its own nodes.  Buckets are very uneven (on a smooth object a few
+//              feature bins hold most pairs), so the (scene pair, model pair) items of a tile of 256 scene points are
+//              FLATTENED — block scan of the bucket lengths, every thread takes items t, t + 256, ... and finds its
+//              scene pair by binary search — which also makes the node loads coalesced.  Block argmax with upstream's
+//              first-maximum rule.
 //   poses      one thread per reference point: Tsg^-1 * Rx(alpha) * Tmg, Pose3D::updatePose (angle, quaternion), double
 //   clustering PPF3DDetector::clusterPoses on the host: a greedy, order-dependent pass over at most a few thousand
 //              poses (sorted by votes) — sequential by definition, microseconds of work.
@@ -29,6 +33,7 @@
 #include <new>
 
 #include "common.cuh"
+#include "sort_scan.cuh"
 
 struct peb_ppf_model {
   peb_ctx* ctx = nullptr;
@@ -39,9 +44,10 @@ struct peb_ppf_model {
   int num_angles = 0;          // alpha bins
   int n = 0;                   // sampled model points
   int na = 0, nd = 0;          // angle bins per component, distance bins
+  int chunk = 0, ranges = 0;   // voting: model reference points per shared-memory pass, number of passes
   peb::DevBuf sampled;         // n x 6 float
   peb::DevBuf frames;          // n x 12 double (R row-major, t)
-  peb::DevBuf bucket_start;    // na^3 * nd + 1
+  peb::DevBuf bucket_start;    // (na^3 * nd) * ranges + 1: the pairs of a feature bin, by range of the model reference point
   peb::DevBuf nodes;           // uint2 (model reference, alpha bits) per stored pair
   std::vector<float> h_sampled;
 };
@@ -51,6 +57,7 @@ namespace {
 
 constexpr double kPpfEps = 1.192092896e-07;  // [CV] c_utils.hpp : EPS
 constexpr double kPi = 3.14159265358979323846;
+constexpr size_t kVoteSmemBytes = 48 * 1024;  // shared-memory accumulator of the voting kernel (four blocks per SM)
 
 // ---- sampling ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned f32_ordered(float f) {
@@ -272,8 +279,8 @@ __device__ __forceinline__ int ppf_bucket(const float* __restrict__ a6, const fl
 // FILL = false: counts[bucket]++ ; FILL = true: nodes[cursor[bucket]++] = (i, alpha)
 template <bool FILL>
 __global__ void __launch_bounds__(256) ppf_train_pairs_kernel(const float* __restrict__ pts6, const double* __restrict__ frames,
-                                                              int n, KeySpace ks, uint32_t* __restrict__ counts_or_cursor,
-                                                              uint2* __restrict__ nodes) {
+                                                              int n, KeySpace ks, int chunk, int ranges,
+                                                              uint32_t* __restrict__ counts_or_cursor, uint2* __restrict__ nodes) {
   const long long total = static_cast<long long>(n) * n;
   for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < total;
        p += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -281,8 +288,9 @@ __global__ void __launch_bounds__(256) ppf_train_pairs_kernel(const float* __res
     if (i == j) continue;
     const float* a6 = pts6 + 6 * static_cast<size_t>(i);
     const float* b6 = pts6 + 6 * static_cast<size_t>(j);
-    const int b = ppf_bucket(a6, b6, ks);
+    int b = ppf_bucket(a6, b6, ks);
     if (b < 0) continue;
+    b = b * ranges + i / chunk;
     if (!FILL) {
       atomicAdd(counts_or_cursor + b, 1u);
     } else {
@@ -298,62 +306,122 @@ struct RefResult {
   uint32_t max_votes, ref_max, alpha_max, pad;
 };
 
-__global__ void __launch_bounds__(256) ppf_vote_kernel(const float* __restrict__ scene6, const double* __restrict__ scene_frames,
+// (int)(num_angles * (alpha + 2 pi) / (4 pi)) like upstream.  The quotient by multiplication with 1 / (4 pi) is within
+// 2 ulp of the division's: it decides the bin unless it lies that close to an integer, and only then is the division
+// itself evaluated (out of line, so that its Newton sequence stays out of the voting loop).
+__device__ __noinline__ double ppf_exact_quotient(double y) { return y / (4 * kPi); }
+__device__ __forceinline__ int ppf_alpha_bin(double alpha, int num_angles) {
+  const double y = num_angles * (alpha + 2 * kPi);
+  double q = y * (1.0 / (4 * kPi));
+  if (fabs(q - rint(q)) < 1e-9) q = ppf_exact_quotient(y);
+  return static_cast<int>(q);
+}
+
+struct ScenePair {
+  double alpha;  // alpha_scene
+  int bucket;    // feature bin, -1: none
+  int pad;
+};
+
+// dynamic shared memory: chunk * num_angles uint32 counters
+__global__ void __launch_bounds__(256, 4) ppf_vote_kernel(const float* __restrict__ scene6, const double* __restrict__ scene_frames,
                                                        int m, int step, int n_ref, KeySpace ks,
                                                        const uint32_t* __restrict__ bucket_start, const uint2* __restrict__ nodes,
-                                                       int n_model, int num_angles, uint32_t* __restrict__ acc_slabs,
-                                                       RefResult* __restrict__ out) {
+                                                       int n_model, int num_angles, int chunk, int ranges,
+                                                       ScenePair* __restrict__ pair_scratch, RefResult* __restrict__ out) {
+  extern __shared__ uint32_t s_acc[];
   __shared__ double s_fr[12];
   __shared__ float s_a6[6];
   __shared__ unsigned long long s_best[256 / 32];
-  const size_t slab = static_cast<size_t>(n_model) * num_angles;
-  uint32_t* acc = acc_slabs + blockIdx.x * slab;
+  __shared__ uint32_t s_start[256], s_prefix[257];
+  __shared__ double s_alpha[256];
+  const int t = threadIdx.x;
+  ScenePair* pairs = pair_scratch + static_cast<size_t>(blockIdx.x) * m;
   for (int ri = blockIdx.x; ri < n_ref; ri += gridDim.x) {
     const int i = ri * step;
-    if (threadIdx.x < 12) s_fr[threadIdx.x] = scene_frames[12 * static_cast<size_t>(i) + threadIdx.x];
-    if (threadIdx.x < 6) s_a6[threadIdx.x] = scene6[6 * static_cast<size_t>(i) + threadIdx.x];
+    if (t < 12) s_fr[t] = scene_frames[12 * static_cast<size_t>(i) + t];
+    if (t < 6) s_a6[t] = scene6[6 * static_cast<size_t>(i) + t];
     __syncthreads();
-    for (int j = threadIdx.x; j < m; j += blockDim.x) {
-      if (j == i) continue;
-      const float* b6 = scene6 + 6 * static_cast<size_t>(j);
-      const int b = ppf_bucket(s_a6, b6, ks);
-      if (b < 0) continue;
-      const uint32_t s = bucket_start[b], e = bucket_start[b + 1];
-      if (s == e) continue;
-      const double alpha_scene = ppf_alpha(s_fr, {b6[0], b6[1], b6[2]});
-      for (uint32_t k = s; k < e; ++k) {
-        const uint2 nd = nodes[k];
-        const double alpha = static_cast<double>(__uint_as_float(nd.y)) - alpha_scene;
-        // (alpha == 2 pi exactly would index one past the row upstream: it goes to the last bin)
-        const int alpha_index = min(static_cast<int>(num_angles * (alpha + 2 * kPi) / (4 * kPi)), num_angles - 1);
-        atomicAdd(acc + static_cast<size_t>(nd.x) * num_angles + alpha_index, 1u);
+    // the feature bin and the planar angle of every scene pair (i, j), once
+    for (int j = t; j < m; j += 256) {
+      ScenePair sp;
+      sp.bucket = -1;
+      sp.alpha = 0.0;
+      sp.pad = 0;
+      if (j != i) {
+        const float* b6 = scene6 + 6 * static_cast<size_t>(j);
+        sp.bucket = ppf_bucket(s_a6, b6, ks);
+        if (sp.bucket >= 0) sp.alpha = ppf_alpha(s_fr, {b6[0], b6[1], b6[2]});
       }
+      pairs[j] = sp;
     }
     __syncthreads();
-    // [CV] "maximize the accumulator": strict >, scanning (k, j) upwards = the lowest index among the maxima; the
-    // key (votes << 32 | ~index) makes that one 64-bit maximum.  The slab is cleared for the next reference point.
     unsigned long long best = 0xFFFFFFFFull;  // 0 votes at index 0
-    for (size_t a = threadIdx.x; a < slab; a += blockDim.x) {
-      const uint32_t v = acc[a];
-      if (v) {
-        acc[a] = 0u;
-        const unsigned long long key = (static_cast<unsigned long long>(v) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(a));
-        best = max(best, key);
+    for (int r = 0; r < ranges; ++r) {
+      const int rows = min(chunk, n_model - r * chunk);
+      const int bins = rows * num_angles;
+      for (int a = t; a < bins; a += 256) s_acc[a] = 0u;
+      __syncthreads();
+      for (int j0 = 0; j0 < m; j0 += 256) {
+        const int j = j0 + t;
+        uint32_t start = 0, len = 0;
+        double alpha_scene = 0.0;
+        if (j < m) {
+          const ScenePair sp = pairs[j];
+          if (sp.bucket >= 0) {
+            const size_t e = static_cast<size_t>(sp.bucket) * ranges + r;
+            start = bucket_start[e];
+            len = bucket_start[e + 1] - start;
+            alpha_scene = sp.alpha;
+          }
+        }
+        uint32_t total;
+        const uint32_t before = block_exclusive_scan(len, &total);
+        s_start[t] = start;
+        s_prefix[t] = before;
+        s_alpha[t] = alpha_scene;
+        if (t == 255) s_prefix[256] = total;
+        __syncthreads();
+        // items [0, total): item `it` belongs to the scene pair p with prefix[p] <= it < prefix[p + 1].  A warp takes 32
+        // consecutive items at a time, 256 items further every trip: the pair of its first item only moves forward
+        // (one step per trip on average — buckets hold hundreds of pairs), every lane then steps on to its own pair
+        int p0 = 0;
+        for (uint32_t c0 = static_cast<uint32_t>(t & ~31); c0 < total; c0 += 256) {
+          while (s_prefix[p0 + 1] <= c0) ++p0;  // (warp-uniform: broadcast reads)
+          const uint32_t it = c0 + static_cast<uint32_t>(t & 31);
+          if (it >= total) continue;
+          int lo = p0;
+          while (s_prefix[lo + 1] <= it) ++lo;
+          const uint2 nd = nodes[s_start[lo] + (it - s_prefix[lo])];
+          const double alpha = static_cast<double>(__uint_as_float(nd.y)) - s_alpha[lo];
+          // (alpha == 2 pi exactly would index one past the row upstream: it goes to the last bin)
+          const int alpha_index = min(ppf_alpha_bin(alpha, num_angles), num_angles - 1);
+          atomicAdd(&s_acc[(static_cast<int>(nd.x) - r * chunk) * num_angles + alpha_index], 1u);
+        }
+        __syncthreads();
       }
+      // [CV] "maximize the accumulator": strict >, scanning (k, j) upwards = the lowest index among the maxima; the
+      // key (votes << 32 | ~index) makes that one 64-bit maximum
+      const uint32_t base = static_cast<uint32_t>(r * chunk) * static_cast<uint32_t>(num_angles);
+      for (int a = t; a < bins; a += 256) {
+        const uint32_t v = s_acc[a];
+        if (v) best = max(best, (static_cast<unsigned long long>(v) << 32) | (0xFFFFFFFFu - (base + static_cast<uint32_t>(a))));
+      }
+      __syncthreads();
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
-    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+    if ((t & 31) == 0) s_best[t >> 5] = best;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (t == 0) {
       for (int w = 1; w < 256 / 32; ++w) best = max(best, s_best[w]);
       const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(best & 0xFFFFFFFFull);
-      RefResult r;
-      r.max_votes = static_cast<uint32_t>(best >> 32);
-      r.ref_max = idx / static_cast<uint32_t>(num_angles);
-      r.alpha_max = idx % static_cast<uint32_t>(num_angles);
-      r.pad = 0;
-      out[ri] = r;
+      RefResult res;
+      res.max_votes = static_cast<uint32_t>(best >> 32);
+      res.ref_max = idx / static_cast<uint32_t>(num_angles);
+      res.alpha_max = idx % static_cast<uint32_t>(num_angles);
+      res.pad = 0;
+      out[ri] = res;
     }
     __syncthreads();
   }
@@ -632,7 +700,8 @@ int train_impl(peb_ctx* ctx, const float* model6, size_t n_model, const peb_ppf_
   Sampled info;
   PEB_TRY(ppf_sample(ctx, model6, n_model, static_cast<float>(prm->relative_sampling_step), &m->sampled, &info));
   if (info.n < 2) return fail(ctx, PEB_E_INVALID_ARG, "ppf_train: the model samples to %d points", info.n);
-  if (info.n > 20000) return fail(ctx, PEB_E_UNSUPPORTED, "ppf_train: %d sampled model points (pair table too large)", info.n);
+  // (a voting tile flattens the buckets of 256 scene pairs into one 32-bit item range: 256 n^2 must stay below 2^32)
+  if (info.n > 4095) return fail(ctx, PEB_E_UNSUPPORTED, "ppf_train: %d sampled model points (at most 4095)", info.n);
   m->n = info.n;
   const float dx = info.hi[0] - info.lo[0], dy = info.hi[1] - info.lo[1], dz = info.hi[2] - info.lo[2];
   const float diameter = std::sqrt(dx * dx + dy * dy + dz * dz);
@@ -644,9 +713,13 @@ int train_impl(peb_ctx* ctx, const float* model6, size_t n_model, const peb_ppf_
   const long long entries = static_cast<long long>(m->na) * m->na * m->na * m->nd;
   if (entries > (64ll << 20)) return fail(ctx, PEB_E_UNSUPPORTED, "ppf_train: %lld feature bins (num_angles %g) exceed the direct table", entries, prm->num_angles);
   const KeySpace ks = {m->angle_step, static_cast<double>(m->distance_step), m->na, m->nd};
+  // voting keeps the accumulator rows of `chunk` model reference points in shared memory (kVoteSmemBytes)
+  m->chunk = std::max(1, static_cast<int>(kVoteSmemBytes / (static_cast<size_t>(m->num_angles) * 4)));
+  m->ranges = ceil_div(m->n, m->chunk);
+  if (entries * m->ranges > (256ll << 20)) return fail(ctx, PEB_E_UNSUPPORTED, "ppf_train: feature table of %lld x %d entries", entries, m->ranges);
   PEB_CUDA(ctx, m->frames.ensure(static_cast<size_t>(m->n) * 12 * sizeof(double)));
   PEB_LAUNCH(ctx, ppf_frames_kernel, ceil_div(m->n, 128), 128, 0, m->sampled.as<float>(), m->n, m->frames.as<double>());
-  const int E = static_cast<int>(entries);
+  const int E = static_cast<int>(entries * m->ranges);
   PEB_CUDA(ctx, m->bucket_start.ensure((static_cast<size_t>(E) + 1) * 4));
   DevBuf cursor;
   struct Free {
@@ -658,12 +731,12 @@ int train_impl(peb_ctx* ctx, const float* model6, size_t n_model, const peb_ppf_
   const long long pairs = static_cast<long long>(m->n) * m->n;
   const int blocks = static_cast<int>(std::min<long long>((pairs + 255) / 256, kSmCount * 16));
   PEB_LAUNCH(ctx, ppf_train_pairs_kernel<false>, blocks, 256, 0, m->sampled.as<float>(), m->frames.as<double>(), m->n, ks,
-             cursor.as<uint32_t>(), static_cast<uint2*>(nullptr));
+             m->chunk, m->ranges, cursor.as<uint32_t>(), static_cast<uint2*>(nullptr));
   PEB_TRY(exclusive_scan_u32(ctx, cursor.as<uint32_t>(), m->bucket_start.as<uint32_t>(), E + 1, nullptr));
   PEB_CUDA(ctx, cudaMemcpyAsync(cursor.p, m->bucket_start.p, (static_cast<size_t>(E) + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
   PEB_CUDA(ctx, m->nodes.ensure(static_cast<size_t>(pairs) * sizeof(uint2)));
   PEB_LAUNCH(ctx, ppf_train_pairs_kernel<true>, blocks, 256, 0, m->sampled.as<float>(), m->frames.as<double>(), m->n, ks,
-             cursor.as<uint32_t>(), m->nodes.as<uint2>());
+             m->chunk, m->ranges, cursor.as<uint32_t>(), m->nodes.as<uint2>());
   m->h_sampled.resize(static_cast<size_t>(m->n) * 6);
   PEB_CUDA(ctx, cudaMemcpyAsync(m->h_sampled.data(), m->sampled.p, m->h_sampled.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
   PEB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -694,19 +767,19 @@ int match_impl(peb_ctx* ctx, const peb_ppf_model* m, const float* scene6, size_t
   PEB_CUDA(ctx, frames.ensure(static_cast<size_t>(ms) * 12 * sizeof(double)));
   PEB_LAUNCH(ctx, ppf_frames_kernel, ceil_div(ms, 128), 128, 0, scene.as<float>(), ms, frames.as<double>());
   const KeySpace ks = {m->angle_step, static_cast<double>(m->distance_step), m->na, m->nd};
-  const int blocks = std::min(n_ref, kSmCount * 2);
-  const size_t slab = static_cast<size_t>(m->n) * m->num_angles;
-  const size_t acc_bytes = static_cast<size_t>(blocks) * slab * 4;
+  const int blocks = std::min(n_ref, kSmCount * 4);
+  const size_t pair_bytes = static_cast<size_t>(blocks) * ms * sizeof(ScenePair);
   const size_t ref_bytes = static_cast<size_t>(n_ref) * sizeof(RefResult);
   const size_t pose_bytes = static_cast<size_t>(n_ref) * sizeof(peb_ppf_pose);
-  PEB_CUDA(ctx, ctx->cv_arena.ensure(acc_bytes + ref_bytes + pose_bytes + 512));
+  PEB_CUDA(ctx, ctx->cv_arena.ensure(pair_bytes + ref_bytes + pose_bytes + 512));
   unsigned char* base = ctx->cv_arena.as<unsigned char>();
-  uint32_t* acc = reinterpret_cast<uint32_t*>(base);
-  RefResult* refs = reinterpret_cast<RefResult*>(base + ((acc_bytes + 255) / 256) * 256);
+  ScenePair* pair_scratch = reinterpret_cast<ScenePair*>(base);
+  RefResult* refs = reinterpret_cast<RefResult*>(base + ((pair_bytes + 255) / 256) * 256);
   peb_ppf_pose* d_poses = reinterpret_cast<peb_ppf_pose*>(reinterpret_cast<unsigned char*>(refs) + ((ref_bytes + 255) / 256) * 256);
-  PEB_CUDA(ctx, cudaMemsetAsync(acc, 0, acc_bytes, ctx->stream));
-  PEB_LAUNCH(ctx, ppf_vote_kernel, blocks, 256, 0, scene.as<float>(), frames.as<double>(), ms, step, n_ref, ks,
-             m->bucket_start.as<uint32_t>(), m->nodes.as<uint2>(), m->n, m->num_angles, acc, refs);
+  const size_t smem = static_cast<size_t>(std::min(m->chunk, m->n)) * m->num_angles * 4;
+  PEB_CUDA(ctx, cudaFuncSetAttribute(ppf_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kVoteSmemBytes)));
+  PEB_LAUNCH(ctx, ppf_vote_kernel, blocks, 256, smem, scene.as<float>(), frames.as<double>(), ms, step, n_ref, ks,
+             m->bucket_start.as<uint32_t>(), m->nodes.as<uint2>(), m->n, m->num_angles, m->chunk, m->ranges, pair_scratch, refs);
   PEB_LAUNCH(ctx, ppf_pose_kernel, ceil_div(n_ref, 128), 128, 0, refs, n_ref, step, frames.as<double>(), m->frames.as<double>(),
              m->num_angles, d_poses);
   std::vector<peb_ppf_pose> h_raw(static_cast<size_t>(n_ref));

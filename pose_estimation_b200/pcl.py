@@ -433,15 +433,17 @@ class PPF3DDetector:
         sc = np.ascontiguousarray(scene6, np.float32)
         if sc.ndim != 2 or sc.shape[1] != 6:
             raise PebError(-1, "PPF3DDetector.match: the scene must be N x 6 float (points + normals)")
-        cap = max(sc.shape[0], 1)
-        res = (PpfPose * cap)()
-        raw = (PpfPose * cap)()
+        # one pose per reference point at most, one reference point per occupied lattice cell at most (the buffers are kept)
+        cap = max(1, min(sc.shape[0], (int(1.0 / np.float32(relativeSceneDistance)) + 1) ** 3))
+        if getattr(self, "_cap", 0) < cap:
+            self._res, self._raw, self._cap = (PpfPose * cap)(), (PpfPose * cap)(), cap
         n = C.c_size_t(0)
         n_raw = C.c_size_t(0)
         self.ctx.check(lib.peb_ppf_match(self.ctx.handle, self._model, sc.ctypes.data, sc.shape[0], float(relativeSceneSampleStep),
-                                         float(relativeSceneDistance), res, cap, C.byref(n), raw, cap, C.byref(n_raw)))
-        out = list(res[: n.value])
-        return (out, list(raw[: n_raw.value])) if return_raw else out
+                                         float(relativeSceneDistance), self._res, self._cap, C.byref(n),
+                                         self._raw if return_raw else None, self._cap if return_raw else 0, C.byref(n_raw)))
+        out = [PpfPose.from_buffer_copy(p) for p in self._res[: n.value]]
+        return (out, [PpfPose.from_buffer_copy(p) for p in self._raw[: n_raw.value]]) if return_raw else out
 
     def close(self):
         if self._model:
