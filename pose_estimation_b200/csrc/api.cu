@@ -186,7 +186,7 @@ PEB_API void peb_ctx_destroy(peb_ctx* ctx) {
   if (!ctx) return;
   DeviceGuard guard(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->d_small, &ctx->d_scratch, &ctx->d_stage, &ctx->tgt_raw, &ctx->tgt_nrm_raw, &ctx->src, &ctx->work, &ctx->slack, &ctx->anchors, &ctx->dbg,
+  DevBuf* bufs[] = {&ctx->d_small, &ctx->d_scratch, &ctx->d_stage, &ctx->tgt_raw, &ctx->tgt_nrm_raw, &ctx->src, &ctx->work, &ctx->slack, &ctx->anchors, &ctx->nn_cache, &ctx->dbg,
                     &ctx->corr_idx, &ctx->corr_d2, &ctx->partials, &ctx->state, &ctx->trace, &ctx->d_guesses,
                     &ctx->d_results, &ctx->d_aligned, &ctx->vg_in, &ctx->vg_out, &ctx->vg_flags, &ctx->vg_scan,
                     &ctx->vg_starts, &ctx->nrm_in, &ctx->nrm_out, &ctx->brute_keys, &ctx->nn_q, &ctx->nn_idx, &ctx->nn_d2, &ctx->epochs, &ctx->cv_arena};
@@ -291,6 +291,16 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
   if (!strcmp(key, "warm_upfront")) {
     if (value < 0 || value > 3) return fail(ctx, PEB_E_INVALID_ARG, "warm_upfront must be 0 (off), 1 / 2 (2 x 2 rows) or 3 (3 x 3 rows)");
     ctx->warm_upfront = value;
+    return PEB_OK;
+  }
+  if (!strcmp(key, "nn_cache_from")) {
+    if (value < 0) return fail(ctx, PEB_E_INVALID_ARG, "nn_cache_from must be >= 0 (0: off; launch 0 is never a warm launch)");
+    ctx->nn_cache_from = value;
+    return PEB_OK;
+  }
+  if (!strcmp(key, "nn_cache_r_x100")) {
+    if (value < 5 || value > 400) return fail(ctx, PEB_E_INVALID_ARG, "nn_cache_r_x100 out of [5, 400]");
+    ctx->nn_cache_r = value / 100.0f;
     return PEB_OK;
   }
   if (!strcmp(key, "warm_upfront_from")) {

@@ -122,6 +122,9 @@ struct peb_ctx {
   peb::DevBuf dbg;
   int dbg_launches = 0;
   peb::DevBuf anchors;          // H x ceil(n / 32) sorted positions
+  int nn_cache_from = 0;        // warm launches from this one on answer from the candidate cache (nn_cache.cuh); 0: off
+  float nn_cache_r = 0.75f;     // radius (cells) a cache entry's collecting search covers
+  peb::DevBuf nn_cache;         // H x n_src entries of 32 bytes
   float cert_margin = 0.0f;     // > 0: warm searches cover this fraction of a cell beyond the match, which
                                 // buys a certificate that lets later iterations skip the search while the
                                 // point has moved less than half of it.  Off by default: on surface scans the

@@ -25,6 +25,7 @@
 // incremental float update is reproduced exactly for every hypothesis.
 #include <algorithm>
 
+#include "nn_cache.cuh"
 #include "nn_search.cuh"
 #include "nn_upfront.cuh"
 
@@ -73,6 +74,9 @@ struct IcpLaunch {
   int* epochs;           // nullable, H: solved iterations per hypothesis, published after the state is complete
   int* err_flag;         // raised if a dependency wait runs into its bound
   float margin;          // extra search radius that buys the skip-the-search certificate (0: none)
+  NnCache* cache;        // nullable, H x n_src candidate caches (nn_cache.cuh) of the cached warm launches
+  float cache_r_cells;   // radius (cells) a cache entry's collecting search covers
+  int cache_init;        // this launch is the first cached one: every entry is still garbage
 };
 
 __global__ void icp_init_kernel(IcpState* __restrict__ states, const float* __restrict__ guesses, int H,
@@ -563,6 +567,163 @@ __global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_kernel(const Ic
   icp_iteration_body<G, EST, MB, CERT, FIRST, UPF>(L, blockIdx.y, blockIdx.x);
 }
 
+// ---- warm iterations with the candidate cache (nn_cache.cuh) -----------------------------------------------------
+// Phase A, queries in rounds of one per thread: move the working point, try the certificate of its cache entry
+// (kCacheK gathers, no grid walk, uniform over the warp).  Queries whose certificate fails are queued in shared memory
+// and, every third round, collected again by DENSE warps — one queued query per thread, every lane busy with the same
+// kind of fixed-radius search.  A query the ball of radius R finds nothing for (far from the scene) takes the plain warm
+// search, as before.  Phase B: every thread accumulates ITS queries in the order of the plain kernel — working point and
+// match re-read from the working cloud — so that the double sums, and with them every result, are bit-identical to the
+// plain warm kernel's.
+constexpr int kCacheRoundsPerFlush = 3;
+constexpr int kCacheQueue = kIcpThreads * kCacheRoundsPerFlush;
+
+__device__ __forceinline__ void cache_rebuild(const IcpLaunch& L, NnCache* __restrict__ cache, float4* __restrict__ work, int i) {
+  float4 p = work[i];  // already moved; .w = the previous match
+  const int j_prev = __float_as_int(p.w);
+  NnTop top;
+  grid_ball_collect(L.grid, p.x, p.y, p.z, L.cache_r_cells, top);
+  NnCache ce = nn_cache_from_top(L.grid, p.x, p.y, p.z, L.cache_r_cells, top);
+  int j = top.j[0];
+  // the collection ranks everything in the cells it touched, but only the ball of radius R is covered completely: its
+  // best point is the nearest neighbour only if it lies inside that ball
+  if (j >= 0 && !(sqrtf(top.d2[0]) * (1.0f + 4e-6f) < L.cache_r_cells * L.grid.h)) j = -1;
+  if (j < 0) {  // nothing within R: the plain search (its ball is the previous match's distance), no certificate
+    NnBest best;
+    if (j_prev >= 0 && j_prev < L.grid.n) best = grid_nn_warm(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2);
+    else best = grid_nn<1>(L.grid, p.x, p.y, p.z, L.stop_d2);
+    j = best.j;
+    ce.bound = 0.0f;
+  }
+  cache[i] = ce;
+  p.w = __int_as_float(j);
+  work[i] = p;
+}
+
+template <int EST, int MB>
+__global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_cached_kernel(const IcpLaunch L) {
+  if (L.epochs == nullptr) {
+    pdl_trigger_and_wait();
+  } else {
+    asm volatile("griddepcontrol.launch_dependents;");
+    wait_for_hypothesis(L.epochs + blockIdx.y, L.launch_idx, L.err_flag);
+  }
+  const int h = blockIdx.y, blk = blockIdx.x;
+  constexpr int NACC = (EST == PEB_ESTIMATOR_SVD) ? kAccSvd : kAccLls;
+  __shared__ double sm[kIcpThreads / 32][kAccMax];
+  __shared__ double sm_tot[kAccMax];
+  __shared__ float s_inc[16];
+  __shared__ int s_active;
+  __shared__ int s_queue[kCacheQueue];
+  __shared__ int s_qn;
+  IcpState* st = L.states + h;
+  if (threadIdx.x < 16) s_inc[threadIdx.x] = __ldcg(&st->inc.m[threadIdx.x]);
+  if (threadIdx.x == 32) {
+    s_active = __ldcg(&st->active);
+    s_qn = 0;
+  }
+  __syncthreads();
+  if (!s_active) return;
+  const float* T = s_inc;
+  float4* work = L.work + static_cast<size_t>(h) * L.n_src;
+  NnCache* cache = L.cache + static_cast<size_t>(h) * L.n_src;
+  const int stride = L.blocks_per_hyp * kIcpThreads;
+
+  // ---- phase A: nearest neighbours ----
+  int round = 0;
+  for (int base = blk * kIcpThreads; base < L.n_src; base += stride, ++round) {
+    const int i = base + threadIdx.x;
+    bool pending = false;
+    if (i < L.n_src) {
+      float4 p = work[i];
+      if (finite3(p.x, p.y, p.z)) {
+        float ox, oy, oz;
+        transform_icp(T, p.x, p.y, p.z, ox, oy, oz);
+        p.x = ox;
+        p.y = oy;
+        p.z = oz;
+        NnBest best;
+        if (!L.cache_init && nn_cache_lookup(L.grid, cache[i], p.x, p.y, p.z, best)) p.w = __int_as_float(best.j);
+        else pending = true;
+        work[i] = p;  // (a pending query keeps its previous match in .w until it is collected again)
+      }
+    }
+    const unsigned mask = __ballot_sync(0xFFFFFFFFu, pending);
+    if (mask) {
+      const int lane = threadIdx.x & 31;
+      int at = 0;
+      if (lane == 0) at = atomicAdd(&s_qn, __popc(mask));
+      at = __shfl_sync(0xFFFFFFFFu, at, 0);
+      if (pending) s_queue[at + __popc(mask & ((1u << lane) - 1u))] = i;
+    }
+    const bool last = base + stride >= L.n_src;
+    if (round % kCacheRoundsPerFlush == kCacheRoundsPerFlush - 1 || last) {
+      __syncthreads();
+      const int qn = s_qn;
+      for (int k = threadIdx.x; k < qn; k += kIcpThreads) cache_rebuild(L, cache, work, s_queue[k]);
+      __syncthreads();
+      if (threadIdx.x == 0) s_qn = 0;
+      // (the next push is separated from this reset by the ballot of the next round only: make it visible first)
+      __syncthreads();
+    }
+  }
+
+  // ---- phase B: thresholds and moments, every thread its own queries in order ----
+  double acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+  for (int base = blk * kIcpThreads; base < L.n_src; base += stride) {
+    const int i = base + threadIdx.x;
+    if (i >= L.n_src) continue;
+    const float4 p = work[i];
+    const bool valid = finite3(p.x, p.y, p.z);
+    const int j = __float_as_int(p.w);
+    NnBest best;
+    best.d2 = pos_inf();
+    best.idx = -1;
+    best.j = -1;
+    if (valid && j >= 0) {
+      const float4 t = L.grid.pts[j];
+      best.d2 = l2_simple(p.x, p.y, p.z, t.x, t.y, t.z);
+      best.idx = __float_as_int(t.w);
+      best.j = j;
+    }
+    bool keep = valid && best.idx >= 0;
+    if (keep && static_cast<double>(best.d2) > L.max_dist_sqr) keep = false;
+    if (keep && L.use_rejector && !(best.d2 < L.rej_max2)) keep = false;
+    if (L.corr_idx) {
+      const int orig = __float_as_int(L.src[i].w);
+      L.corr_idx[orig] = keep ? best.idx : -1;
+      L.corr_d2[orig] = keep ? best.d2 : 0.0f;
+    }
+    if (keep) accumulate_pair<EST>(L.grid, p, best, acc);
+  }
+
+  // ---- the block's record, the last block's solve: as in icp_iteration_body ----
+  const double r = block_reduce_acc<NACC>(acc, sm);
+  double* part = L.partials + (static_cast<size_t>(h) * L.part_stride) * kAccMax;
+  if (threadIdx.x < NACC) __stcg(part + static_cast<size_t>(blk) * kAccMax + threadIdx.x, r);
+  __threadfence();
+  __syncthreads();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(&st->ticket, 1u);
+    s_last = (t == static_cast<unsigned>(L.blocks_per_hyp) - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  reduce_partials<NACC>(part, L.blocks_per_hyp, sm, sm_tot);
+  if (threadIdx.x == 0) {
+    finish_iteration<MB>(st, &L.crit, sm_tot, L.trace, L.trace_cap, nullptr);
+    if (L.epochs) {
+      const int still_active = st->active;
+      __threadfence();
+      atomicAdd(L.epochs + h, still_active ? 1 : kEpochStopped);
+    }
+  }
+}
+
 // [PCL] registration/impl/registration.hpp : getFitnessScore(max_range) with the final transform
 // applied by pcl::transformPointCloud's association (transform_tpc), then the result record.
 template <int G>
@@ -742,6 +903,15 @@ int launch_one_iteration(peb_ctx* ctx, const IcpLaunch& L, size_t H, int estimat
       else        { if (svd) PEB_ICP_LAUNCH_UPF(S, kMinBlocksBatch, 2);  else PEB_ICP_LAUNCH_UPF(P, kMinBlocksBatch, 2); }
     }
 #undef PEB_ICP_LAUNCH_UPF
+    return PEB_OK;
+  }
+  // warm launches with the candidate cache (nn_cache.cuh; peb_ctx_set_int "nn_cache_from")
+  if (G == 1 && !FIRST && !cert && L.cache && L.warm) {
+#define PEB_ICP_LAUNCH_CACHED(EST, MB) \
+  PEB_LAUNCH_PDL(ctx, (icp_iteration_cached_kernel<EST, MB>), grid, dim3(kIcpThreads), L)
+    if (H == 1) { if (svd) PEB_ICP_LAUNCH_CACHED(S, kMinBlocksSingle); else PEB_ICP_LAUNCH_CACHED(P, kMinBlocksSingle); }
+    else        { if (svd) PEB_ICP_LAUNCH_CACHED(S, kMinBlocksBatch);  else PEB_ICP_LAUNCH_CACHED(P, kMinBlocksBatch); }
+#undef PEB_ICP_LAUNCH_CACHED
     return PEB_OK;
   }
   if (H == 1) {
@@ -924,6 +1094,19 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
   }
   Lw.blocks_per_hyp = blocks_for(n, H, g_warm, ctx->blocks_factor);
   Lw.warm = ctx->warm_start ? 1 : 0;
+  // the candidate cache of the warm launches from launch nn_cache_from on (0: never)
+  const int cache_from = (ctx->nn_cache_from > 0 && ctx->warm_start && g_warm == 1 && !(L.margin > 0.0f)) ? ctx->nn_cache_from : 0;
+  NnCache* cache_buf = nullptr;
+  if (cache_from > 0 && cache_from < launches) {
+    PEB_CUDA(ctx, ctx->nn_cache.ensure(H * static_cast<size_t>(std::max(n, 1)) * sizeof(NnCache)));
+    cache_buf = ctx->nn_cache.as<NnCache>();
+    Lw.cache_r_cells = ctx->nn_cache_r;
+  }
+  // (per launch: Lw.cache is set from cache_from on; the fitness launch keeps the plain warm search)
+  auto set_cache = [&](int it) {
+    Lw.cache = (cache_buf && it >= cache_from && it < launches) ? cache_buf : nullptr;
+    Lw.cache_init = it == cache_from ? 1 : 0;
+  };
   ctx->prof_launches = 0;
   ctx->prof_chain_ends = 0;
   if (ctx->debug_timers) {
@@ -969,6 +1152,7 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
       C.results += h0;
       if (C.anchors) C.anchors += h0 * static_cast<size_t>(C.n_anchor);
       if (C.epochs) C.epochs += h0;
+      if (C.cache) C.cache += h0 * static_cast<size_t>(n);
       return C;
     };
     // the anchor launch above ran on the main stream for all hypotheses: the fork event orders it
@@ -979,6 +1163,7 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
         if (h0 >= h1) continue;
         StreamSwap swap(ctx, ctx->sub_streams[c]);
         Lc.launch_idx = Lw.launch_idx = it;
+        set_cache(it);
         if (it == 0) {
           PEB_TRY(launch_one_iteration_g(ctx, g_cold, true, chunk_of(Lc, h0), h1 - h0, prm->estimator));
         } else if (it < launches) {
@@ -1005,6 +1190,7 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
   for (int it = 0; it < launches; ++it) {
     if (per_launch) PEB_TRY(prof_mark(ctx, 2 * it));
     Lc.launch_idx = Lw.launch_idx = it;
+    set_cache(it);
     if (it == 0)
       PEB_TRY(launch_one_iteration_g(ctx, g_cold, true, Lc, H, prm->estimator));
     else
@@ -1012,6 +1198,7 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
     if (per_launch) PEB_TRY(prof_mark(ctx, 2 * it + 1));
   }
   Lw.launch_idx = launches;  // the fitness launch needs all iteration launches of its hypothesis
+  set_cache(launches);
   if (per_launch) {
     PEB_TRY(prof_mark(ctx, 2 * launches));
     PEB_TRY(launch_fitness_g(ctx, g_warm, Lw, H));

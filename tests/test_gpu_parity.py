@@ -355,7 +355,11 @@ def test_icp_batch_equals_single_and_oracle(pcl, ctx, oracle, scene_small):
                                           # next patch's anchor or to a cold search
                                           ("coop_max_rows", 0), ("coop_max_rows", 40), ("seed_guard_x10", 15),
                                           # whole-grid dependencies between the launches instead of per-hypothesis flags
-                                          ("flag_deps", 0)])
+                                          ("flag_deps", 0),
+                                          # the candidate cache of the warm launches (nn_cache.cuh): from launch 1, 3 or 10
+                                          # on, with balls small enough that most certificates fail and large ones
+                                          ("nn_cache_from", 1), ("nn_cache_from", 3), ("nn_cache_from", 10),
+                                          ("nn_cache_from+r", (2, 20)), ("nn_cache_from+r", (2, 200))])
 def test_speed_options_never_change_results(pcl, oracle, scene_small, option, value):
     """warm start, search-skipping certificates, the cold lane-group width and the cooperative first iteration
     (packed-arithmetic filter + exact re-evaluation) are exactness-preserving: every combination must give the
@@ -366,8 +370,13 @@ def test_speed_options_never_change_results(pcl, oracle, scene_small, option, va
     out = []
     for use in (False, True):
         c = pcl.Context(0)
-        if use:
+        if use and option == "nn_cache_from+r":
+            c.set_int("nn_cache_from", value[0])
+            c.set_int("nn_cache_r_x100", value[1])
+        elif use:
             c.set_int(option, value)
+        elif option.startswith("nn_cache"):
+            c.set_int("nn_cache_from", 0)  # (the comparison run: the plain warm search, whatever the default is)
         icp = pcl.IterativeClosestPoint(c)
         icp.setInputSource(p.source)
         icp.setInputTarget(p.target)
