@@ -210,9 +210,12 @@ def run_reference(args):
         "impl": "reference", "metric": "icp_hypotheses_per_s", "value": value, "unit": "hypotheses/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(c4, sample),
+        # the SAME config as the CUDA arm's line (the workload); a step of this arm is a bounded sample of it, named in
+        # cpu_baseline.sample, and `value` is a rate, so the two lines compare directly
+        "config": workload_config(c4, N_HYP),
         "cpu_baseline": {"value": value, "unit": "hypotheses/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} of the {N_HYP} hypotheses per step, OpenMP over hypotheses, "
+                         "sample": f"{sample} of the {N_HYP} hypotheses per step ({cores} host threads; the ratio to the CUDA arm "
+                                   f"depends on the host: round 1 saw 354x on a 16-core and 188x on a 32-core box), OpenMP over hypotheses, "
                                    f"oracle timing build (-O3 AVX2/FMA), PCL 1.10 restatement: real PCL is not installable here"},
         "e2e": {"value": value, "unit": "hypotheses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

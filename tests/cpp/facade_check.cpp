@@ -136,6 +136,14 @@ int main(int argc, char** argv) {
       std::printf("cvicp residuals %.17g %.17g pose0", residuals[0], residuals[1]);
       for (int i = 0; i < 16; ++i) std::printf(" %.17g", cvposes[i]);
       std::printf("\n");
+      // the coarse matcher with the reference's parameters shape (opencv_surface_match.cpp:45-46, :65)
+      pe_b200::PPF3DDetector det(ctx, 0.08, 0.08, 30);
+      det.trainModel(model6.data(), model6.size() / 6);
+      std::vector<peb_ppf_pose> found;
+      det.match(scene6.data(), scene6.size() / 6, found, 0.5, 0.08);
+      std::printf("ppf clusters %zu votes %llu pose0", found.size(), found.empty() ? 0ull : (unsigned long long)found[0].num_votes);
+      for (int i = 0; i < 16 && !found.empty(); ++i) std::printf(" %.17g", found[0].pose[i]);
+      std::printf("\n");
     }
 
     // PCL options without a CUDA path must be refused, not emulated

@@ -108,4 +108,11 @@ def test_facade_matches_python_host_classes(exe, tmp_path):
     got, res = pcl.CvIcp(250, 0.005, 2.5, 8, ctx=ctx).registerModelToScene(model6, scene6, poses2)
     cv = [float(v) for v in lines["cvicp"][2:4]] , [float(v) for v in lines["cvicp"][5:21]]
     assert np.array_equal(np.array(cv[0]), res) and np.array_equal(np.array(cv[1]).reshape(4, 4), got[0])
+    # PPF3DDetector of the facade against the Python mirror (same library underneath: identical clusters)
+    det = pcl.PPF3DDetector(0.08, 0.08, 30, ctx=ctx)
+    det.trainModel(model6)
+    found = det.match(scene6, 0.5, 0.08)
+    assert int(lines["ppf"][2]) == len(found) and int(lines["ppf"][4]) == found[0].num_votes
+    assert np.array_equal(np.array([float(v) for v in lines["ppf"][6:22]]).reshape(4, 4), found[0].matrix)
+    det.close()
     ctx.close()
