@@ -130,7 +130,11 @@ PEB_API uint64_t peb_ctx_launch_count(const peb_ctx* ctx);
  * "warm_upfront" (default 0; 1 / 2: warm searches whose ball spans up to 2 x 2 grid rows fetch all row bounds up
  * front, 3: up to 3 x 3 — csrc/nn_upfront.cuh; bit-identical results, measured SLOWER on B200 (C4: -4 % and -19 %,
  * profiles/README.md round 2) and kept only as a recorded experiment; "warm_upfront_from": the first iteration
- * launch that uses it, default 2) */
+ * launch that uses it, default 2), "nn_cache_from" / "nn_cache_r_x100" (candidate cache of the warm launches,
+ * csrc/nn_cache.cuh; bit-identical, measured slower, off), "warm_bin" (default 0; 1: the warm launches of a batch
+ * sort the queries of a block by the number of grid rows their search walks before the warps search them —
+ * icp.cu : icp_iteration_binned_kernel; bit-identical by construction, measured -6 % on C4,
+ * profiles/r2_p_warm_bin.txt) */
 PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value);
 
 /* ---- pcl::VoxelGrid<PointXYZ>::filter  [PCL] filters/.../impl/voxel_grid.hpp -------- */

@@ -288,6 +288,11 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
     ctx->warm_start = value != 0;
     return PEB_OK;
   }
+  if (!strcmp(key, "warm_bin")) {
+    if (value < 0 || value > 1) return fail(ctx, PEB_E_INVALID_ARG, "warm_bin must be 0 or 1");
+    ctx->warm_bin = value;
+    return PEB_OK;
+  }
   if (!strcmp(key, "warm_upfront")) {
     if (value < 0 || value > 3) return fail(ctx, PEB_E_INVALID_ARG, "warm_upfront must be 0 (off), 1 / 2 (2 x 2 rows) or 3 (3 x 3 rows)");
     ctx->warm_upfront = value;

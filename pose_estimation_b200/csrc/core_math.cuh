@@ -240,6 +240,18 @@ PEB_HD void grid_ball_search(const GridView& g, float qx, float qy, float qz, fl
   }
 }
 
+// Grid rows (fixed y, z) in the bounding box of the ball grid_ball_search would walk for a candidate at squared
+// distance d2: the walk's trip count, known before any cell is looked at.  Scheduling only (icp.cu bins the queries of
+// a block by it so that the lanes of a warp walk equally many rows); it never decides a result.
+PEB_HD int grid_ball_rows(const GridView& g, float qy, float qz, float d2, float limit_d2) {
+  const float fy = (qy - g.oy) * g.inv_h, fz = (qz - g.oz) * g.inv_h;
+  const float pad = 0.001f + 4.8e-7f * static_cast<float>(max(g.dx, max(g.dy, g.dz)));
+  const float R = sqrtf(fminf(d2, limit_d2) * (g.inv_h * g.inv_h)) * 1.0001f + pad;
+  const int y0 = grid_clamp_cell(fy - R, g.dy), y1 = grid_clamp_cell(fy + R, g.dy);
+  const int z0 = grid_clamp_cell(fz - R, g.dz), z1 = grid_clamp_cell(fz + R, g.dz);
+  return (y1 - y0 + 1) * (z1 - z0 + 1);
+}
+
 // Exact 1-NN given one candidate (sorted position j_prev, e.g. last iteration's match)
 PEB_HD NnBest grid_nn_warm(const GridView& g, float qx, float qy, float qz, int j_prev, float limit_d2) {
   NnBest best;

@@ -567,6 +567,202 @@ __global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_kernel(const Ic
   icp_iteration_body<G, EST, MB, CERT, FIRST, UPF>(L, blockIdx.y, blockIdx.x);
 }
 
+// ---- warm iterations with the queries of a block binned by the size of their search ------------------------------
+// The ball walk of a warm query visits the rows of the ball's bounding box (core_math.cuh : grid_ball_search); a
+// lane with a 1 x 1 box next to a lane with a 3 x 4 box idles through eleven row steps, and almost every warp of 32
+// consecutive queries holds such a lane (box rows per query on C4: 1: 19 %, 2: 35 %, 3-4: 38 %, more: 8 %; the plain
+// kernel runs at ~15 of 32 active lanes).  Here a block takes a TILE of kBinQ passes of the plain kernel's loop:
+//   1. every thread moves its kBinQ queries, gathers their previous matches and parks query + candidate in shared
+//      memory, classed by the number of rows the walk will visit (queries without a previous match search cold:
+//      heaviest class);
+//   2. the tile is counting-sorted by class, heaviest first;
+//   3. warps draw 32 sorted queries at a time from a shared counter and search them — the lanes of a warp now walk
+//      (nearly) the same number of rows;
+//   4. every thread takes ITS queries back in the plain kernel's order: working point written, threshold, moments.
+// The queries, the searches and the order of every thread's double sums are those of icp_iteration_kernel: results
+// are bit-identical by construction (tests/test_gpu_bin_option.py).
+constexpr int kBinQ = 4;                         // plain-loop passes per tile
+constexpr int kBinTile = kBinQ * kIcpThreads;    // queries per tile
+constexpr int kBinClasses = 5;                   // searching classes, heaviest first; class kBinClasses = nothing to search
+
+__device__ __forceinline__ int bin_class_of_rows(int rows) {
+  return rows >= 7 ? 0 : rows >= 5 ? 1 : rows >= 3 ? 2 : rows == 2 ? 3 : 4;
+}
+
+template <int EST, int MB>
+__global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_binned_kernel(const IcpLaunch L) {
+  if (L.epochs == nullptr) {
+    pdl_trigger_and_wait();
+  } else {
+    asm volatile("griddepcontrol.launch_dependents;");
+    wait_for_hypothesis(L.epochs + blockIdx.y, L.launch_idx, L.err_flag);
+  }
+  const int h = blockIdx.y, blk = blockIdx.x;
+  constexpr int NACC = (EST == PEB_ESTIMATOR_SVD) ? kAccSvd : kAccLls;
+  __shared__ double sm[kIcpThreads / 32][kAccMax];
+  __shared__ double sm_tot[kAccMax];
+  __shared__ float s_inc[16];
+  __shared__ int s_active;
+  __shared__ float s_qx[kBinTile], s_qy[kBinTile], s_qz[kBinTile], s_d2[kBinTile];
+  __shared__ int s_idx[kBinTile], s_j[kBinTile];
+  __shared__ unsigned short s_key[kBinTile], s_perm[kBinTile];
+  __shared__ int s_cnt[2][kBinClasses + 1];  // per class; [kBinClasses] = the chunk counter of phase 3 (double-buffered by tile parity)
+  IcpState* st = L.states + h;
+  if (threadIdx.x < 16) s_inc[threadIdx.x] = __ldcg(&st->inc.m[threadIdx.x]);
+  if (threadIdx.x == 32) s_active = __ldcg(&st->active);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 2 * (kBinClasses + 1)) (&s_cnt[0][0])[threadIdx.x - 64] = 0;
+  __syncthreads();
+  if (!s_active) return;
+  const float* T = s_inc;
+  float4* work = L.work + static_cast<size_t>(h) * L.n_src;
+  const int stride = L.blocks_per_hyp * kIcpThreads;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+
+  double acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+
+  int buf = 0;
+  for (int base0 = blk * kIcpThreads; base0 < L.n_src; base0 += kBinQ * stride, buf ^= 1) {
+    // ---- 1: move, gather the previous match, class ----
+#pragma unroll 1
+    for (int kk = 0; kk < kBinQ; ++kk) {
+      const int i = base0 + kk * stride + threadIdx.x;
+      const int slot = kk * kIcpThreads + threadIdx.x;
+      int cls = kBinClasses;
+      float qx = 0.0f, qy = 0.0f, qz = 0.0f, d2 = pos_inf();
+      int idx = -1, j = -2;  // -2: nothing here (out of range or a non-finite working point), -1: no previous match
+      if (i < L.n_src) {
+        const float4 p = work[i];
+        if (finite3(p.x, p.y, p.z)) {
+          transform_icp(T, p.x, p.y, p.z, qx, qy, qz);
+          const int j_prev = __float_as_int(p.w);
+          cls = 0;  // no usable previous match: cold search
+          j = -1;
+          if (L.warm && j_prev >= 0 && j_prev < L.grid.n) {
+            const float4 t = L.grid.pts[j_prev];
+            d2 = l2_simple(qx, qy, qz, t.x, t.y, t.z);
+            idx = __float_as_int(t.w);
+            j = j_prev;
+            cls = bin_class_of_rows(grid_ball_rows(L.grid, qy, qz, d2, L.stop_d2));
+          }
+        }
+      }
+      s_qx[slot] = qx;
+      s_qy[slot] = qy;
+      s_qz[slot] = qz;
+      s_d2[slot] = d2;
+      s_idx[slot] = idx;
+      s_j[slot] = j;
+      // position inside the class: one shared-memory atomic per class present in the warp
+      const unsigned same = __match_any_sync(0xFFFFFFFFu, cls);
+      const int leader = __ffs(same) - 1;
+      int at = 0;
+      if (lane == leader && cls < kBinClasses) at = atomicAdd(&s_cnt[buf][cls], __popc(same));
+      at = __shfl_sync(0xFFFFFFFFu, at, leader);
+      s_key[slot] = static_cast<unsigned short>((cls << 12) | (at + __popc(same & lt)));
+    }
+    __syncthreads();
+    // ---- 2: counting sort by class ----
+    int off[kBinClasses + 1];
+    off[0] = 0;
+#pragma unroll
+    for (int c = 0; c < kBinClasses; ++c) off[c + 1] = off[c] + s_cnt[buf][c];
+    const int n_search = off[kBinClasses];
+#pragma unroll
+    for (int kk = 0; kk < kBinQ; ++kk) {
+      const int slot = kk * kIcpThreads + threadIdx.x;
+      const int key = s_key[slot];
+      const int cls = key >> 12;
+      if (cls < kBinClasses) {
+        int o = 0;
+#pragma unroll
+        for (int c = 1; c < kBinClasses; ++c) o = cls == c ? off[c] : o;
+        s_perm[o + (key & 0xFFF)] = static_cast<unsigned short>(slot);
+      }
+    }
+    // (the other buffer's counters were last read before this tile's first barrier: reset them for the next tile)
+    if (threadIdx.x < kBinClasses + 1) s_cnt[buf ^ 1][threadIdx.x] = 0;
+    __syncthreads();
+    // ---- 3: searches, 32 sorted queries per draw ----
+    for (;;) {
+      int c = 0;
+      if (lane == 0) c = atomicAdd(&s_cnt[buf][kBinClasses], 1);
+      c = __shfl_sync(0xFFFFFFFFu, c, 0);
+      if (c * 32 >= n_search) break;
+      const int k = c * 32 + lane;
+      if (k < n_search) {
+        const int slot = s_perm[k];
+        NnBest best;
+        best.d2 = s_d2[slot];
+        best.idx = s_idx[slot];
+        best.j = s_j[slot];
+        const float qx = s_qx[slot], qy = s_qy[slot], qz = s_qz[slot];
+        if (best.j >= 0) grid_ball_search(L.grid, qx, qy, qz, L.stop_d2, best);
+        else best = grid_nn<1>(L.grid, qx, qy, qz, L.stop_d2);
+        s_d2[slot] = best.d2;
+        s_idx[slot] = best.idx;
+        s_j[slot] = best.j;
+      }
+    }
+    __syncthreads();
+    // ---- 4: every thread its own queries, in the plain kernel's order ----
+#pragma unroll 1
+    for (int kk = 0; kk < kBinQ; ++kk) {
+      const int i = base0 + kk * stride + threadIdx.x;
+      const int slot = kk * kIcpThreads + threadIdx.x;
+      if (i >= L.n_src) break;
+      NnBest best;
+      best.j = s_j[slot];
+      if (best.j == -2) continue;  // non-finite working point: untouched, no correspondence
+      best.d2 = s_d2[slot];
+      best.idx = s_idx[slot];
+      float4 p;
+      p.x = s_qx[slot];
+      p.y = s_qy[slot];
+      p.z = s_qz[slot];
+      p.w = __int_as_float(best.j);
+      work[i] = p;
+      bool keep = best.idx >= 0;
+      if (keep && static_cast<double>(best.d2) > L.max_dist_sqr) keep = false;
+      if (keep && L.use_rejector && !(best.d2 < L.rej_max2)) keep = false;
+      if (L.corr_idx) {
+        const int orig = __float_as_int(L.src[i].w);
+        L.corr_idx[orig] = keep ? best.idx : -1;
+        L.corr_d2[orig] = keep ? best.d2 : 0.0f;
+      }
+      if (keep) accumulate_pair<EST>(L.grid, p, best, acc);
+    }
+    // (phase 1 of the next tile writes only this thread's own slots, and the sort keys / permutation are rewritten
+    //  behind its first barrier: no barrier needed here)
+  }
+
+  // ---- the block's record, the last block's solve: as in icp_iteration_body ----
+  const double r = block_reduce_acc<NACC>(acc, sm);
+  double* part = L.partials + (static_cast<size_t>(h) * L.part_stride) * kAccMax;
+  if (threadIdx.x < NACC) __stcg(part + static_cast<size_t>(blk) * kAccMax + threadIdx.x, r);
+  __threadfence();
+  __syncthreads();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(&st->ticket, 1u);
+    s_last = (t == static_cast<unsigned>(L.blocks_per_hyp) - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  reduce_partials<NACC>(part, L.blocks_per_hyp, sm, sm_tot);
+  if (threadIdx.x == 0) {
+    finish_iteration<MB>(st, &L.crit, sm_tot, L.trace, L.trace_cap, nullptr);
+    if (L.epochs) {
+      const int still_active = st->active;
+      __threadfence();
+      atomicAdd(L.epochs + h, still_active ? 1 : kEpochStopped);
+    }
+  }
+}
+
 // ---- warm iterations with the candidate cache (nn_cache.cuh) -----------------------------------------------------
 // Phase A, queries in rounds of one per thread: move the working point, try the certificate of its cache entry
 // (kCacheK gathers, no grid walk, uniform over the warp).  Queries whose certificate fails are queued in shared memory
@@ -903,6 +1099,12 @@ int launch_one_iteration(peb_ctx* ctx, const IcpLaunch& L, size_t H, int estimat
       else        { if (svd) PEB_ICP_LAUNCH_UPF(S, kMinBlocksBatch, 2);  else PEB_ICP_LAUNCH_UPF(P, kMinBlocksBatch, 2); }
     }
 #undef PEB_ICP_LAUNCH_UPF
+    return PEB_OK;
+  }
+  // warm launches of a batch with the queries of a block binned by the size of their search ("warm_bin")
+  if (G == 1 && !FIRST && !cert && !L.cache && L.warm && ctx->warm_bin && H > 1) {
+    if (svd) PEB_LAUNCH_PDL(ctx, (icp_iteration_binned_kernel<S, kMinBlocksBatch>), grid, dim3(kIcpThreads), L);
+    else     PEB_LAUNCH_PDL(ctx, (icp_iteration_binned_kernel<P, kMinBlocksBatch>), grid, dim3(kIcpThreads), L);
     return PEB_OK;
   }
   // warm launches with the candidate cache (nn_cache.cuh; peb_ctx_set_int "nn_cache_from")
