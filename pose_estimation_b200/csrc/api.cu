@@ -69,6 +69,7 @@ struct DeviceGuard {
 };
 
 int target_finish(peb_ctx* ctx, size_t n, bool has_normals) {
+  ctx->tgt_knn_valid = false;
   ctx->n_tgt = n;
   ctx->tgt_has_normals = has_normals;
   return grid_build(ctx, &ctx->tgt_grid, ctx->tgt_raw.as<float4>(), has_normals ? ctx->tgt_nrm_raw.as<float4>() : nullptr,
@@ -286,6 +287,16 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
   }
   if (!strcmp(key, "warm_start")) {
     ctx->warm_start = value != 0;
+    return PEB_OK;
+  }
+  if (!strcmp(key, "warm_graph")) {
+    if (value < 0 || value > 1) return fail(ctx, PEB_E_INVALID_ARG, "warm_graph must be 0 or 1");
+    ctx->warm_graph = value;
+    return PEB_OK;
+  }
+  if (!strcmp(key, "warm_graph_min_hyp")) {
+    if (value < 2) return fail(ctx, PEB_E_INVALID_ARG, "warm_graph_min_hyp must be >= 2 (batches only)");
+    ctx->warm_graph_min_hyp = value;
     return PEB_OK;
   }
   if (!strcmp(key, "warm_bin")) {

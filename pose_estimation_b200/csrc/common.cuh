@@ -105,6 +105,8 @@ struct peb_ctx {
   int warm_upfront = 0;         // experimental: warm searches fetch the row bounds of their ball up front (nn_upfront.cuh):
                                 // 0 = off, 1 or 2 = boxes up to 2 x 2 rows, 3 = up to 3 x 3; unmeasured
   int warm_upfront_from = 2;    // ... from this iteration launch on (launch 1 searches balls of 1.3 cells: 61 % of its warps hold a lane beyond 3 x 3 rows)
+  int warm_graph = 1;           // batched warm launches search over the target's k-NN graph (nn_graph.cuh) instead of walking the grid
+  int warm_graph_min_hyp = 32;  // ... for batches of at least this many hypotheses (the graph costs one k-NN pass over the target)
   int warm_bin = 0;             // (measured: -6 %, off) batched warm launches bin the queries of a block by the rows their search walks (icp.cu : icp_iteration_binned_kernel)
   bool anchor_seed = true;      // iteration 0: one cold search per 32-point patch seeds the patch
   int coop_max_rows = 1024;     // first iteration of a batch: a patch verifies its 32 candidates together (nn_search.cuh) up to this many grid rows
@@ -149,6 +151,8 @@ struct peb_ctx {
   bool tgt_staged = false;            // tgt_raw (+ normals) holds a cloud; tgt_stage_event orders a replica's copy after it
   cudaEvent_t tgt_stage_event = nullptr;
   peb::Grid tgt_grid;
+  peb::DevBuf tgt_knn;                // k-nearest-neighbour graph of the target grid's points (nn_graph.cuh), 64 bytes per point,
+  bool tgt_knn_valid = false;         // built by the first batched align on this target that uses it
 
   // source (model)
   peb::DevBuf src;           // float4 xyz1, original order
@@ -272,6 +276,7 @@ int sac_plane_device(peb_ctx* ctx, const float4* d_pts, int n, const peb_sac_par
 int cvicp_register_device(peb_ctx* ctx, const float* h_model, size_t n_model, const float* h_scene, size_t n_scene,
                           const peb_cvicp_params* prm, double* poses, size_t n_poses, double* residuals);
 // normals.cu
+int target_graph_ensure(peb_ctx* ctx);  // builds ctx->tgt_knn for the current target grid if it is not there yet
 int normals_knn_device(peb_ctx* ctx, const float4* d_in, int n, int k, const float vp[3], float* d_out8,
                        int32_t* d_out_nn /*nullable, n x k original indices*/);
 

@@ -26,6 +26,7 @@
 #include <algorithm>
 
 #include "nn_cache.cuh"
+#include "nn_graph.cuh"
 #include "nn_search.cuh"
 #include "nn_upfront.cuh"
 
@@ -77,6 +78,7 @@ struct IcpLaunch {
   NnCache* cache;        // nullable, H x n_src candidate caches (nn_cache.cuh) of the cached warm launches
   float cache_r_cells;   // radius (cells) a cache entry's collecting search covers
   int cache_init;        // this launch is the first cached one: every entry is still garbage
+  const KnnRow* knn;     // nullable: the target's k-NN graph (nn_graph.cuh) for the warm searches
 };
 
 __global__ void icp_init_kernel(IcpState* __restrict__ states, const float* __restrict__ guesses, int H,
@@ -393,7 +395,8 @@ __device__ __forceinline__ NnBest first_iteration_search(const IcpLaunch& L, int
 // by its previous match when there is one), the correspondence is thresholded and added to the
 // estimator's moment sums.  Shared by the per-iteration kernel and the work-queue kernel.
 // UPF: the warm search fetches all row bounds of its ball up front (nn_upfront.cuh; experimental, off by default):
-// 0 = off, 2 / 3 = balls whose box spans up to 2 x 2 / 3 x 3 grid rows take that path
+// 0 = off, 2 / 3 = balls whose box spans up to 2 x 2 / 3 x 3 grid rows take that path; 4 = the search over the target's
+// k-NN graph (nn_graph.cuh; L.knn)
 template <int G, int EST, bool CERT, int UPF, int NACC>
 __device__ __forceinline__ void icp_query(const IcpLaunch& L, const int h, float4* __restrict__ work, const int i,
                                           const bool first, const bool apply, const float* T, CoopTile* tile,
@@ -443,8 +446,9 @@ __device__ __forceinline__ void icp_query(const IcpLaunch& L, const int h, float
         }
         *sl = slack;
       } else {
-        best = UPF ? grid_nn_warm_upfront<(UPF > 0 ? UPF : 2)>(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2)
-                   : grid_nn_warm(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2);
+        if (UPF == 4) best = grid_nn_warm_graph(L.grid, L.knn, p.x, p.y, p.z, j_prev, L.stop_d2);
+        else best = UPF ? grid_nn_warm_upfront<(UPF == 3 ? 3 : 2)>(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2)
+                        : grid_nn_warm(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2);
       }
     } else {
       best = grid_nn<G>(L.grid, p.x, p.y, p.z, L.stop_d2);
@@ -1101,6 +1105,12 @@ int launch_one_iteration(peb_ctx* ctx, const IcpLaunch& L, size_t H, int estimat
 #undef PEB_ICP_LAUNCH_UPF
     return PEB_OK;
   }
+  // warm launches of a batch over the target's k-NN graph (nn_graph.cuh; "warm_graph")
+  if (G == 1 && !FIRST && !cert && !L.cache && L.warm && L.knn && H > 1) {
+    if (svd) PEB_LAUNCH_PDL(ctx, (icp_iteration_kernel<1, S, kMinBlocksBatch, false, false, 4>), grid, dim3(kIcpThreads), L);
+    else     PEB_LAUNCH_PDL(ctx, (icp_iteration_kernel<1, P, kMinBlocksBatch, false, false, 4>), grid, dim3(kIcpThreads), L);
+    return PEB_OK;
+  }
   // warm launches of a batch with the queries of a block binned by the size of their search ("warm_bin")
   if (G == 1 && !FIRST && !cert && !L.cache && L.warm && ctx->warm_bin && H > 1) {
     if (svd) PEB_LAUNCH_PDL(ctx, (icp_iteration_binned_kernel<S, kMinBlocksBatch>), grid, dim3(kIcpThreads), L);
@@ -1296,6 +1306,12 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
   }
   Lw.blocks_per_hyp = blocks_for(n, H, g_warm, ctx->blocks_factor);
   Lw.warm = ctx->warm_start ? 1 : 0;
+  // the warm searches of a large enough batch run over the target's k-NN graph (built once per target)
+  if (ctx->warm_graph && ctx->warm_start && g_warm == 1 && !single_mode && !(L.margin > 0.0f) && !ctx->warm_upfront &&
+      !ctx->warm_bin && ctx->nn_cache_from == 0 && H >= static_cast<size_t>(ctx->warm_graph_min_hyp) && launches > 1) {
+    PEB_TRY(target_graph_ensure(ctx));
+    Lw.knn = ctx->tgt_knn.as<KnnRow>();
+  }
   // the candidate cache of the warm launches from launch nn_cache_from on (0: never)
   const int cache_from = (ctx->nn_cache_from > 0 && ctx->warm_start && g_warm == 1 && !(L.margin > 0.0f)) ? ctx->nn_cache_from : 0;
   NnCache* cache_buf = nullptr;

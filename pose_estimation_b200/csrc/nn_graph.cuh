@@ -1,0 +1,92 @@
+// nn_graph.cuh — exact warm nearest-neighbour search over a k-nearest-neighbour graph of the TARGET.
+//
+// The warm searches of a batched align start from last iteration's match s and have to PROVE that nothing is closer to
+// the moved query q (or find what is).  The grid walk (core_math.cuh : grid_ball_search) proves it by scanning every
+// cell the ball of radius |q - s| touches: ~3 grid rows and ~16 points per query on C4, per-lane loops of different
+// lengths, 8 dependent load levels.  The scene does not change during the 30 x 1024 x 50 000 searches of a batch, so
+// the neighbourhood of every target point is computed ONCE (normals.cu : knn_graph_kernel):
+//
+//   row(s) = the sorted positions of the kGraphK nearest other target points of s in ascending (distance, position)
+//            order, and the squared distance from s to the first point that a scan of 4, 8 or all kGraphK of them has
+//            NOT examined (+inf where there is none).
+//
+// Certificate.  With d = |q - s|, a point p closer to q than s satisfies |s - p| <= |s - q| + |q - p| < 2 d.  Rows are
+// sorted by |s - p|, so once the first unexamined point of a row is farther than 2 d from s, every such p has been
+// compared: the best of s and the examined points IS the nearest neighbour.  On C4 the first four neighbours settle
+// most late-iteration queries: one 64-byte row and four gathers that hit L1.  Rows that cannot give the certificate
+// (2 d beyond the kGraphK-th neighbour) are still scanned completely — a greedy step on the graph that usually lands
+// next to the true match, whose own (smaller) ball is then tried — and if a full row does not improve the candidate
+// either, the grid walk finishes the search from the best point found (exact for any candidate).  Every comparison
+// uses the library's tie rule (smaller squared distance, then lower original index; nn_consider), which does not
+// depend on the order candidates are met in, so the result is bit-identical to the grid search's
+// (tests/test_gpu_warm_options.py; on the CPU against brute force: tests/test_host_fuzz.py).
+//
+// Rounding: the row order and the stored distances are the float values l2_simple(s, p) of the kernel that built the
+// rows; the triangle inequality is applied with a relative margin of 1e-5 on 4 d^2, three orders of magnitude above
+// the rounding of the squared distances involved.
+#pragma once
+
+#include "core_math.cuh"
+
+namespace peb {
+
+constexpr int kGraphK = 12;  // neighbours per row
+
+struct __align__(16) KnnRow {
+  uint32_t pos[kGraphK];  // sorted positions of the kGraphK nearest, ascending (distance, position); 0xFFFFFFFF: none
+  float next2[3];         // |s - p|^2 of neighbour 5, 9 and kGraphK + 1: the nearest point a scan of 4 / 8 / all has not seen
+  float spare;
+};
+static_assert(sizeof(KnnRow) == 64, "one row = two 32-byte sectors");
+// (Rows of 128 bytes that also carry the coordinates of the first four neighbours — no second gather for most queries —
+//  were measured: slower, 1.77 against 1.56 ms per late C4 launch.  The copies take the graph from 32 to 65 MB of L2 and
+//  are private to a row, while gathers from the 8 MB point array are shared by neighbouring queries and hit L1.)
+
+constexpr int kGraphMaxRounds = 6;  // greedy steps before the grid walk takes over (late iterations need 1-2)
+
+// Exact 1-NN of q given a candidate at sorted position j_prev (last iteration's match).
+PEB_HD NnBest grid_nn_warm_graph(const GridView& g, const KnnRow* __restrict__ rows, float qx, float qy, float qz,
+                                 int j_prev, float limit_d2) {
+  NnBest best;
+  int js = j_prev;
+  // the candidate, the first four positions of its row and the row's three distances: independent loads
+  const KnnRow* row = rows + js;
+  uint4 p0 = *reinterpret_cast<const uint4*>(row->pos);
+  float4 nx = *reinterpret_cast<const float4*>(row->next2);
+  {
+    const float4 s = g.pts[j_prev];
+    best.d2 = l2_simple(qx, qy, qz, s.x, s.y, s.z);
+    best.idx = point_index(s);
+    best.j = j_prev;
+  }
+  for (int round = 0; round < kGraphMaxRounds; ++round) {
+    const float lim = 4.0f * best.d2 * 1.00001f;
+    bool proven = false;
+#pragma unroll 1
+    for (int c = 0; c < kGraphK / 4 && !proven; ++c) {
+      const uint4 pc = c == 0 ? p0 : *reinterpret_cast<const uint4*>(row->pos + 4 * c);
+      const uint32_t pos[4] = {pc.x, pc.y, pc.z, pc.w};
+      float4 n[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)  // (independent gathers; an empty slot reads the row's own point)
+        n[k] = g.pts[pos[k] == 0xFFFFFFFFu ? static_cast<uint32_t>(js) : pos[k]];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (pos[k] != 0xFFFFFFFFu)
+          nn_consider(best, l2_simple(qx, qy, qz, n[k].x, n[k].y, n[k].z), point_index(n[k]), static_cast<int>(pos[k]));
+      // (+inf when nothing is left: everything has been compared)
+      proven = (c == 0 ? nx.x : c == 1 ? nx.y : nx.z) > lim;
+    }
+    // proven: every point within 2 d of s has been compared, and nothing else can be closer to q than s is
+    if (proven) return best;
+    if (best.j == js) break;  // no certificate and no better point on the graph: the grid walk decides
+    js = best.j;              // a closer point: its ball is smaller, try its row
+    row = rows + js;
+    p0 = *reinterpret_cast<const uint4*>(row->pos);
+    nx = *reinterpret_cast<const float4*>(row->next2);
+  }
+  grid_ball_search(g, qx, qy, qz, limit_d2, best);
+  return best;
+}
+
+}  // namespace peb

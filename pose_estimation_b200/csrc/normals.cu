@@ -18,6 +18,9 @@
 // k > 32, or leftovers (normals_knn_kernel): one thread per query; its candidate list lives in shared memory, column
 // per thread, kept sorted by insertion, rings until the bound proves the list.
 // Algorithmic HBM bytes: N * (16 read + 16 k gather + 32 write).
+#include <algorithm>
+
+#include "nn_graph.cuh"
 #include "nn_search.cuh"
 
 namespace peb {
@@ -212,15 +215,10 @@ __device__ __forceinline__ void reglist_scan_range(const GridView& g, uint32_t s
   }
 }
 
+// the kk nearest points of p (grid g, the point itself included if it is in g) in slots K - kk .. K - 1, ascending
+// (distance, position); slots in front hold sentinels (j = -1)
 template <int K>
-__global__ void __launch_bounds__(128, 4) normals_reglist_kernel(const GridView g, int k, float vx, float vy, float vz,
-                                                                 float* __restrict__ out8, int32_t* __restrict__ out_nn) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= g.n) return;
-  const float4 p = g.pts[q];
-  const int orig = __float_as_int(p.w);
-  const int kk = min(k, g.n);  // neighbours wanted
-  RegList<K> l;
+__device__ __forceinline__ void reglist_knn(const GridView& g, const float4& p, int kk, RegList<K>& l) {
 #pragma unroll
   for (int i = 0; i < K; ++i) {
     const bool sentinel = i < K - kk;
@@ -258,6 +256,18 @@ __global__ void __launch_bounds__(128, 4) normals_reglist_kernel(const GridView 
       }
     }
   }
+}
+
+template <int K>
+__global__ void __launch_bounds__(128, 4) normals_reglist_kernel(const GridView g, int k, float vx, float vy, float vz,
+                                                                 float* __restrict__ out8, int32_t* __restrict__ out_nn) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= g.n) return;
+  const float4 p = g.pts[q];
+  const int orig = __float_as_int(p.w);
+  const int kk = min(k, g.n);  // neighbours wanted
+  RegList<K> l;
+  reglist_knn<K>(g, p, kk, l);
   // the neighbours in list order: slots K - kk .. K - 1 ([PCL] normal_3d.hpp: computePointNormal over nn_indices)
   int count = 0;
   float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -292,7 +302,53 @@ int launch_reglist(peb_ctx* ctx, const GridView& g, int k, const float vp[3], fl
   return PEB_OK;
 }
 
+// The k-nearest-neighbour graph of a grid's own points (nn_graph.cuh): row(q) = the kGraphK nearest OTHER points of
+// sorted position q, ascending (distance, position), and the distances from q to neighbours 5, 9 and kGraphK + 1.
+constexpr int kGraphSlots = kGraphK + 2;  // the point itself + the row + the point behind the row
+__global__ void __launch_bounds__(128, 4) knn_graph_kernel(const GridView g, KnnRow* __restrict__ rows) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= g.n) return;
+  const float4 p = g.pts[q];
+  RegList<kGraphSlots> l;
+  reglist_knn<kGraphSlots>(g, p, min(kGraphSlots, g.n), l);
+  // the other points in list order: entry m of the row comes from the m-th slot that is filled and not q itself
+  uint32_t pos[kGraphK + 1];
+  float d2[kGraphK + 1];
+#pragma unroll
+  for (int t = 0; t <= kGraphK; ++t) {
+    pos[t] = 0xFFFFFFFFu;
+    d2[t] = pos_inf();
+  }
+  int m = 0;
+#pragma unroll
+  for (int s = 0; s < kGraphSlots; ++s) {
+    if (l.j[s] >= 0 && l.j[s] != q) {
+#pragma unroll
+      for (int t = 0; t <= kGraphK; ++t)
+        if (t == m) {
+          pos[t] = static_cast<uint32_t>(l.j[s]);
+          d2[t] = l.d[s];
+        }
+      ++m;
+    }
+  }
+  uint4* u = reinterpret_cast<uint4*>(rows + q);
+#pragma unroll
+  for (int c = 0; c < kGraphK / 4; ++c) u[c] = make_uint4(pos[4 * c], pos[4 * c + 1], pos[4 * c + 2], pos[4 * c + 3]);
+  reinterpret_cast<float4*>(u)[kGraphK / 4] = make_float4(d2[4], d2[8], d2[kGraphK], 0.0f);
+}
+
 }  // namespace
+
+// the graph of the target grid, built once per target and kept until the target changes (icp.cu asks for it)
+int target_graph_ensure(peb_ctx* ctx) {
+  if (ctx->tgt_knn_valid) return PEB_OK;
+  const GridView& g = ctx->tgt_grid.view;
+  PEB_CUDA(ctx, ctx->tgt_knn.ensure(std::max<size_t>(g.n, 1) * sizeof(KnnRow)));
+  if (g.n > 0) PEB_LAUNCH(ctx, knn_graph_kernel, ceil_div(g.n, 128), 128, 0, g, ctx->tgt_knn.as<KnnRow>());
+  ctx->tgt_knn_valid = true;
+  return PEB_OK;
+}
 
 int normals_knn_device(peb_ctx* ctx, const float4* d_in, int n, int k, const float vp[3], float* d_out8,
                        int32_t* d_out_nn) {

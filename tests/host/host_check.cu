@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../pose_estimation_b200/csrc/core_math.cuh"
+#include "../../pose_estimation_b200/csrc/nn_graph.cuh"
 #include "../../pose_estimation_b200/csrc/nn_upfront.cuh"
 
 using namespace peb;
@@ -169,6 +170,39 @@ HC_API void hc_grid_nn_warm_upfront(const float* tgt, size_t n, size_t tstride, 
     const float* p = q + i * (qstride / 4);
     NnBest b = rows3 ? grid_nn_warm_upfront<3>(g.v, p[0], p[1], p[2], pos[prev[i]], limit_d2)
                      : grid_nn_warm_upfront<2>(g.v, p[0], p[1], p[2], pos[prev[i]], limit_d2);
+    out_idx[i] = b.idx;
+    out_d2[i] = b.d2;
+  }
+}
+
+// the warm search over the target's k-NN graph (csrc/nn_graph.cuh): the rows are built here by brute force with the
+// arithmetic and the (distance, position) order of normals.cu : knn_graph_kernel; same interface as hc_grid_nn_warm.
+// out_rounds (nullable) is not filled by the search itself: the caller only checks results.
+HC_API void hc_grid_nn_warm_graph(const float* tgt, size_t n, size_t tstride, const float* q, size_t nq, size_t qstride,
+                                  float occupancy, const int32_t* prev, float limit_d2, int32_t* out_idx, float* out_d2) {
+  HostGrid g;
+  build_grid(tgt, n, tstride / 4, occupancy, 0.0f, g);
+  std::vector<int> pos(n, -1);
+  for (int j = 0; j < g.v.n; ++j) pos[point_index(g.pts[j])] = j;
+  std::vector<KnnRow> rows(std::max(g.v.n, 1));
+  std::vector<std::pair<float, int>> cand;
+  for (int sj = 0; sj < g.v.n; ++sj) {
+    const float4 s = g.pts[sj];
+    cand.clear();
+    for (int j = 0; j < g.v.n; ++j)
+      if (j != sj) cand.push_back({l2_simple(s.x, s.y, s.z, g.pts[j].x, g.pts[j].y, g.pts[j].z), j});
+    std::sort(cand.begin(), cand.end());
+    KnnRow& r = rows[sj];
+    memset(&r, 0, sizeof(r));
+    auto d2_of = [&](int k) { return k < (int)cand.size() ? cand[k].first : INFINITY; };
+    for (int k = 0; k < kGraphK; ++k) r.pos[k] = k < (int)cand.size() ? (uint32_t)cand[k].second : 0xFFFFFFFFu;
+    r.next2[0] = d2_of(4);
+    r.next2[1] = d2_of(8);
+    r.next2[2] = d2_of(kGraphK);
+  }
+  for (size_t i = 0; i < nq; ++i) {
+    const float* p = q + i * (qstride / 4);
+    NnBest b = grid_nn_warm_graph(g.v, rows.data(), p[0], p[1], p[2], pos[prev[i]], limit_d2);
     out_idx[i] = b.idx;
     out_d2[i] = b.d2;
   }

@@ -107,6 +107,31 @@ def test_warm_ball_search_is_exact_on_adversarial_clouds(hc, oracle, seed):  # n
                 assert np.array_equal(gi, bi), (name, occ, kind, np.flatnonzero(gi != bi)[:5])
 
 
+def grid_nn_warm_graph(hc, tgt, q, prev, occupancy, limit=np.inf):  # noqa: F811
+    tgt = np.ascontiguousarray(tgt, F)
+    idx = np.empty(len(q), np.int32)
+    d2 = np.empty(len(q), F)
+    hc.hc_grid_nn_warm_graph(tgt.ctypes.data, len(tgt), tgt.strides[0], q.ctypes.data, len(q), q.strides[0], occupancy,
+                             prev.ctypes.data, limit, idx.ctypes.data, d2.ctypes.data)
+    return idx, d2
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_knn_graph_warm_search_is_exact_on_adversarial_clouds(hc, oracle, seed):  # noqa: F811
+    """csrc/nn_graph.cuh: certificate from the candidate's k-NN row, greedy steps, grid walk as the last resort — exact
+    whatever the candidate (lattices full of ties, duplicates: more equal points than a row holds, clouds smaller than a row)"""
+    rng = np.random.default_rng(7000 + seed)
+    for name, tgt in clouds(rng).items():
+        q = queries(rng, tgt)
+        bi, bd = oracle.nn_bruteforce(tgt, q)
+        ok = np.flatnonzero(np.isfinite(tgt).all(1))
+        for occ in (1.0, 3.5):
+            for kind, prev in (("true", bi), ("next", ok[(np.searchsorted(ok, bi) + 1) % len(ok)]), ("random", rng.choice(ok, len(q)))):
+                gi, gd = grid_nn_warm_graph(hc, tgt, q, np.ascontiguousarray(prev, np.int32), occ)
+                assert np.array_equal(gd, bd), (name, occ, kind, np.flatnonzero(gd != bd)[:5])
+                assert np.array_equal(gi, bi), (name, occ, kind, np.flatnonzero(gi != bi)[:5])
+
+
 @pytest.mark.parametrize("seed", [0, 1])
 def test_warm_search_with_a_rejection_limit_is_exact_where_it_matters(hc, oracle, seed):  # noqa: F811
     """limit_d2 (the max-correspondence-distance cut): matches within the limit are exact, the others stay beyond it"""
