@@ -79,6 +79,8 @@ struct IcpLaunch {
   float cache_r_cells;   // radius (cells) a cache entry's collecting search covers
   int cache_init;        // this launch is the first cached one: every entry is still garbage
   const KnnRow* knn;     // nullable: the target's k-NN graph (nn_graph.cuh) for the warm searches
+  const double* knn_stat;  // [0] sum, [1] count of the finite outer bounds (next2[2]) of the graph's rows
+  float knn_kappa;       // a hypothesis searches over the graph once 4 * (its last MSE) * kappa < the mean outer bound
 };
 
 __global__ void icp_init_kernel(IcpState* __restrict__ states, const float* __restrict__ guesses, int H,
@@ -255,6 +257,19 @@ __device__ __forceinline__ void wait_for_hypothesis(const int* __restrict__ solv
   __syncthreads();
 }
 
+// Does hypothesis `st` search over the target's k-NN graph in this launch?  The graph pays once the matches are close
+// enough for its certificate (4 d^2 < the row's outer bound): while the hypothesis is still millimetres off, every query
+// would scan its row in vain and walk the grid afterwards.  The mean squared distance of the last iteration's
+// correspondences predicts this iteration's d^2; the choice only moves time (both searches are exact), so a coarse
+// predictor is enough.  kappa = 0: always.
+__device__ __forceinline__ bool graph_pays(const IcpLaunch& L, const IcpState* st) {
+  if (!L.knn) return false;
+  if (L.knn_kappa <= 0.0f) return true;
+  const double mse = __ldcg(&st->cur_mse);
+  const double cnt = __ldcg(L.knn_stat + 1);
+  return cnt > 0.0 && 4.0 * mse * static_cast<double>(L.knn_kappa) * cnt < __ldcg(L.knn_stat);
+}
+
 // adds one accepted correspondence (working point p, match best) to the estimator's moment sums
 template <int EST, int NACC>
 __device__ __forceinline__ void accumulate_pair_impl(const GridView& g, const float4& p, const NnBest& best,
@@ -399,8 +414,8 @@ __device__ __forceinline__ NnBest first_iteration_search(const IcpLaunch& L, int
 // k-NN graph (nn_graph.cuh; L.knn)
 template <int G, int EST, bool CERT, int UPF, int NACC>
 __device__ __forceinline__ void icp_query(const IcpLaunch& L, const int h, float4* __restrict__ work, const int i,
-                                          const bool first, const bool apply, const float* T, CoopTile* tile,
-                                          double (&acc)[NACC]) {
+                                          const bool first, const bool apply, const bool graph, const float* T,
+                                          CoopTile* tile, double (&acc)[NACC]) {
   const int lane_in_group = threadIdx.x & (G - 1);
   const bool in = i < L.n_src;
   float4 p = make_float4(0.f, 0.f, 0.f, 1.f);
@@ -446,7 +461,8 @@ __device__ __forceinline__ void icp_query(const IcpLaunch& L, const int h, float
         }
         *sl = slack;
       } else {
-        if (UPF == 4) best = grid_nn_warm_graph(L.grid, L.knn, p.x, p.y, p.z, j_prev, L.stop_d2);
+        if (UPF == 4) best = graph ? grid_nn_warm_graph(L.grid, L.knn, p.x, p.y, p.z, j_prev, L.stop_d2)
+                                   : grid_nn_warm(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2);
         else best = UPF ? grid_nn_warm_upfront<(UPF == 3 ? 3 : 2)>(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2)
                         : grid_nn_warm(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2);
       }
@@ -480,7 +496,7 @@ __device__ __forceinline__ void icp_iteration_body(const IcpLaunch& L, const int
   __shared__ double sm[kIcpThreads / 32][kAccMax];
   __shared__ double sm_tot[kAccMax];
   __shared__ float s_inc[16];
-  __shared__ int s_flags[3];  // active, first iteration, apply transform
+  __shared__ int s_flags[4];  // active, first iteration, apply transform, warm searches over the k-NN graph
   __shared__ CoopTile s_tile[kIcpThreads / 32];  // first iteration of a batch: one staging tile per warp
   IcpState* st = L.states + h;
   // the transform every query of this launch is moved by: the guess in launch 0, else the last increment
@@ -500,6 +516,8 @@ __device__ __forceinline__ void icp_iteration_body(const IcpLaunch& L, const int
     s_flags[0] = active;
     s_flags[1] = first;
     s_flags[2] = apply;
+    const int graph = (UPF == 4 && graph_pays(L, st)) ? 1 : 0;
+    s_flags[3] = graph;
   }
   __syncthreads();
   if (!s_flags[0]) return;
@@ -515,8 +533,9 @@ __device__ __forceinline__ void icp_iteration_body(const IcpLaunch& L, const int
   float4* work = L.work + static_cast<size_t>(h) * L.n_src;
   constexpr int kQ = kIcpThreads / G;  // queries per block per pass
   const int q_local = threadIdx.x / G;
+  const bool graph = UPF == 4 && s_flags[3] != 0;
   for (int base = blk * kQ; base < L.n_src; base += L.blocks_per_hyp * kQ)
-    icp_query<G, EST, CERT, UPF>(L, h, work, base + q_local, first, apply, T, &s_tile[threadIdx.x >> 5], acc);
+    icp_query<G, EST, CERT, UPF>(L, h, work, base + q_local, first, apply, graph, T, &s_tile[threadIdx.x >> 5], acc);
 
   if (L.dbg) t_dbg[1] = global_ns();
   const double r = block_reduce_acc<NACC>(acc, sm);
@@ -941,6 +960,7 @@ __global__ void __launch_bounds__(kIcpThreads) icp_fitness_kernel(const IcpLaunc
   float T[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) T[i] = __ldcg(&st->final_t.m[i]);
+  const bool graph = G == 1 && graph_pays(L, st);  // (uniform over the block)
   double acc[2] = {0.0, 0.0};
   const int lane_in_group = threadIdx.x & (G - 1);
   constexpr int kQ = kIcpThreads / G;
@@ -978,7 +998,8 @@ __global__ void __launch_bounds__(kIcpThreads) icp_fitness_kernel(const IcpLaunc
           best.idx = __float_as_int(t.w);
           best.j = j_prev;
         } else {
-          best = grid_nn_warm(L.grid, qx, qy, qz, j_prev, L.fitness_stop_d2);
+          best = graph ? grid_nn_warm_graph(L.grid, L.knn, qx, qy, qz, j_prev, L.fitness_stop_d2)
+                       : grid_nn_warm(L.grid, qx, qy, qz, j_prev, L.fitness_stop_d2);
         }
       } else {
         best = grid_nn<G>(L.grid, qx, qy, qz, L.fitness_stop_d2);
@@ -1311,6 +1332,8 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
       !ctx->warm_bin && ctx->nn_cache_from == 0 && H >= static_cast<size_t>(ctx->warm_graph_min_hyp) && launches > 1) {
     PEB_TRY(target_graph_ensure(ctx));
     Lw.knn = ctx->tgt_knn.as<KnnRow>();
+    Lw.knn_stat = ctx->tgt_knn_stat.as<double>();
+    Lw.knn_kappa = ctx->warm_graph_kappa;
   }
   // the candidate cache of the warm launches from launch nn_cache_from on (0: never)
   const int cache_from = (ctx->nn_cache_from > 0 && ctx->warm_start && g_warm == 1 && !(L.margin > 0.0f)) ? ctx->nn_cache_from : 0;

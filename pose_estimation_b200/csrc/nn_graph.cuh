@@ -33,7 +33,8 @@ namespace peb {
 constexpr int kGraphK = 12;  // neighbours per row
 
 struct __align__(16) KnnRow {
-  uint32_t pos[kGraphK];  // sorted positions of the kGraphK nearest, ascending (distance, position); 0xFFFFFFFF: none
+  uint32_t pos[kGraphK];  // sorted positions of the kGraphK nearest, ascending (distance, position); a cloud with fewer
+                          // points fills up with the row's own position (comparing s with itself changes nothing)
   float next2[3];         // |s - p|^2 of neighbour 5, 9 and kGraphK + 1: the nearest point a scan of 4 / 8 / all has not seen
   float spare;
 };
@@ -67,13 +68,16 @@ PEB_HD NnBest grid_nn_warm_graph(const GridView& g, const KnnRow* __restrict__ r
       const uint4 pc = c == 0 ? p0 : *reinterpret_cast<const uint4*>(row->pos + 4 * c);
       const uint32_t pos[4] = {pc.x, pc.y, pc.z, pc.w};
       float4 n[4];
+      float d2[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)  // (independent gathers; an empty slot reads the row's own point)
-        n[k] = g.pts[pos[k] == 0xFFFFFFFFu ? static_cast<uint32_t>(js) : pos[k]];
+      for (int k = 0; k < 4; ++k) n[k] = g.pts[pos[k]];  // (independent gathers)
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (pos[k] != 0xFFFFFFFFu)
-          nn_consider(best, l2_simple(qx, qy, qz, n[k].x, n[k].y, n[k].z), point_index(n[k]), static_cast<int>(pos[k]));
+      for (int k = 0; k < 4; ++k) d2[k] = l2_simple(qx, qy, qz, n[k].x, n[k].y, n[k].z);
+      // (most chunks hold nothing that beats or ties the candidate: one test instead of four tie rules)
+      if (fminf(fminf(d2[0], d2[1]), fminf(d2[2], d2[3])) <= best.d2) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) nn_consider(best, d2[k], point_index(n[k]), static_cast<int>(pos[k]));
+      }
       // (+inf when nothing is left: everything has been compared)
       proven = (c == 0 ? nx.x : c == 1 ? nx.y : nx.z) > lim;
     }

@@ -305,9 +305,8 @@ int launch_reglist(peb_ctx* ctx, const GridView& g, int k, const float vp[3], fl
 // The k-nearest-neighbour graph of a grid's own points (nn_graph.cuh): row(q) = the kGraphK nearest OTHER points of
 // sorted position q, ascending (distance, position), and the distances from q to neighbours 5, 9 and kGraphK + 1.
 constexpr int kGraphSlots = kGraphK + 2;  // the point itself + the row + the point behind the row
-__global__ void __launch_bounds__(128, 4) knn_graph_kernel(const GridView g, KnnRow* __restrict__ rows) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= g.n) return;
+// writes row q; returns the row's outer bound (squared distance from q to neighbour kGraphK + 1; +inf: none)
+__device__ __forceinline__ float knn_graph_row(const GridView& g, KnnRow* __restrict__ rows, int q) {
   const float4 p = g.pts[q];
   RegList<kGraphSlots> l;
   reglist_knn<kGraphSlots>(g, p, min(kGraphSlots, g.n), l);
@@ -316,7 +315,7 @@ __global__ void __launch_bounds__(128, 4) knn_graph_kernel(const GridView g, Knn
   float d2[kGraphK + 1];
 #pragma unroll
   for (int t = 0; t <= kGraphK; ++t) {
-    pos[t] = 0xFFFFFFFFu;
+    pos[t] = static_cast<uint32_t>(q);  // (a missing neighbour: the point itself, see nn_graph.cuh)
     d2[t] = pos_inf();
   }
   int m = 0;
@@ -336,6 +335,27 @@ __global__ void __launch_bounds__(128, 4) knn_graph_kernel(const GridView g, Knn
 #pragma unroll
   for (int c = 0; c < kGraphK / 4; ++c) u[c] = make_uint4(pos[4 * c], pos[4 * c + 1], pos[4 * c + 2], pos[4 * c + 3]);
   reinterpret_cast<float4*>(u)[kGraphK / 4] = make_float4(d2[4], d2[8], d2[kGraphK], 0.0f);
+  return d2[kGraphK];
+}
+
+__global__ void __launch_bounds__(128, 4) knn_graph_kernel(const GridView g, KnnRow* __restrict__ rows,
+                                                           double* __restrict__ stat) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  // (no early return: the block sums its rows' outer bounds at the end)
+  float outer = 0.0f;
+  if (q < g.n) outer = knn_graph_row(g, rows, q);
+  // sum and count of the finite outer bounds (icp.cu decides per hypothesis from their mean when the graph pays)
+  float v = (outer > 0.0f && outer < pos_inf()) ? outer : 0.0f;
+  float c = (outer > 0.0f && outer < pos_inf()) ? 1.0f : 0.0f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+  }
+  if ((threadIdx.x & 31) == 0 && c > 0.0f) {
+    atomicAdd(stat, static_cast<double>(v));
+    atomicAdd(stat + 1, static_cast<double>(c));
+  }
 }
 
 }  // namespace
@@ -345,7 +365,10 @@ int target_graph_ensure(peb_ctx* ctx) {
   if (ctx->tgt_knn_valid) return PEB_OK;
   const GridView& g = ctx->tgt_grid.view;
   PEB_CUDA(ctx, ctx->tgt_knn.ensure(std::max<size_t>(g.n, 1) * sizeof(KnnRow)));
-  if (g.n > 0) PEB_LAUNCH(ctx, knn_graph_kernel, ceil_div(g.n, 128), 128, 0, g, ctx->tgt_knn.as<KnnRow>());
+  PEB_CUDA(ctx, ctx->tgt_knn_stat.ensure(2 * sizeof(double)));
+  PEB_CUDA(ctx, cudaMemsetAsync(ctx->tgt_knn_stat.p, 0, 2 * sizeof(double), ctx->stream));
+  if (g.n > 0)
+    PEB_LAUNCH(ctx, knn_graph_kernel, ceil_div(g.n, 128), 128, 0, g, ctx->tgt_knn.as<KnnRow>(), ctx->tgt_knn_stat.as<double>());
   ctx->tgt_knn_valid = true;
   return PEB_OK;
 }

@@ -195,7 +195,7 @@ HC_API void hc_grid_nn_warm_graph(const float* tgt, size_t n, size_t tstride, co
     KnnRow& r = rows[sj];
     memset(&r, 0, sizeof(r));
     auto d2_of = [&](int k) { return k < (int)cand.size() ? cand[k].first : INFINITY; };
-    for (int k = 0; k < kGraphK; ++k) r.pos[k] = k < (int)cand.size() ? (uint32_t)cand[k].second : 0xFFFFFFFFu;
+    for (int k = 0; k < kGraphK; ++k) r.pos[k] = k < (int)cand.size() ? (uint32_t)cand[k].second : (uint32_t)sj;
     r.next2[0] = d2_of(4);
     r.next2[1] = d2_of(8);
     r.next2[2] = d2_of(kGraphK);

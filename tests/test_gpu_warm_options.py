@@ -29,7 +29,10 @@ def scene_small(oracle):
     return synth.make_c2(scale=0.25, downsample=lambda p, leaf: oracle.voxel_grid(p, leaf)[0])
 
 
-VARIANTS = {"plain": (("warm_graph", 0), ("warm_bin", 0)), "graph": (("warm_graph", 1), ("warm_graph_min_hyp", 2), ("warm_bin", 0)),
+VARIANTS = {"plain": (("warm_graph", 0), ("warm_bin", 0)),
+            # every warm launch over the graph / hypotheses switch to it when their MSE says the certificate will hold
+            "graph": (("warm_graph", 1), ("warm_graph_min_hyp", 2), ("warm_graph_kappa_x100", 0), ("warm_bin", 0)),
+            "graph_auto": (("warm_graph", 1), ("warm_graph_min_hyp", 2), ("warm_bin", 0)),
             "bin": (("warm_graph", 0), ("warm_bin", 1))}
 
 
@@ -54,7 +57,7 @@ def _run(pcl, source, target, cls, normals, guesses, variant, opts=(), **params)
     return out
 
 
-@pytest.mark.parametrize("variant", ["graph", "bin"])
+@pytest.mark.parametrize("variant", ["graph", "graph_auto", "bin"])
 def test_warm_variants_never_change_results(pcl, scene_small, variant):
     p = scene_small
     rng = np.random.default_rng(15)
@@ -69,7 +72,7 @@ def test_warm_variants_never_change_results(pcl, scene_small, variant):
                _run(pcl, p.source, p.target, pcl.IterativeClosestPoint, None, guesses, "plain", opts, **kw)
 
 
-@pytest.mark.parametrize("variant", ["graph", "bin"])
+@pytest.mark.parametrize("variant", ["graph", "graph_auto", "bin"])
 def test_warm_variants_point_to_plane_rejector_and_criteria(pcl, scene_small, variant):
     p = scene_small
     c = pcl.Context(0)
@@ -87,7 +90,7 @@ def test_warm_variants_point_to_plane_rejector_and_criteria(pcl, scene_small, va
     assert len({r[-32:] for r in a}) > 1  # (the records differ between hypotheses: the comparison is not vacuous)
 
 
-@pytest.mark.parametrize("variant", ["graph", "bin"])
+@pytest.mark.parametrize("variant", ["graph", "graph_auto", "bin"])
 def test_warm_variants_nonfinite_points_far_hypotheses_and_tiny_sources(pcl, scene_small, variant):
     p = scene_small
     rng = np.random.default_rng(17)
