@@ -30,18 +30,27 @@
 
 namespace peb {
 
-constexpr int kGraphK = 12;  // neighbours per row
+constexpr int kGraphHalves = 1;              // 64-byte half rows per row
+constexpr int kGraphK = 12 * kGraphHalves;   // neighbours per row
 
-struct __align__(16) KnnRow {
-  uint32_t pos[kGraphK];  // sorted positions of the kGraphK nearest, ascending (distance, position); a cloud with fewer
-                          // points fills up with the row's own position (comparing s with itself changes nothing)
-  float next2[3];         // |s - p|^2 of neighbour 5, 9 and kGraphK + 1: the nearest point a scan of 4 / 8 / all has not seen
+// half h of a row: neighbours 12 h .. 12 h + 11 and the distances that end a scan after 4, 8 and 12 of them.  Most
+// queries are settled by the first half; the second one is only touched by queries whose ball reaches past it.
+struct __align__(16) KnnHalf {
+  uint32_t pos[12];  // sorted positions, ascending (distance, position); a cloud with fewer points fills up with the row's
+                     // own position (comparing s with itself changes nothing)
+  float next2[3];    // |s - p|^2 of the first neighbour BEHIND chunk 0, 1, 2 of this half (+inf: there is none)
   float spare;
 };
-static_assert(sizeof(KnnRow) == 64, "one row = two 32-byte sectors");
-// (Rows of 128 bytes that also carry the coordinates of the first four neighbours — no second gather for most queries —
-//  were measured: slower, 1.77 against 1.56 ms per late C4 launch.  The copies take the graph from 32 to 65 MB of L2 and
-//  are private to a row, while gathers from the 8 MB point array are shared by neighbouring queries and hit L1.)
+struct __align__(16) KnnRow {
+  KnnHalf half[kGraphHalves];
+};
+static_assert(sizeof(KnnRow) == 64 * kGraphHalves, "a half row = two 32-byte sectors");
+// (Two halves = 24 neighbours per row, certificates up to d = 1.3 mm on C4 instead of 0.95: measured 14 390 against
+//  14 400 hypotheses/s.  Launches 5-12 get 5 % faster, the late ones 12 % slower — rows at a stride of 128 bytes fill
+//  L1 / L2 lines with second halves nobody reads — and the graph takes twice as long to build.)
+// (Rows that also carry the coordinates of the first four neighbours — no second gather for most queries — were
+//  measured: slower, 1.77 against 1.56 ms per late C4 launch.  The copies are private to a row, while gathers from the
+//  8 MB point array are shared by neighbouring queries and hit L1.)
 
 constexpr int kGraphMaxRounds = 6;  // greedy steps before the grid walk takes over (late iterations need 1-2)
 
@@ -52,8 +61,8 @@ PEB_HD NnBest grid_nn_warm_graph(const GridView& g, const KnnRow* __restrict__ r
   int js = j_prev;
   // the candidate, the first four positions of its row and the row's three distances: independent loads
   const KnnRow* row = rows + js;
-  uint4 p0 = *reinterpret_cast<const uint4*>(row->pos);
-  float4 nx = *reinterpret_cast<const float4*>(row->next2);
+  uint4 p0 = *reinterpret_cast<const uint4*>(row->half[0].pos);
+  float4 nx = *reinterpret_cast<const float4*>(row->half[0].next2);
   {
     const float4 s = g.pts[j_prev];
     best.d2 = l2_simple(qx, qy, qz, s.x, s.y, s.z);
@@ -64,30 +73,35 @@ PEB_HD NnBest grid_nn_warm_graph(const GridView& g, const KnnRow* __restrict__ r
     const float lim = 4.0f * best.d2 * 1.00001f;
     bool proven = false;
 #pragma unroll 1
-    for (int c = 0; c < kGraphK / 4 && !proven; ++c) {
-      const uint4 pc = c == 0 ? p0 : *reinterpret_cast<const uint4*>(row->pos + 4 * c);
-      const uint32_t pos[4] = {pc.x, pc.y, pc.z, pc.w};
-      float4 n[4];
-      float d2[4];
+    for (int hf = 0; hf < kGraphHalves && !proven; ++hf) {
+      const KnnHalf* half = row->half + hf;
+      const float4 nxh = hf == 0 ? nx : *reinterpret_cast<const float4*>(half->next2);
+#pragma unroll 1
+      for (int c = 0; c < 3 && !proven; ++c) {
+        const uint4 pc = (hf == 0 && c == 0) ? p0 : *reinterpret_cast<const uint4*>(half->pos + 4 * c);
+        const uint32_t pos[4] = {pc.x, pc.y, pc.z, pc.w};
+        float4 n[4];
+        float d2[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) n[k] = g.pts[pos[k]];  // (independent gathers)
+        for (int k = 0; k < 4; ++k) n[k] = g.pts[pos[k]];  // (independent gathers)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) d2[k] = l2_simple(qx, qy, qz, n[k].x, n[k].y, n[k].z);
-      // (most chunks hold nothing that beats or ties the candidate: one test instead of four tie rules)
-      if (fminf(fminf(d2[0], d2[1]), fminf(d2[2], d2[3])) <= best.d2) {
+        for (int k = 0; k < 4; ++k) d2[k] = l2_simple(qx, qy, qz, n[k].x, n[k].y, n[k].z);
+        // (most chunks hold nothing that beats or ties the candidate: one test instead of four tie rules)
+        if (fminf(fminf(d2[0], d2[1]), fminf(d2[2], d2[3])) <= best.d2) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) nn_consider(best, d2[k], point_index(n[k]), static_cast<int>(pos[k]));
+          for (int k = 0; k < 4; ++k) nn_consider(best, d2[k], point_index(n[k]), static_cast<int>(pos[k]));
+        }
+        // (+inf when nothing is left: everything has been compared)
+        proven = (c == 0 ? nxh.x : c == 1 ? nxh.y : nxh.z) > lim;
       }
-      // (+inf when nothing is left: everything has been compared)
-      proven = (c == 0 ? nx.x : c == 1 ? nx.y : nx.z) > lim;
     }
     // proven: every point within 2 d of s has been compared, and nothing else can be closer to q than s is
     if (proven) return best;
     if (best.j == js) break;  // no certificate and no better point on the graph: the grid walk decides
     js = best.j;              // a closer point: its ball is smaller, try its row
     row = rows + js;
-    p0 = *reinterpret_cast<const uint4*>(row->pos);
-    nx = *reinterpret_cast<const float4*>(row->next2);
+    p0 = *reinterpret_cast<const uint4*>(row->half[0].pos);
+    nx = *reinterpret_cast<const float4*>(row->half[0].next2);
   }
   grid_ball_search(g, qx, qy, qz, limit_d2, best);
   return best;

@@ -303,7 +303,8 @@ int launch_reglist(peb_ctx* ctx, const GridView& g, int k, const float vp[3], fl
 }
 
 // The k-nearest-neighbour graph of a grid's own points (nn_graph.cuh): row(q) = the kGraphK nearest OTHER points of
-// sorted position q, ascending (distance, position), and the distances from q to neighbours 5, 9 and kGraphK + 1.
+// sorted position q, ascending (distance, position), in half rows of 12 with the distances from q to the neighbour
+// behind every chunk of four.
 constexpr int kGraphSlots = kGraphK + 2;  // the point itself + the row + the point behind the row
 // writes row q; returns the row's outer bound (squared distance from q to neighbour kGraphK + 1; +inf: none)
 __device__ __forceinline__ float knn_graph_row(const GridView& g, KnnRow* __restrict__ rows, int q) {
@@ -333,8 +334,14 @@ __device__ __forceinline__ float knn_graph_row(const GridView& g, KnnRow* __rest
   }
   uint4* u = reinterpret_cast<uint4*>(rows + q);
 #pragma unroll
-  for (int c = 0; c < kGraphK / 4; ++c) u[c] = make_uint4(pos[4 * c], pos[4 * c + 1], pos[4 * c + 2], pos[4 * c + 3]);
-  reinterpret_cast<float4*>(u)[kGraphK / 4] = make_float4(d2[4], d2[8], d2[kGraphK], 0.0f);
+  for (int h = 0; h < kGraphHalves; ++h) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int t = 12 * h + 4 * c;
+      u[4 * h + c] = make_uint4(pos[t], pos[t + 1], pos[t + 2], pos[t + 3]);
+    }
+    reinterpret_cast<float4*>(u)[4 * h + 3] = make_float4(d2[12 * h + 4], d2[12 * h + 8], d2[12 * h + 12], 0.0f);
+  }
   return d2[kGraphK];
 }
 

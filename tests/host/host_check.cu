@@ -195,10 +195,10 @@ HC_API void hc_grid_nn_warm_graph(const float* tgt, size_t n, size_t tstride, co
     KnnRow& r = rows[sj];
     memset(&r, 0, sizeof(r));
     auto d2_of = [&](int k) { return k < (int)cand.size() ? cand[k].first : INFINITY; };
-    for (int k = 0; k < kGraphK; ++k) r.pos[k] = k < (int)cand.size() ? (uint32_t)cand[k].second : (uint32_t)sj;
-    r.next2[0] = d2_of(4);
-    r.next2[1] = d2_of(8);
-    r.next2[2] = d2_of(kGraphK);
+    for (int h = 0; h < kGraphHalves; ++h) {
+      for (int k = 0; k < 12; ++k) r.half[h].pos[k] = 12 * h + k < (int)cand.size() ? (uint32_t)cand[12 * h + k].second : (uint32_t)sj;
+      for (int c = 0; c < 3; ++c) r.half[h].next2[c] = d2_of(12 * h + 4 * c + 4);
+    }
   }
   for (size_t i = 0; i < nq; ++i) {
     const float* p = q + i * (qstride / 4);
