@@ -299,6 +299,11 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
     ctx->warm_graph_kappa = value / 100.0f;
     return PEB_OK;
   }
+  if (!strcmp(key, "warm_graph_queue")) {
+    if (value != 0 && value != 8 && value != 16) return fail(ctx, PEB_E_INVALID_ARG, "warm_graph_queue must be 0, 8 or 16");
+    ctx->warm_graph_queue = value;
+    return PEB_OK;
+  }
   if (!strcmp(key, "warm_graph_min_hyp")) {
     if (value < 2) return fail(ctx, PEB_E_INVALID_ARG, "warm_graph_min_hyp must be >= 2 (batches only)");
     ctx->warm_graph_min_hyp = value;

@@ -461,7 +461,7 @@ __device__ __forceinline__ void icp_query(const IcpLaunch& L, const int h, float
         }
         *sl = slack;
       } else {
-        if (UPF == 4) best = graph ? grid_nn_warm_graph(L.grid, L.knn, p.x, p.y, p.z, j_prev, L.stop_d2)
+        if (UPF == 4) best = graph ? grid_nn_warm_graph(L.grid, L.knn, p.x, p.y, p.z, j_prev, L.stop_d2, kGraphSkipHopeless)
                                    : grid_nn_warm(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2);
         else best = UPF ? grid_nn_warm_upfront<(UPF == 3 ? 3 : 2)>(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2)
                         : grid_nn_warm(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2);
@@ -534,6 +534,10 @@ __device__ __forceinline__ void icp_iteration_body(const IcpLaunch& L, const int
   constexpr int kQ = kIcpThreads / G;  // queries per block per pass
   const int q_local = threadIdx.x / G;
   const bool graph = UPF == 4 && s_flags[3] != 0;
+  // (Measured and dropped: fetching the working point of the NEXT pass while this pass searches — cp.async into one or
+  //  two shared-memory slots per thread, or prefetch.global.L2.  work[i] is the one load of a warm launch that comes
+  //  from HBM, the first of three dependent levels, but with 25 warps per SM in flight it is already hidden:
+  //  15 020-15 050 against 15 170 hypotheses/s without, profiles/r2_al_prefetch_modes.txt.)
   for (int base = blk * kQ; base < L.n_src; base += L.blocks_per_hyp * kQ)
     icp_query<G, EST, CERT, UPF>(L, h, work, base + q_local, first, apply, graph, T, &s_tile[threadIdx.x >> 5], acc);
 
@@ -759,6 +763,185 @@ __global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_binned_kernel(c
     }
     // (phase 1 of the next tile writes only this thread's own slots, and the sort keys / permutation are rewritten
     //  behind its first barrier: no barrier needed here)
+  }
+
+  // ---- the block's record, the last block's solve: as in icp_iteration_body ----
+  const double r = block_reduce_acc<NACC>(acc, sm);
+  double* part = L.partials + (static_cast<size_t>(h) * L.part_stride) * kAccMax;
+  if (threadIdx.x < NACC) __stcg(part + static_cast<size_t>(blk) * kAccMax + threadIdx.x, r);
+  __threadfence();
+  __syncthreads();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(&st->ticket, 1u);
+    s_last = (t == static_cast<unsigned>(L.blocks_per_hyp) - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  reduce_partials<NACC>(part, L.blocks_per_hyp, sm, sm_tot);
+  if (threadIdx.x == 0) {
+    finish_iteration<MB>(st, &L.crit, sm_tot, L.trace, L.trace_cap, nullptr);
+    if (L.epochs) {
+      const int still_active = st->active;
+      __threadfence();
+      atomicAdd(L.epochs + h, still_active ? 1 : kEpochStopped);
+    }
+  }
+}
+
+// ---- warm iterations over the k-NN graph with the unproven queries of a tile walked by dense warps -----------------
+// In a graph launch (nn_graph.cuh) most queries are settled by the row of their previous match; the few that are not
+// — points of the model that lie millimetres off the scene: 6 % of the queries of a late C4 iteration — walk the grid
+// for a ball of several rows.  Inside icp_iteration_kernel such a lane keeps its whole warp waiting: ncu attributes half
+// of the warp instructions AND half of the stall samples of a late launch to the walk, at 8 of 32 active lanes
+// (profiles/r2_af_*).  Here every WARP takes a tile of TQ passes of the plain kernel's loop on its own (no block
+// barrier: a first version that staged the tile of the whole block in shared memory behind __syncthreads lost 8 % —
+// three warps idle while one walks):
+//   1. every lane moves its TQ queries and tries the graph (grid_nn_graph_try); the moved point goes to the working
+//      cloud at once with the best point met so far in .w (the match if proven); unproven queries (and those without
+//      a previous match) are queued in the warp's shared-memory queue, and whenever 32 are waiting
+//   2. the warp drains them, one per lane — a full warp that walks the grid (query and candidate are read back from
+//      the working cloud; only the position in .w is rewritten);
+//   3. a lane adds proven queries to its moment sums at once; a query that waits for a walk, and every later query of
+//      the same lane and tile (the ORDER of a thread's sums is the plain kernel's), is taken up after the drain: point
+//      and match re-read from the working cloud (L2), the squared distance recomputed with the same expression.
+// MEASURED SLOWER, off by default ("warm_graph_queue"): 13 450 (tiles of 8 passes) and 13 310 (16) against 14 440
+// hypotheses/s for the plain graph kernel on C4; putting off ALL queries of a tile instead: 14 130; the block-wide
+// version: 13 280 (profiles/r2_ai_graph_queue.txt).  The walks it saves (a quarter of the warp-level walks are left)
+// cost less than what it adds: the L2 round trips of the re-reads in phases 2 and 3, which nothing overlaps in a
+// latency-bound kernel, and 330 more bytes of spills at the 64-register cap.
+// Queries, exact searches (same tie rule) and the order of every thread's double sums are those of
+// icp_iteration_kernel: byte-identical records (tests/test_gpu_warm_options.py).  Hypotheses that do not search over
+// the graph in this launch (graph_pays) run the plain body.
+template <int EST, int MB, int TQ>
+__global__ void __launch_bounds__(kIcpThreads, MB) icp_iteration_graphq_kernel(const IcpLaunch L) {
+  static_assert(TQ >= 1 && TQ <= 32, "one validity bit per pass of a tile");
+  if (L.epochs == nullptr) {
+    pdl_trigger_and_wait();
+  } else {
+    asm volatile("griddepcontrol.launch_dependents;");
+    wait_for_hypothesis(L.epochs + blockIdx.y, L.launch_idx, L.err_flag);
+  }
+  const int h = blockIdx.y, blk = blockIdx.x;
+  IcpState* st = L.states + h;
+  __shared__ int s_mode[2];  // active, graph
+  if (threadIdx.x == 0) {
+    s_mode[0] = __ldcg(&st->active);
+    s_mode[1] = graph_pays(L, st) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_mode[0]) return;
+  if (!s_mode[1]) {  // (block-uniform)
+    icp_iteration_body<1, EST, MB, false, false, 0>(L, h, blk);
+    return;
+  }
+  constexpr int NACC = (EST == PEB_ESTIMATOR_SVD) ? kAccSvd : kAccLls;
+  __shared__ double sm[kIcpThreads / 32][kAccMax];
+  __shared__ double sm_tot[kAccMax];
+  __shared__ float s_inc[16];
+  __shared__ int s_queue[kIcpThreads / 32][64];  // per warp: query indices waiting for a grid walk (at most 31 + 32)
+  if (threadIdx.x < 16) s_inc[threadIdx.x] = __ldcg(&st->inc.m[threadIdx.x]);
+  __syncthreads();
+  const float* T = s_inc;
+  float4* work = L.work + static_cast<size_t>(h) * L.n_src;
+  const int stride = L.blocks_per_hyp * kIcpThreads;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  int* queue = s_queue[threadIdx.x >> 5];
+
+  // lanes [0, count) walk the grid for the LAST count entries of the queue
+  auto drain = [&](int n_queue, int count) {
+    if (lane < count) {
+      const int i = queue[n_queue - count + lane];
+      const float4 q = __ldcg(work + i);
+      NnBest best;
+      best.j = __float_as_int(q.w);
+      if (best.j >= 0) {
+        const float4 t = L.grid.pts[best.j];
+        best.d2 = l2_simple(q.x, q.y, q.z, t.x, t.y, t.z);
+        best.idx = point_index(t);
+        grid_ball_search(L.grid, q.x, q.y, q.z, L.stop_d2, best);
+      } else {
+        best = grid_nn<1>(L.grid, q.x, q.y, q.z, L.stop_d2);
+      }
+      __stcg(reinterpret_cast<int*>(work + i) + 3, best.j);
+    }
+    __syncwarp();
+  };
+
+  double acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+
+  for (int base0 = blk * kIcpThreads; base0 < L.n_src; base0 += TQ * stride) {
+    // ---- 1 (+ 2 whenever a warp's worth of walks is waiting): move, try the graph ----
+    // A lane adds a proven query to its sums at once — unless one of its earlier queries of this tile is still
+    // waiting for its walk: the order of a thread's sums is the plain kernel's, so everything behind a waiting
+    // query waits with it (defer_mask) and is taken up again in phase 3.
+    unsigned defer_mask = 0u;
+    int n_queue = 0;  // (warp-uniform)
+#pragma unroll 1
+    for (int kk = 0; kk < TQ; ++kk) {
+      const int i = base0 + kk * stride + threadIdx.x;
+      if (i - lane >= L.n_src) break;  // (warp-uniform: the warp's first query of this pass)
+      bool need = false;
+      if (i < L.n_src) {
+        float4 p = work[i];
+        if (finite3(p.x, p.y, p.z)) {
+          const int j_prev = __float_as_int(p.w);
+          float qx, qy, qz;
+          transform_icp(T, p.x, p.y, p.z, qx, qy, qz);
+          p.x = qx;
+          p.y = qy;
+          p.z = qz;
+          NnBest best;
+          best.d2 = pos_inf();
+          best.idx = -1;
+          best.j = -1;
+          need = true;
+          if (j_prev >= 0 && j_prev < L.grid.n) need = !grid_nn_graph_try(L.grid, L.knn, qx, qy, qz, j_prev, best, kGraphSkipHopeless);
+          p.w = __int_as_float(best.j);
+          __stcg(work + i, p);
+          if (need || defer_mask) {
+            defer_mask |= 1u << kk;
+          } else {
+            bool keep = best.idx >= 0;
+            if (keep && static_cast<double>(best.d2) > L.max_dist_sqr) keep = false;
+            if (keep && L.use_rejector && !(best.d2 < L.rej_max2)) keep = false;
+            if (keep) accumulate_pair<EST>(L.grid, p, best, acc);
+          }
+        }
+      }
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, need);
+      if (m) {
+        if (need) queue[n_queue + __popc(m & lt)] = i;
+        n_queue += __popc(m);
+        __syncwarp();
+        if (n_queue >= 32) {
+          drain(n_queue, 32);
+          n_queue -= 32;
+        }
+      }
+    }
+    if (n_queue) drain(n_queue, n_queue);
+    // ---- 3: every lane the queries it had to put off, in the plain kernel's order ----
+#pragma unroll 1
+    for (int kk = 0; kk < TQ; ++kk) {
+      if (!((defer_mask >> kk) & 1u)) continue;
+      const int i = base0 + kk * stride + threadIdx.x;
+      const float4 p = __ldcg(work + i);
+      NnBest best;
+      best.j = __float_as_int(p.w);
+      if (best.j < 0) continue;  // nothing found within the search limit
+      const float4 t = L.grid.pts[best.j];
+      best.d2 = l2_simple(p.x, p.y, p.z, t.x, t.y, t.z);
+      best.idx = point_index(t);
+      bool keep = best.idx >= 0;
+      if (keep && static_cast<double>(best.d2) > L.max_dist_sqr) keep = false;
+      if (keep && L.use_rejector && !(best.d2 < L.rej_max2)) keep = false;
+      if (keep) accumulate_pair<EST>(L.grid, p, best, acc);
+    }
   }
 
   // ---- the block's record, the last block's solve: as in icp_iteration_body ----
@@ -1128,6 +1311,15 @@ int launch_one_iteration(peb_ctx* ctx, const IcpLaunch& L, size_t H, int estimat
   }
   // warm launches of a batch over the target's k-NN graph (nn_graph.cuh; "warm_graph")
   if (G == 1 && !FIRST && !cert && !L.cache && L.warm && L.knn && H > 1) {
+    // ... with the unproven queries of a tile queued and walked by dense warps ("warm_graph_queue" = passes per tile)
+#define PEB_ICP_LAUNCH_GQ(TQ) \
+  do { \
+    if (svd) PEB_LAUNCH_PDL(ctx, (icp_iteration_graphq_kernel<S, kMinBlocksBatch, TQ>), grid, dim3(kIcpThreads), L); \
+    else     PEB_LAUNCH_PDL(ctx, (icp_iteration_graphq_kernel<P, kMinBlocksBatch, TQ>), grid, dim3(kIcpThreads), L); \
+  } while (0)
+    if (ctx->warm_graph_queue == 8) { PEB_ICP_LAUNCH_GQ(8); return PEB_OK; }
+    if (ctx->warm_graph_queue == 16) { PEB_ICP_LAUNCH_GQ(16); return PEB_OK; }
+#undef PEB_ICP_LAUNCH_GQ
     if (svd) PEB_LAUNCH_PDL(ctx, (icp_iteration_kernel<1, S, kMinBlocksBatch, false, false, 4>), grid, dim3(kIcpThreads), L);
     else     PEB_LAUNCH_PDL(ctx, (icp_iteration_kernel<1, P, kMinBlocksBatch, false, false, 4>), grid, dim3(kIcpThreads), L);
     return PEB_OK;

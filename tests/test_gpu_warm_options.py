@@ -2,6 +2,8 @@
 
 * `warm_graph` (default ON for batches of >= 32 hypotheses): the search over the target's k-nearest-neighbour graph
   (csrc/nn_graph.cuh) — certificate from the previous match's row, greedy steps, grid walk as the last resort;
+* `warm_graph_queue` (off: measured slower): in a graph launch every warp queues the unproven queries of a tile of 8 / 16 passes
+  and walks the grid for them 32 at a time (icp_iteration_graphq_kernel);
 * `warm_bin` (off: measured slower): the queries of a block sorted by the number of grid rows their ball search walks
   (icp_iteration_binned_kernel).
 
@@ -31,8 +33,15 @@ def scene_small(oracle):
 
 VARIANTS = {"plain": (("warm_graph", 0), ("warm_bin", 0)),
             # every warm launch over the graph / hypotheses switch to it when their MSE says the certificate will hold
-            "graph": (("warm_graph", 1), ("warm_graph_min_hyp", 2), ("warm_graph_kappa_x100", 0), ("warm_bin", 0)),
-            "graph_auto": (("warm_graph", 1), ("warm_graph_min_hyp", 2), ("warm_bin", 0)),
+            "graph": (("warm_graph", 1), ("warm_graph_min_hyp", 2), ("warm_graph_kappa_x100", 0), ("warm_bin", 0),
+                      ("warm_graph_queue", 0)),
+            "graph_auto": (("warm_graph", 1), ("warm_graph_min_hyp", 2), ("warm_bin", 0), ("warm_graph_queue", 0)),
+            # ... with the unproven queries of a tile of 8 / 16 passes queued per warp and walked 32 at a time (off: measured slower)
+            "graphq": (("warm_graph", 1), ("warm_graph_min_hyp", 2), ("warm_graph_kappa_x100", 0), ("warm_bin", 0),
+                       ("warm_graph_queue", 8)),
+            "graphq_auto": (("warm_graph", 1), ("warm_graph_min_hyp", 2), ("warm_bin", 0), ("warm_graph_queue", 8)),
+            "graphq16": (("warm_graph", 1), ("warm_graph_min_hyp", 2), ("warm_graph_kappa_x100", 0), ("warm_bin", 0),
+                        ("warm_graph_queue", 16)),
             "bin": (("warm_graph", 0), ("warm_bin", 1))}
 
 
@@ -57,7 +66,7 @@ def _run(pcl, source, target, cls, normals, guesses, variant, opts=(), **params)
     return out
 
 
-@pytest.mark.parametrize("variant", ["graph", "graph_auto", "bin"])
+@pytest.mark.parametrize("variant", ["graph", "graph_auto", "graphq", "graphq_auto", "graphq16", "bin"])
 def test_warm_variants_never_change_results(pcl, scene_small, variant):
     p = scene_small
     rng = np.random.default_rng(15)
@@ -72,7 +81,7 @@ def test_warm_variants_never_change_results(pcl, scene_small, variant):
                _run(pcl, p.source, p.target, pcl.IterativeClosestPoint, None, guesses, "plain", opts, **kw)
 
 
-@pytest.mark.parametrize("variant", ["graph", "graph_auto", "bin"])
+@pytest.mark.parametrize("variant", ["graph", "graph_auto", "graphq", "graphq_auto", "bin"])
 def test_warm_variants_point_to_plane_rejector_and_criteria(pcl, scene_small, variant):
     p = scene_small
     c = pcl.Context(0)
@@ -90,7 +99,7 @@ def test_warm_variants_point_to_plane_rejector_and_criteria(pcl, scene_small, va
     assert len({r[-32:] for r in a}) > 1  # (the records differ between hypotheses: the comparison is not vacuous)
 
 
-@pytest.mark.parametrize("variant", ["graph", "graph_auto", "bin"])
+@pytest.mark.parametrize("variant", ["graph", "graph_auto", "graphq", "graphq_auto", "bin"])
 def test_warm_variants_nonfinite_points_far_hypotheses_and_tiny_sources(pcl, scene_small, variant):
     p = scene_small
     rng = np.random.default_rng(17)
