@@ -106,7 +106,7 @@ struct peb_ctx {
                                 // 0 = off, 1 or 2 = boxes up to 2 x 2 rows, 3 = up to 3 x 3; unmeasured
   int warm_upfront_from = 2;    // ... from this iteration launch on (launch 1 searches balls of 1.3 cells: 61 % of its warps hold a lane beyond 3 x 3 rows)
   int warm_graph = 1;           // batched warm launches search over the target's k-NN graph (nn_graph.cuh) instead of walking the grid
-  float warm_graph_kappa = 1.2f; // a hypothesis takes the graph once 4 * MSE * kappa < mean outer bound of the rows (0: from launch 1 on)
+  float warm_graph_kappa = 0.0f; // > 0: a hypothesis takes the graph once 4 * MSE * kappa < mean outer bound of the rows; 0: from launch 1 on (measured flat from 0 to 0.6 once hopeless rows are skipped)
   int warm_graph_queue = 0;     // (measured: -7 %, off) graph launches: every warp queues the unproven queries of a tile of 8 / 16 passes and
                                 // walks the grid for them 32 at a time (icp.cu : icp_iteration_graphq_kernel); 0 = every lane walks for itself
   int warm_graph_min_hyp = 32;  // ... for batches of at least this many hypotheses (the graph costs one k-NN pass over the target)

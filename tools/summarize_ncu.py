@@ -27,18 +27,27 @@ WANT = [
     ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64 pipe %"),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu pipe %"),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe %"),
+    ("smsp__inst_executed.sum", "warp instructions"),
+    ("lts__t_sectors.sum", "L2 sectors"),
 ]
 
 
 def raw_summary(rep: str, title: str) -> str:
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(out.splitlines()))
-    hdr, units, body = rows[0], rows[1], rows[2:]
+    """rep: one or more (comma-separated) .ncu-rep files or `ncu --page raw --csv` exports of them"""
+    hdr, units, body = None, None, []
+    for one in rep.split(","):
+        if one.endswith(".csv"):
+            out = open(one).read()
+        else:
+            out = subprocess.run(["ncu", "-i", one, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = [r for r in csv.reader(out.splitlines()) if len(r) > 20]
+        hdr, units = rows[0], rows[1]
+        body += [(one.split("/")[-1], r, rows[1]) for r in rows[2:]]
     ki = hdr.index("Kernel Name")
-    lines = [f"# {title}", f"# source: ncu --set full --clock-control none, {rep.split('/')[-1]}", ""]
-    for n, r in enumerate(body):
+    lines = [f"# {title}", f"# source: ncu --set full --clock-control none --import-source on, {', '.join(x.split('/')[-1] for x in rep.split(','))}", ""]
+    for n, (src, r, units) in enumerate(body):
         name = r[ki].replace("peb::<unnamed>::", "").replace("void ", "")
-        lines.append(f"## launch {n}: {name[:110]}")
+        lines.append(f"## launch {n} ({src}): {name[:110]}")
         for key, label in WANT:
             if key in hdr:
                 i = hdr.index(key)
