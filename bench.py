@@ -44,7 +44,12 @@ def make_workloads(downsample, want_c2: bool, n_hyp: int, scale: float):
     from pose_estimation_b200.testing import synth
 
     t0 = time.perf_counter()
-    c4 = synth.make_c4(scale=scale, n_guesses=n_hyp, downsample=downsample)
+    # PEB_HYP_OFFSET (development): the block of n_hyp hypotheses that starts at this index of the full sequence — the
+    # share of one rank of an N-GPU run, alone on one GPU
+    off = int(os.environ.get("PEB_HYP_OFFSET", "0"))
+    c4 = synth.make_c4(scale=scale, n_guesses=off + n_hyp, downsample=downsample)
+    if off:
+        c4.guess = c4.guess[off:]
     c2 = synth.make_c2(scale=scale, downsample=downsample) if want_c2 else None
     log(f"[bench] workloads generated in {time.perf_counter() - t0:.1f} s: C4 target {len(c4.target)} pts, "
         f"model {len(c4.source)} pts, {len(c4.guess)} poses" + (f"; C2 target {len(c2.target)} pts" if c2 else ""))
