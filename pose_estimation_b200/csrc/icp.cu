@@ -81,6 +81,7 @@ struct IcpLaunch {
   const KnnRow* knn;     // nullable: the target's k-NN graph (nn_graph.cuh) for the warm searches
   const double* knn_stat;  // [0] sum, [1] count of the finite outer bounds (next2[2]) of the graph's rows
   float knn_kappa;       // a hypothesis searches over the graph once 4 * (its last MSE) * kappa < the mean outer bound
+  int cold_graph;        // launch 0: candidates by greedy descent on the graph instead of the 3 x 3 x 3 probe
 };
 
 __global__ void icp_init_kernel(IcpState* __restrict__ states, const float* __restrict__ guesses, int H,
@@ -387,7 +388,10 @@ __device__ __forceinline__ NnBest first_iteration_search(const IcpLaunch& L, int
       }
     }
     if (j_seed >= 0) {
-      best = grid_nn_seed_probe(L.grid, p.x, p.y, p.z, j_seed, a.x, a.y, a.z);
+      // the candidate: greedy descent on the target's k-NN graph from the anchor's match ("cold_graph"), or the best of
+      // the 3 x 3 x 3 block around the anchor's match shifted by (q - q_anchor)
+      best = (L.knn && L.cold_graph) ? grid_nn_graph_descend(L.grid, L.knn, p.x, p.y, p.z, j_seed)
+                                     : grid_nn_seed_probe(L.grid, p.x, p.y, p.z, j_seed, a.x, a.y, a.z);
       need = true;
     } else {
       best = grid_nn<1>(L.grid, p.x, p.y, p.z, L.stop_d2);
@@ -1532,6 +1536,10 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
     Lw.knn = ctx->tgt_knn.as<KnnRow>();
     Lw.knn_stat = ctx->tgt_knn_stat.as<double>();
     Lw.knn_kappa = ctx->warm_graph_kappa;
+    if (ctx->cold_graph && Lc.anchors) {
+      Lc.knn = Lw.knn;
+      Lc.cold_graph = 1;
+    }
   }
   // the candidate cache of the warm launches from launch nn_cache_from on (0: never)
   const int cache_from = (ctx->nn_cache_from > 0 && ctx->warm_start && g_warm == 1 && !(L.margin > 0.0f)) ? ctx->nn_cache_from : 0;

@@ -63,6 +63,9 @@ constexpr int kGraphMaxRounds = 6;  // greedy steps before the grid walk takes o
 // outer bound) the scan is skipped and the walk starts from j_prev itself — the twelve gathers of such a row are
 // only worth their three dependent rounds when they find a closer point, and late in an align the previous match
 // still is the nearest point for four queries out of five.
+// (Skipping only rows whose bound is missed by less than a factor — greedy steps first where the previous match is far
+//  away, so that the walk covers a smaller ball — measured slower for every factor from 2 to 16: 13 870-15 480 against
+//  15 830 hypotheses/s; the steps cost more than the rows they save, also in launch 1.)
 PEB_HD bool grid_nn_graph_try(const GridView& g, const KnnRow* __restrict__ rows, float qx, float qy, float qz,
                               int j_prev, NnBest& best, bool skip_hopeless = false) {
   int js = j_prev;
@@ -112,6 +115,42 @@ PEB_HD bool grid_nn_graph_try(const GridView& g, const KnnRow* __restrict__ rows
     nx = *reinterpret_cast<const float4*>(row->half[0].next2);
   }
   return false;
+}
+
+// Greedy descent: from the point at sorted position j_start to a point none of whose kGraphK neighbours is closer to q.
+// A CANDIDATE only (the first iteration of a batch verifies it: icp.cu : first_iteration_search) — on a surface scan
+// the local minimum usually is the nearest neighbour, at a hole or a depth edge it may not be.
+constexpr int kGraphMaxHops = 24;
+PEB_HD NnBest grid_nn_graph_descend(const GridView& g, const KnnRow* __restrict__ rows, float qx, float qy, float qz, int j_start) {
+  NnBest best;
+  {
+    const float4 s = g.pts[j_start];
+    best.d2 = l2_simple(qx, qy, qz, s.x, s.y, s.z);
+    best.idx = point_index(s);
+    best.j = j_start;
+  }
+  int js = j_start;
+#pragma unroll 1
+  for (int hop = 0; hop < kGraphMaxHops; ++hop) {
+    const KnnRow* row = rows + js;
+#pragma unroll 1
+    for (int hf = 0; hf < kGraphHalves; ++hf) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const uint4 pc = *reinterpret_cast<const uint4*>(row->half[hf].pos + 4 * c);
+        const uint32_t pos[4] = {pc.x, pc.y, pc.z, pc.w};
+        float4 n[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) n[k] = g.pts[pos[k]];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          nn_consider(best, l2_simple(qx, qy, qz, n[k].x, n[k].y, n[k].z), point_index(n[k]), static_cast<int>(pos[k]));
+      }
+    }
+    if (best.j == js) break;
+    js = best.j;
+  }
+  return best;
 }
 
 // Exact 1-NN of q given a candidate at sorted position j_prev (last iteration's match).

@@ -42,6 +42,9 @@ VARIANTS = {"plain": (("warm_graph", 0), ("warm_bin", 0)),
             "graphq_auto": (("warm_graph", 1), ("warm_graph_min_hyp", 2), ("warm_bin", 0), ("warm_graph_queue", 8)),
             "graphq16": (("warm_graph", 1), ("warm_graph_min_hyp", 2), ("warm_graph_kappa_x100", 0), ("warm_bin", 0),
                         ("warm_graph_queue", 16)),
+            # launch 0 takes its candidates from a greedy descent on the graph instead of the 3 x 3 x 3 probe
+            "cold_graph": (("warm_graph", 1), ("warm_graph_min_hyp", 2), ("warm_bin", 0), ("warm_graph_queue", 0),
+                           ("cold_graph", 1)),
             "bin": (("warm_graph", 0), ("warm_bin", 1))}
 
 
@@ -66,7 +69,7 @@ def _run(pcl, source, target, cls, normals, guesses, variant, opts=(), **params)
     return out
 
 
-@pytest.mark.parametrize("variant", ["graph", "graph_auto", "graphq", "graphq_auto", "graphq16", "bin"])
+@pytest.mark.parametrize("variant", ["graph", "graph_auto", "graphq", "graphq_auto", "graphq16", "cold_graph", "bin"])
 def test_warm_variants_never_change_results(pcl, scene_small, variant):
     p = scene_small
     rng = np.random.default_rng(15)
@@ -81,7 +84,7 @@ def test_warm_variants_never_change_results(pcl, scene_small, variant):
                _run(pcl, p.source, p.target, pcl.IterativeClosestPoint, None, guesses, "plain", opts, **kw)
 
 
-@pytest.mark.parametrize("variant", ["graph", "graph_auto", "graphq", "graphq_auto", "bin"])
+@pytest.mark.parametrize("variant", ["graph", "graph_auto", "graphq", "graphq_auto", "cold_graph", "bin"])
 def test_warm_variants_point_to_plane_rejector_and_criteria(pcl, scene_small, variant):
     p = scene_small
     c = pcl.Context(0)
@@ -99,7 +102,7 @@ def test_warm_variants_point_to_plane_rejector_and_criteria(pcl, scene_small, va
     assert len({r[-32:] for r in a}) > 1  # (the records differ between hypotheses: the comparison is not vacuous)
 
 
-@pytest.mark.parametrize("variant", ["graph", "graph_auto", "graphq", "graphq_auto", "bin"])
+@pytest.mark.parametrize("variant", ["graph", "graph_auto", "graphq", "graphq_auto", "cold_graph", "bin"])
 def test_warm_variants_nonfinite_points_far_hypotheses_and_tiny_sources(pcl, scene_small, variant):
     p = scene_small
     rng = np.random.default_rng(17)
