@@ -39,7 +39,10 @@ constexpr int kIcpThreads = 128;
 // wants no spills (5 blocks/SM = 96 registers); the batched mode is throughput-bound and gains 17 %
 // from 8 blocks/SM (64 registers, a few spills to L1) through the extra warps that hide L2 latency.
 constexpr int kMinBlocksSingle = 5;
-constexpr int kMinBlocksBatch = 8;
+#ifndef PEB_MIN_BLOCKS_BATCH
+#define PEB_MIN_BLOCKS_BATCH 8
+#endif
+constexpr int kMinBlocksBatch = PEB_MIN_BLOCKS_BATCH;  // (development: -DPEB_MIN_BLOCKS_BATCH=n builds a variant library, PEB_LIB_VARIANT)
 
 struct IcpLaunch {
   GridView grid;
@@ -1185,7 +1188,7 @@ __global__ void __launch_bounds__(kIcpThreads) icp_fitness_kernel(const IcpLaunc
           best.idx = __float_as_int(t.w);
           best.j = j_prev;
         } else {
-          best = graph ? grid_nn_warm_graph(L.grid, L.knn, qx, qy, qz, j_prev, L.fitness_stop_d2)
+          best = graph ? grid_nn_warm_graph(L.grid, L.knn, qx, qy, qz, j_prev, L.fitness_stop_d2, kGraphSkipHopeless)
                        : grid_nn_warm(L.grid, qx, qy, qz, j_prev, L.fitness_stop_d2);
         }
       } else {
