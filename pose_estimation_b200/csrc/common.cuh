@@ -98,9 +98,12 @@ struct peb_ctx {
   std::string err;
   uint64_t launches = 0;
   int nn_group = 1;             // lanes that share one COLD nearest-neighbour query (1, 2, 4, 8, 16)
-  float grid_occupancy = 3.5f;  // wanted mean points per occupied cell of the target grid (measured on C4 / C2: 1.0 93.3 ms,
-                                // 1.5 94.1, 2.0 97.1, 2.5 93.4, 3.0 91.8, 3.5 91.5, 4.0 91.2, 5.0 92.7, 6.0 95.4, 8.0 101.0 per
-                                // 1024-hypothesis batch; single align 0.736 ms at 2.0, 0.721 at 3.0, 0.729 at 4.0)
+  float grid_occupancy = 5.0f;  // wanted mean points per occupied cell of the target grid.  Round 1 (every warm query walks the grid), C4 / C2:
+                                // 1.0 93.3 ms, 1.5 94.1, 2.0 97.1, 2.5 93.4, 3.0 91.8, 3.5 91.5, 4.0 91.2, 5.0 92.7, 6.0 95.4, 8.0 101.0 per
+                                // 1024-hypothesis batch; single align 0.736 ms at 2.0, 0.721 at 3.0, 0.729 at 4.0.  Round 2 (near queries are
+                                // settled by the k-NN graph, only the larger balls still walk): 2.0 70.1 ms, 2.75 67.1, 3.5 64.5, 4.5 63.1,
+                                // 5.0 62.8, 6.0 62.5, 7.0 62.6, 8.0 62.9; single align 0.722 ms at 3.5, 0.733 at 5.0, 0.741 at 6.0, 0.751 at 7.0;
+                                // a 128-hypothesis shard 8.83 ms at 3.5, 8.49 at 5.0
   bool warm_start = true;       // iterations >= 1 seed the search with the previous match
   int warm_upfront = 0;         // experimental: warm searches fetch the row bounds of their ball up front (nn_upfront.cuh):
                                 // 0 = off, 1 or 2 = boxes up to 2 x 2 rows, 3 = up to 3 x 3; unmeasured
