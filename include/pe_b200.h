@@ -117,7 +117,7 @@ PEB_API uint64_t peb_ctx_launch_count(const peb_ctx* ctx);
  * every one of them; the exception are the block-count knobs "blocks_factor" / "blocks_factor_cold" — and "nn_group" in
  * a batch, which changes launch 0's block count —: they change the ORDER in which the per-block partial sums of the
  * double moments are added, i.e. at most their last bits): "nn_group" (lanes per COLD nearest-neighbour query: 1, 2, 4, 8, 16),
- * "grid_occupancy_x100" (wanted points per occupied target-grid cell x 100, default 350; takes effect at
+ * "grid_occupancy_x100" (wanted points per occupied target-grid cell x 100, default 500; takes effect at
  * the next peb_target_set), "source_sort_occupancy" (points per cell of the source's own sort grid = patch
  * compactness, default 32), "warm_start" (iterations >= 1 seed their search with the previous match),
  * "anchor_seed" / "seed_guard_x10" / "coop_max_rows" (first iteration of a batch: one anchor search per
@@ -134,7 +134,15 @@ PEB_API uint64_t peb_ctx_launch_count(const peb_ctx* ctx);
  * csrc/nn_cache.cuh; bit-identical, measured slower, off), "warm_bin" (default 0; 1: the warm launches of a batch
  * sort the queries of a block by the number of grid rows their search walks before the warps search them —
  * icp.cu : icp_iteration_binned_kernel; bit-identical by construction, measured -6 % on C4,
- * profiles/r2_p_warm_bin.txt) */
+ * profiles/r2_p_warm_bin.txt),
+ * "warm_graph" (default 1: the warm launches of a batch of at least "warm_graph_min_hyp" (32) hypotheses search over a
+ * 12-nearest-neighbour graph of the target, built once per target — csrc/nn_graph.cuh: the row of the previous match
+ * proves most answers without a grid walk; byte-identical records, C4 11 480 -> 16 330 hypotheses/s),
+ * "warm_graph_kappa_x100" (default 0 = every hypothesis from launch 1 on; > 0: a hypothesis takes the graph once
+ * 4 x its last MSE x kappa is below the mean outer bound of the rows), "cold_graph" (default 1: launch 0 of such a batch
+ * takes its candidates from a greedy descent on the graph instead of a 3 x 3 x 3 probe), "warm_graph_queue" (default 0;
+ * 8 / 16: every warp queues the unproven queries of a tile of that many passes and walks the grid for them 32 at a
+ * time — icp.cu : icp_iteration_graphq_kernel; byte-identical, measured -7 %, profiles/r2_ai_graph_queue.txt) */
 PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value);
 
 /* ---- pcl::VoxelGrid<PointXYZ>::filter  [PCL] filters/.../impl/voxel_grid.hpp -------- */
