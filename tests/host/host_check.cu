@@ -179,7 +179,9 @@ HC_API void hc_grid_nn_warm_upfront(const float* tgt, size_t n, size_t tstride, 
 // arithmetic and the (distance, position) order of normals.cu : knn_graph_kernel; same interface as hc_grid_nn_warm.
 // out_rounds (nullable) is not filled by the search itself: the caller only checks results.
 HC_API void hc_grid_nn_warm_graph(const float* tgt, size_t n, size_t tstride, const float* q, size_t nq, size_t qstride,
-                                  float occupancy, const int32_t* prev, float limit_d2, int32_t* out_idx, float* out_d2) {
+                                  float occupancy, const int32_t* prev, float limit_d2, int32_t* out_idx, float* out_d2, int mode) {
+  // mode 0: every row is scanned; 1: rows that cannot certify are skipped (the library's warm launches); 2: launch 0's
+  // candidate — greedy descent from prev — verified by the ball search
   HostGrid g;
   build_grid(tgt, n, tstride / 4, occupancy, 0.0f, g);
   std::vector<int> pos(n, -1);
@@ -202,7 +204,13 @@ HC_API void hc_grid_nn_warm_graph(const float* tgt, size_t n, size_t tstride, co
   }
   for (size_t i = 0; i < nq; ++i) {
     const float* p = q + i * (qstride / 4);
-    NnBest b = grid_nn_warm_graph(g.v, rows.data(), p[0], p[1], p[2], pos[prev[i]], limit_d2);
+    NnBest b;
+    if (mode == 2) {
+      b = grid_nn_graph_descend(g.v, rows.data(), p[0], p[1], p[2], pos[prev[i]]);
+      grid_ball_search(g.v, p[0], p[1], p[2], limit_d2, b);
+    } else {
+      b = grid_nn_warm_graph(g.v, rows.data(), p[0], p[1], p[2], pos[prev[i]], limit_d2, mode == 1);
+    }
     out_idx[i] = b.idx;
     out_d2[i] = b.d2;
   }

@@ -107,12 +107,14 @@ def test_warm_ball_search_is_exact_on_adversarial_clouds(hc, oracle, seed):  # n
                 assert np.array_equal(gi, bi), (name, occ, kind, np.flatnonzero(gi != bi)[:5])
 
 
-def grid_nn_warm_graph(hc, tgt, q, prev, occupancy, limit=np.inf):  # noqa: F811
+def grid_nn_warm_graph(hc, tgt, q, prev, occupancy, limit=np.inf, mode=0):  # noqa: F811
+    """mode 0: every row scanned; 1: rows that cannot certify skipped (the warm launches of a batch); 2: greedy descent
+    from prev, then the ball search (launch 0's candidate and its verification)"""
     tgt = np.ascontiguousarray(tgt, F)
     idx = np.empty(len(q), np.int32)
     d2 = np.empty(len(q), F)
     hc.hc_grid_nn_warm_graph(tgt.ctypes.data, len(tgt), tgt.strides[0], q.ctypes.data, len(q), q.strides[0], occupancy,
-                             prev.ctypes.data, limit, idx.ctypes.data, d2.ctypes.data)
+                             prev.ctypes.data, limit, idx.ctypes.data, d2.ctypes.data, mode)
     return idx, d2
 
 
@@ -125,11 +127,12 @@ def test_knn_graph_warm_search_is_exact_on_adversarial_clouds(hc, oracle, seed):
         q = queries(rng, tgt)
         bi, bd = oracle.nn_bruteforce(tgt, q)
         ok = np.flatnonzero(np.isfinite(tgt).all(1))
-        for occ in (1.0, 3.5):
+        for occ in (1.0, 5.0):
             for kind, prev in (("true", bi), ("next", ok[(np.searchsorted(ok, bi) + 1) % len(ok)]), ("random", rng.choice(ok, len(q)))):
-                gi, gd = grid_nn_warm_graph(hc, tgt, q, np.ascontiguousarray(prev, np.int32), occ)
-                assert np.array_equal(gd, bd), (name, occ, kind, np.flatnonzero(gd != bd)[:5])
-                assert np.array_equal(gi, bi), (name, occ, kind, np.flatnonzero(gi != bi)[:5])
+                for mode in (0, 1, 2):
+                    gi, gd = grid_nn_warm_graph(hc, tgt, q, np.ascontiguousarray(prev, np.int32), occ, mode=mode)
+                    assert np.array_equal(gd, bd), (name, occ, kind, mode, np.flatnonzero(gd != bd)[:5])
+                    assert np.array_equal(gi, bi), (name, occ, kind, mode, np.flatnonzero(gi != bi)[:5])
 
 
 @pytest.mark.parametrize("seed", [0, 1])

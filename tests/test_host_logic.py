@@ -23,7 +23,7 @@ def hc():
     L.hc_grid_nn.argtypes = [vp, sz, sz, vp, sz, sz, C.c_float, C.c_float, C.c_float, vp, vp, vp]
     L.hc_grid_nn_warm.argtypes = [vp, sz, sz, vp, sz, sz, C.c_float, vp, C.c_float, C.c_float, vp, vp, vp]
     L.hc_grid_nn_seeded.argtypes = [vp, sz, sz, vp, vp, sz, C.c_float, C.c_float, vp, vp]
-    L.hc_grid_nn_warm_graph.argtypes = [vp, sz, sz, vp, sz, sz, C.c_float, vp, C.c_float, vp, vp]
+    L.hc_grid_nn_warm_graph.argtypes = [vp, sz, sz, vp, sz, sz, C.c_float, vp, C.c_float, vp, vp, C.c_int]
     L.hc_rotation_paths.argtypes = [vp, vp, vp]
     L.hc_umeyama_pairs.argtypes = [vp, vp, sz, vp]
     L.hc_lls_pairs.argtypes = [vp, vp, vp, sz, vp]
