@@ -288,15 +288,17 @@ __device__ __forceinline__ void accumulate_pair_impl(const GridView& g, const fl
     acc[4] += tx;
     acc[5] += ty;
     acc[6] += tz;
-    acc[7] += tx * sx;
-    acc[8] += tx * sy;
-    acc[9] += tx * sz;
-    acc[10] += ty * sx;
-    acc[11] += ty * sy;
-    acc[12] += ty * sz;
-    acc[13] += tz * sx;
-    acc[14] += tz * sy;
-    acc[15] += tz * sz;
+    // (the product of two widened floats is exact in double, so the fused form rounds exactly like multiply-then-add:
+    //  one DFMA instead of DMUL + DADD under -fmad=false, bit-identical sums)
+    acc[7] = fma(tx, sx, acc[7]);
+    acc[8] = fma(tx, sy, acc[8]);
+    acc[9] = fma(tx, sz, acc[9]);
+    acc[10] = fma(ty, sx, acc[10]);
+    acc[11] = fma(ty, sy, acc[11]);
+    acc[12] = fma(ty, sz, acc[12]);
+    acc[13] = fma(tz, sx, acc[13]);
+    acc[14] = fma(tz, sy, acc[14]);
+    acc[15] = fma(tz, sz, acc[15]);
     acc[16] += static_cast<double>(best.d2);
   } else {
     acc[0] += 1.0;
