@@ -246,27 +246,43 @@ __device__ __forceinline__ bool grid_nn_coop_verify(const GridView& g, CoopTile*
         e = g.cell_start[base + x1 + 1];
       }
     }
-    // the non-empty rows are staged one after the other, 32 points per step (coalesced)
-    unsigned live = __ballot_sync(kFull, e > s);
-    PEB_COOP_COUNT(3, __popc(live));
-    while (live) {
-      const int src_lane = __ffs(live) - 1;
-      live &= live - 1;
-      const uint32_t rs = __shfl_sync(kFull, s, src_lane), re = __shfl_sync(kFull, e, src_lane);
-      for (uint32_t j0 = rs; j0 < re; j0 += 32) {
-        if (fill + 32 > kCoopTile - 4) flush();  // (the scan pads to a multiple of four)
-        const uint32_t j = j0 + lane;
-        if (j < re) {
-          const float4 pt = g.pts[j];
-          tile->xs[fill + lane] = pt.x;
-          tile->ys[fill + lane] = pt.y;
-          tile->zs[fill + lane] = pt.z;
-          tile->ids[fill + lane] = __float_as_int(pt.w);
-          tile->pos[fill + lane] = static_cast<int>(j);
-        }
-        fill += static_cast<int>(min(32u, re - j0));
-        PEB_COOP_COUNT(4, min(32u, re - j0));
+    // The points of these 32 rows are staged as ONE list, 32 points per step whatever the rows' lengths (rows hold
+    // 0-15 points: staging them one row per step kept a third of the lanes busy and made every row a load round trip
+    // of its own): inclusive scan of the lengths, then every lane finds the row of its list element by a binary
+    // search over the lanes' scan values.  The tile receives the points in the same order as before.
+    const int len = e > s ? static_cast<int>(e - s) : 0;
+    int end = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(kFull, end, o);
+      if (lane >= o) end += v;
+    }
+    const int total = __shfl_sync(kFull, end, 31);
+    PEB_COOP_COUNT(3, __popc(__ballot_sync(kFull, len > 0)));
+    PEB_COOP_COUNT(4, total);
+    for (int t0 = 0; t0 < total; t0 += 32) {
+      if (fill + 32 > kCoopTile - 4) flush();  // (the scan pads to a multiple of four)
+      const int t = t0 + lane;
+      int lo = 0;  // the first row whose scan value exceeds t
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const int ev = __shfl_sync(kFull, end, lo + step - 1);
+        if (ev <= t) lo += step;
       }
+      const int src_lane = min(lo, 31);
+      const int end_r = __shfl_sync(kFull, end, src_lane);
+      const int len_r = __shfl_sync(kFull, len, src_lane);
+      const uint32_t s_r = __shfl_sync(kFull, s, src_lane);
+      if (t < total) {
+        const uint32_t j = s_r + static_cast<uint32_t>(t - (end_r - len_r));
+        const float4 pt = g.pts[j];
+        tile->xs[fill + lane] = pt.x;
+        tile->ys[fill + lane] = pt.y;
+        tile->zs[fill + lane] = pt.z;
+        tile->ids[fill + lane] = __float_as_int(pt.w);
+        tile->pos[fill + lane] = static_cast<int>(j);
+      }
+      fill += min(32, total - t0);
     }
   }
   flush();
