@@ -304,6 +304,11 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
     ctx->warm_graph_queue = value;
     return PEB_OK;
   }
+  if (!strcmp(key, "warm_graph_peek")) {
+    if (value < 0) return fail(ctx, PEB_E_INVALID_ARG, "warm_graph_peek must be >= 0");
+    ctx->warm_graph_peek = value;
+    return PEB_OK;
+  }
   if (!strcmp(key, "cold_graph")) {
     if (value < 0 || value > 1) return fail(ctx, PEB_E_INVALID_ARG, "cold_graph must be 0 or 1");
     ctx->cold_graph = value;

@@ -112,6 +112,7 @@ struct peb_ctx {
   float warm_graph_kappa = 0.0f; // > 0: a hypothesis takes the graph once 4 * MSE * kappa < mean outer bound of the rows; 0: from launch 1 on (measured flat from 0 to 0.6 once hopeless rows are skipped)
   int warm_graph_queue = 0;     // (measured: -7 %, off) graph launches: every warp queues the unproven queries of a tile of 8 / 16 passes and
                                 // walks the grid for them 32 at a time (icp.cu : icp_iteration_graphq_kernel); 0 = every lane walks for itself
+  int warm_graph_peek = 1;      // (measured: launch 1 5.0 -> 4.6 ms, nothing after it) graph launches 1 .. this: a query whose row cannot certify looks at the four nearest neighbours of its previous match before it walks
   int cold_graph = 1;           // launch 0 of a batch with a graph: candidates by greedy descent from the patch's anchor match instead of the 3 x 3 x 3 probe
   int warm_graph_min_hyp = 32;  // ... for batches of at least this many hypotheses (the graph costs one k-NN pass over the target)
   int warm_bin = 0;             // (measured: -6 %, off) batched warm launches bin the queries of a block by the rows their search walks (icp.cu : icp_iteration_binned_kernel)

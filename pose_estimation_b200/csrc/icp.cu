@@ -85,6 +85,7 @@ struct IcpLaunch {
   const double* knn_stat;  // [0] sum, [1] count of the finite outer bounds (next2[2]) of the graph's rows
   float knn_kappa;       // a hypothesis searches over the graph once 4 * (its last MSE) * kappa < the mean outer bound
   int cold_graph;        // launch 0: candidates by greedy descent on the graph instead of the 3 x 3 x 3 probe
+  int knn_peek_until;    // graph launches up to this one look at the four nearest neighbours of the previous match before a walk
 };
 
 __global__ void icp_init_kernel(IcpState* __restrict__ states, const float* __restrict__ guesses, int H,
@@ -470,7 +471,7 @@ __device__ __forceinline__ void icp_query(const IcpLaunch& L, const int h, float
         }
         *sl = slack;
       } else {
-        if (UPF == 4) best = graph ? grid_nn_warm_graph(L.grid, L.knn, p.x, p.y, p.z, j_prev, L.stop_d2, kGraphSkipHopeless)
+        if (UPF == 4) best = graph ? grid_nn_warm_graph(L.grid, L.knn, p.x, p.y, p.z, j_prev, L.stop_d2, kGraphSkipHopeless, L.launch_idx <= L.knn_peek_until)
                                    : grid_nn_warm(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2);
         else best = UPF ? grid_nn_warm_upfront<(UPF == 3 ? 3 : 2)>(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2)
                         : grid_nn_warm(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2);
@@ -1541,6 +1542,7 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
     Lw.knn = ctx->tgt_knn.as<KnnRow>();
     Lw.knn_stat = ctx->tgt_knn_stat.as<double>();
     Lw.knn_kappa = ctx->warm_graph_kappa;
+    Lw.knn_peek_until = ctx->warm_graph_peek;
     if (ctx->cold_graph && Lc.anchors) {
       Lc.knn = Lw.knn;
       Lc.cold_graph = 1;

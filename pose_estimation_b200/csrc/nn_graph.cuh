@@ -67,7 +67,7 @@ constexpr int kGraphMaxRounds = 6;  // greedy steps before the grid walk takes o
 //  away, so that the walk covers a smaller ball — measured slower for every factor from 2 to 16: 13 870-15 480 against
 //  15 830 hypotheses/s; the steps cost more than the rows they save, also in launch 1.)
 PEB_HD bool grid_nn_graph_try(const GridView& g, const KnnRow* __restrict__ rows, float qx, float qy, float qz,
-                              int j_prev, NnBest& best, bool skip_hopeless = false) {
+                              int j_prev, NnBest& best, bool skip_hopeless = false, bool peek = false) {
   int js = j_prev;
   // the candidate, the first four positions of its row and the row's three distances: independent loads
   const KnnRow* row = rows + js;
@@ -81,7 +81,21 @@ PEB_HD bool grid_nn_graph_try(const GridView& g, const KnnRow* __restrict__ rows
   }
   for (int round = 0; round < kGraphMaxRounds; ++round) {
     const float lim = 4.0f * best.d2 * 1.00001f;
-    if (skip_hopeless && kGraphHalves == 1 && round == 0 && !(nx.z > lim)) return false;
+    if (skip_hopeless && kGraphHalves == 1 && round == 0 && !(nx.z > lim)) {
+      if (peek) {
+        // the first launches after launch 0 move the queries by millimetres and the nearest point often has moved on to
+        // a neighbour of s: a look at the four nearest ones shrinks the ball the walk has to cover (launch 1 of C4:
+        // 5.0 -> 4.6 ms; from launch 3 on it costs more than it saves)
+        const uint32_t pos[4] = {p0.x, p0.y, p0.z, p0.w};
+        float4 n[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) n[k] = g.pts[pos[k]];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          nn_consider(best, l2_simple(qx, qy, qz, n[k].x, n[k].y, n[k].z), point_index(n[k]), static_cast<int>(pos[k]));
+      }
+      return false;
+    }
     bool proven = false;
 #pragma unroll 1
     for (int hf = 0; hf < kGraphHalves && !proven; ++hf) {
@@ -155,9 +169,9 @@ PEB_HD NnBest grid_nn_graph_descend(const GridView& g, const KnnRow* __restrict_
 
 // Exact 1-NN of q given a candidate at sorted position j_prev (last iteration's match).
 PEB_HD NnBest grid_nn_warm_graph(const GridView& g, const KnnRow* __restrict__ rows, float qx, float qy, float qz,
-                                 int j_prev, float limit_d2, bool skip_hopeless = false) {
+                                 int j_prev, float limit_d2, bool skip_hopeless = false, bool peek = false) {
   NnBest best;
-  if (!grid_nn_graph_try(g, rows, qx, qy, qz, j_prev, best, skip_hopeless)) grid_ball_search(g, qx, qy, qz, limit_d2, best);
+  if (!grid_nn_graph_try(g, rows, qx, qy, qz, j_prev, best, skip_hopeless, peek)) grid_ball_search(g, qx, qy, qz, limit_d2, best);
   return best;
 }
 
