@@ -304,6 +304,16 @@ PEB_API int peb_ctx_set_int(peb_ctx* ctx, const char* key, int value) {
     ctx->warm_graph_queue = value;
     return PEB_OK;
   }
+  if (!strcmp(key, "warm_graph_flat")) {
+    if (value < 0 || value > 1) return fail(ctx, PEB_E_INVALID_ARG, "warm_graph_flat must be 0 or 1");
+    ctx->warm_graph_flat = value;
+    return PEB_OK;
+  }
+  if (!strcmp(key, "warm_graph_flat_from") || !strcmp(key, "warm_graph_flat_until")) {
+    if (value < 0) return fail(ctx, PEB_E_INVALID_ARG, "%s must be >= 0", key);
+    (key[16] == 'f' ? ctx->warm_graph_flat_from : ctx->warm_graph_flat_until) = value;
+    return PEB_OK;
+  }
   if (!strcmp(key, "warm_graph_peek")) {
     if (value < 0) return fail(ctx, PEB_E_INVALID_ARG, "warm_graph_peek must be >= 0");
     ctx->warm_graph_peek = value;

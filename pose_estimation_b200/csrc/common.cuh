@@ -112,6 +112,8 @@ struct peb_ctx {
   float warm_graph_kappa = 0.0f; // > 0: a hypothesis takes the graph once 4 * MSE * kappa < mean outer bound of the rows; 0: from launch 1 on (measured flat from 0 to 0.6 once hopeless rows are skipped)
   int warm_graph_queue = 0;     // (measured: -7 %, off) graph launches: every warp queues the unproven queries of a tile of 8 / 16 passes and
                                 // walks the grid for them 32 at a time (icp.cu : icp_iteration_graphq_kernel); 0 = every lane walks for itself
+  int warm_graph_flat = 1;      // graph searches also try the flatness certificate (nn_graph.cuh : knn_aux_of) ...
+  int warm_graph_flat_from = 2, warm_graph_flat_until = 15;  // ... in these iteration launches
   int warm_graph_peek = 1;      // (measured: launch 1 5.0 -> 4.6 ms, nothing after it) graph launches 1 .. this: a query whose row cannot certify looks at the four nearest neighbours of its previous match before it walks
   int cold_graph = 1;           // launch 0 of a batch with a graph: candidates by greedy descent from the patch's anchor match instead of the 3 x 3 x 3 probe
   int warm_graph_min_hyp = 32;  // ... for batches of at least this many hypotheses (the graph costs one k-NN pass over the target)
@@ -160,6 +162,7 @@ struct peb_ctx {
   cudaEvent_t tgt_stage_event = nullptr;
   peb::Grid tgt_grid;
   peb::DevBuf tgt_knn;                // k-nearest-neighbour graph of the target grid's points (nn_graph.cuh), 64 bytes per point,
+  peb::DevBuf tgt_knn_aux;            // ... and the flatness certificate's (direction, height bound) per point, 16 bytes
   peb::DevBuf tgt_knn_stat;           // two doubles: sum and count of the rows' finite outer bounds
   bool tgt_knn_valid = false;         // built by the first batched align on this target that uses it
 

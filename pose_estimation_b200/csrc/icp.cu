@@ -86,6 +86,7 @@ struct IcpLaunch {
   float knn_kappa;       // a hypothesis searches over the graph once 4 * (its last MSE) * kappa < the mean outer bound
   int cold_graph;        // launch 0: candidates by greedy descent on the graph instead of the 3 x 3 x 3 probe
   int knn_peek_until;    // graph launches up to this one look at the four nearest neighbours of the previous match before a walk
+  const float4* knn_aux; // nullable: the flatness certificate's per-point records (nn_graph.cuh : knn_aux_of)
 };
 
 __global__ void icp_init_kernel(IcpState* __restrict__ states, const float* __restrict__ guesses, int H,
@@ -471,7 +472,9 @@ __device__ __forceinline__ void icp_query(const IcpLaunch& L, const int h, float
         }
         *sl = slack;
       } else {
-        if (UPF == 4) best = graph ? grid_nn_warm_graph(L.grid, L.knn, p.x, p.y, p.z, j_prev, L.stop_d2, kGraphSkipHopeless, L.launch_idx <= L.knn_peek_until)
+        // (UPF 6: the graph search with the flatness certificate — a kernel of its own, so that the launches that do not
+        //  use it carry none of its registers)
+        if (UPF == 4 || UPF == 6) best = graph ? grid_nn_warm_graph(L.grid, L.knn, p.x, p.y, p.z, j_prev, L.stop_d2, kGraphSkipHopeless, L.launch_idx <= L.knn_peek_until, UPF == 6 ? L.knn_aux : nullptr)
                                    : grid_nn_warm(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2);
         else best = UPF ? grid_nn_warm_upfront<(UPF == 3 ? 3 : 2)>(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2)
                         : grid_nn_warm(L.grid, p.x, p.y, p.z, j_prev, L.stop_d2);
@@ -526,7 +529,7 @@ __device__ __forceinline__ void icp_iteration_body(const IcpLaunch& L, const int
     s_flags[0] = active;
     s_flags[1] = first;
     s_flags[2] = apply;
-    const int graph = (UPF == 4 && graph_pays(L, st)) ? 1 : 0;
+    const int graph = ((UPF == 4 || UPF == 6) && graph_pays(L, st)) ? 1 : 0;
     s_flags[3] = graph;
   }
   __syncthreads();
@@ -543,7 +546,7 @@ __device__ __forceinline__ void icp_iteration_body(const IcpLaunch& L, const int
   float4* work = L.work + static_cast<size_t>(h) * L.n_src;
   constexpr int kQ = kIcpThreads / G;  // queries per block per pass
   const int q_local = threadIdx.x / G;
-  const bool graph = UPF == 4 && s_flags[3] != 0;
+  const bool graph = (UPF == 4 || UPF == 6) && s_flags[3] != 0;
   // (Measured and dropped: fetching the working point of the NEXT pass while this pass searches — cp.async into one or
   //  two shared-memory slots per thread, or prefetch.global.L2.  work[i] is the one load of a warm launch that comes
   //  from HBM, the first of three dependent levels, but with 25 warps per SM in flight it is already hidden:
@@ -1330,6 +1333,13 @@ int launch_one_iteration(peb_ctx* ctx, const IcpLaunch& L, size_t H, int estimat
     if (ctx->warm_graph_queue == 8) { PEB_ICP_LAUNCH_GQ(8); return PEB_OK; }
     if (ctx->warm_graph_queue == 16) { PEB_ICP_LAUNCH_GQ(16); return PEB_OK; }
 #undef PEB_ICP_LAUNCH_GQ
+    // ... with the flatness certificate in the launches where the queries are still beyond the plain one ("warm_graph_flat_from"
+    // .. "warm_graph_flat_until"; later the plain certificate settles nearly everything and the extra record only costs)
+    if (L.knn_aux && L.launch_idx >= ctx->warm_graph_flat_from && L.launch_idx <= ctx->warm_graph_flat_until) {
+      if (svd) PEB_LAUNCH_PDL(ctx, (icp_iteration_kernel<1, S, kMinBlocksBatch, false, false, 6>), grid, dim3(kIcpThreads), L);
+      else     PEB_LAUNCH_PDL(ctx, (icp_iteration_kernel<1, P, kMinBlocksBatch, false, false, 6>), grid, dim3(kIcpThreads), L);
+      return PEB_OK;
+    }
     if (svd) PEB_LAUNCH_PDL(ctx, (icp_iteration_kernel<1, S, kMinBlocksBatch, false, false, 4>), grid, dim3(kIcpThreads), L);
     else     PEB_LAUNCH_PDL(ctx, (icp_iteration_kernel<1, P, kMinBlocksBatch, false, false, 4>), grid, dim3(kIcpThreads), L);
     return PEB_OK;
@@ -1543,6 +1553,7 @@ int icp_align_device(peb_ctx* ctx, const float* d_guesses, size_t H, const peb_i
     Lw.knn_stat = ctx->tgt_knn_stat.as<double>();
     Lw.knn_kappa = ctx->warm_graph_kappa;
     Lw.knn_peek_until = ctx->warm_graph_peek;
+    Lw.knn_aux = ctx->warm_graph_flat ? ctx->tgt_knn_aux.as<float4>() : nullptr;
     if (ctx->cold_graph && Lc.anchors) {
       Lc.knn = Lw.knn;
       Lc.cold_graph = 1;

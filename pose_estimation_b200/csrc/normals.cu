@@ -365,6 +365,12 @@ __global__ void __launch_bounds__(128, 4) knn_graph_kernel(const GridView g, Knn
   }
 }
 
+// the flatness certificate's per-point record (nn_graph.cuh : knn_aux_of), one thread per target point
+__global__ void __launch_bounds__(128) knn_aux_kernel(const GridView g, const KnnRow* __restrict__ rows, float4* __restrict__ aux) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < g.n) aux[j] = knn_aux_of(g, rows, j);
+}
+
 }  // namespace
 
 // the graph of the target grid, built once per target and kept until the target changes (icp.cu asks for it)
@@ -376,6 +382,9 @@ int target_graph_ensure(peb_ctx* ctx) {
   PEB_CUDA(ctx, cudaMemsetAsync(ctx->tgt_knn_stat.p, 0, 2 * sizeof(double), ctx->stream));
   if (g.n > 0)
     PEB_LAUNCH(ctx, knn_graph_kernel, ceil_div(g.n, 128), 128, 0, g, ctx->tgt_knn.as<KnnRow>(), ctx->tgt_knn_stat.as<double>());
+  PEB_CUDA(ctx, ctx->tgt_knn_aux.ensure(std::max<size_t>(g.n, 1) * sizeof(float4)));
+  if (g.n > 0)
+    PEB_LAUNCH(ctx, knn_aux_kernel, ceil_div(g.n, 128), 128, 0, g, ctx->tgt_knn.as<KnnRow>(), ctx->tgt_knn_aux.as<float4>());
   ctx->tgt_knn_valid = true;
   return PEB_OK;
 }

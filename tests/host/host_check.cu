@@ -202,10 +202,18 @@ HC_API void hc_grid_nn_warm_graph(const float* tgt, size_t n, size_t tstride, co
       for (int c = 0; c < 3; ++c) r.half[h].next2[c] = d2_of(12 * h + 4 * c + 4);
     }
   }
+  // mode 3: mode 1 + the flatness certificate (records of knn_aux_of)
+  std::vector<float4> aux;
+  if (mode == 3) {
+    aux.resize(std::max(g.v.n, 1));
+    for (int sj = 0; sj < g.v.n; ++sj) aux[sj] = knn_aux_of(g.v, rows.data(), sj);
+  }
   for (size_t i = 0; i < nq; ++i) {
     const float* p = q + i * (qstride / 4);
     NnBest b;
-    if (mode == 2) {
+    if (mode == 3) {
+      b = grid_nn_warm_graph(g.v, rows.data(), p[0], p[1], p[2], pos[prev[i]], limit_d2, true, (i & 1) != 0, aux.data());
+    } else if (mode == 2) {
       b = grid_nn_graph_descend(g.v, rows.data(), p[0], p[1], p[2], pos[prev[i]]);
       grid_ball_search(g.v, p[0], p[1], p[2], limit_d2, b);
     } else {

@@ -50,6 +50,11 @@ VARIANTS = {"plain": (("warm_graph", 0), ("warm_bin", 0)),
                          ("warm_graph_peek", 1000)),
             "peek_none": (("warm_graph", 1), ("warm_graph_min_hyp", 2), ("warm_bin", 0), ("warm_graph_queue", 0),
                           ("warm_graph_peek", 0)),
+            # without the flatness certificate (only the triangle inequality proves a match)
+            "flat_off": (("warm_graph", 1), ("warm_graph_min_hyp", 2), ("warm_bin", 0), ("warm_graph_queue", 0),
+                         ("warm_graph_flat", 0)),
+            "flat_all": (("warm_graph", 1), ("warm_graph_min_hyp", 2), ("warm_bin", 0), ("warm_graph_queue", 0),
+                         ("warm_graph_flat", 1), ("warm_graph_flat_from", 1), ("warm_graph_flat_until", 1000)),
             "bin": (("warm_graph", 0), ("warm_bin", 1))}
 
 
@@ -74,7 +79,7 @@ def _run(pcl, source, target, cls, normals, guesses, variant, opts=(), **params)
     return out
 
 
-@pytest.mark.parametrize("variant", ["graph", "graph_auto", "graphq", "graphq_auto", "graphq16", "cold_graph", "peek_all", "peek_none", "bin"])
+@pytest.mark.parametrize("variant", ["graph", "graph_auto", "graphq", "graphq_auto", "graphq16", "cold_graph", "peek_all", "peek_none", "flat_off", "flat_all", "bin"])
 def test_warm_variants_never_change_results(pcl, scene_small, variant):
     p = scene_small
     rng = np.random.default_rng(15)
@@ -89,7 +94,7 @@ def test_warm_variants_never_change_results(pcl, scene_small, variant):
                _run(pcl, p.source, p.target, pcl.IterativeClosestPoint, None, guesses, "plain", opts, **kw)
 
 
-@pytest.mark.parametrize("variant", ["graph", "graph_auto", "graphq", "graphq_auto", "cold_graph", "peek_all", "peek_none", "bin"])
+@pytest.mark.parametrize("variant", ["graph", "graph_auto", "graphq", "graphq_auto", "cold_graph", "peek_all", "peek_none", "flat_off", "flat_all", "bin"])
 def test_warm_variants_point_to_plane_rejector_and_criteria(pcl, scene_small, variant):
     p = scene_small
     c = pcl.Context(0)
@@ -107,7 +112,7 @@ def test_warm_variants_point_to_plane_rejector_and_criteria(pcl, scene_small, va
     assert len({r[-32:] for r in a}) > 1  # (the records differ between hypotheses: the comparison is not vacuous)
 
 
-@pytest.mark.parametrize("variant", ["graph", "graph_auto", "graphq", "graphq_auto", "cold_graph", "peek_all", "peek_none", "bin"])
+@pytest.mark.parametrize("variant", ["graph", "graph_auto", "graphq", "graphq_auto", "cold_graph", "peek_all", "peek_none", "flat_off", "flat_all", "bin"])
 def test_warm_variants_nonfinite_points_far_hypotheses_and_tiny_sources(pcl, scene_small, variant):
     p = scene_small
     rng = np.random.default_rng(17)

@@ -109,7 +109,8 @@ def test_warm_ball_search_is_exact_on_adversarial_clouds(hc, oracle, seed):  # n
 
 def grid_nn_warm_graph(hc, tgt, q, prev, occupancy, limit=np.inf, mode=0):  # noqa: F811
     """mode 0: every row scanned; 1: rows that cannot certify skipped (the warm launches of a batch); 2: greedy descent
-    from prev, then the ball search (launch 0's candidate and its verification)"""
+    from prev, then the ball search (launch 0's candidate and its verification); 3: mode 1 with the flatness certificate
+    (and the look at four neighbours for every other query)"""
     tgt = np.ascontiguousarray(tgt, F)
     idx = np.empty(len(q), np.int32)
     d2 = np.empty(len(q), F)
@@ -129,10 +130,44 @@ def test_knn_graph_warm_search_is_exact_on_adversarial_clouds(hc, oracle, seed):
         ok = np.flatnonzero(np.isfinite(tgt).all(1))
         for occ in (1.0, 5.0):
             for kind, prev in (("true", bi), ("next", ok[(np.searchsorted(ok, bi) + 1) % len(ok)]), ("random", rng.choice(ok, len(q)))):
-                for mode in (0, 1, 2):
+                for mode in (0, 1, 2, 3):
                     gi, gd = grid_nn_warm_graph(hc, tgt, q, np.ascontiguousarray(prev, np.int32), occ, mode=mode)
                     assert np.array_equal(gd, bd), (name, occ, kind, mode, np.flatnonzero(gd != bd)[:5])
                     assert np.array_equal(gi, bi), (name, occ, kind, mode, np.flatnonzero(gi != bi)[:5])
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_flatness_certificate_is_exact_on_sheets_steps_and_creases(hc, oracle, seed):  # noqa: F811
+    """csrc/nn_graph.cuh : knn_aux_of / flat() — the geometry the certificate is made for and the geometry that must stop
+    it: a noisy sheet, a sheet with a second one a few spacings behind half of it (depth step), a crease, a sheet with a
+    lone point hovering above it; queries hover 0.1-4 spacings off the sheet around true, neighbouring and random matches"""
+    rng = np.random.default_rng(9100 + seed)
+    a = 1e-3  # spacing
+    n = 45
+    gx, gy = np.meshgrid(np.arange(n), np.arange(n))
+    base = np.column_stack([gx.ravel(), gy.ravel(), np.zeros(n * n)]).astype(np.float64) * a
+    base[:, :2] += rng.uniform(-0.3, 0.3, (n * n, 2)) * a
+    sheets = {}
+    noisy = base.copy()
+    noisy[:, 2] += rng.normal(0, 0.05 * a, n * n)
+    sheets["noisy_sheet"] = noisy
+    step = np.concatenate([noisy, noisy[noisy[:, 0] > 0.5 * n * a] + [0.0, 0.0, -2.5 * a]])
+    sheets["depth_step"] = step
+    crease = noisy.copy()
+    crease[:, 2] += np.abs(crease[:, 0] - 0.5 * n * a) * 0.8
+    sheets["crease"] = crease
+    sheets["hovering_point"] = np.concatenate([noisy, [[0.5 * n * a, 0.5 * n * a, 1.3 * a]]])
+    for name, cloud in sheets.items():
+        tgt = (cloud + [0.1, -0.2, 0.7]).astype(F)
+        pick = rng.integers(0, len(tgt), 1500)
+        off = np.column_stack([rng.normal(0, 0.4 * a, (1500, 2)), rng.uniform(-4 * a, 4 * a, 1500) * rng.choice([0.03, 0.3, 1.0], 1500)])
+        q = np.ascontiguousarray((tgt[pick].astype(np.float64) + off).astype(F))
+        bi, bd = oracle.nn_bruteforce(tgt, q)
+        for occ in (2.0, 5.0):
+            for kind, prev in (("true", bi), ("picked", pick), ("random", rng.integers(0, len(tgt), len(q)))):
+                gi, gd = grid_nn_warm_graph(hc, tgt, q, np.ascontiguousarray(prev, np.int32), occ, mode=3)
+                assert np.array_equal(gd, bd), (name, occ, kind, np.flatnonzero(gd != bd)[:5])
+                assert np.array_equal(gi, bi), (name, occ, kind, np.flatnonzero(gi != bi)[:5])
 
 
 @pytest.mark.parametrize("seed", [0, 1])
