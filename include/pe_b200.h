@@ -140,7 +140,9 @@ PEB_API uint64_t peb_ctx_launch_count(const peb_ctx* ctx);
  * proves most answers without a grid walk; byte-identical records, C4 11 480 -> 16 330 hypotheses/s),
  * "warm_graph_kappa_x100" (default 0 = every hypothesis from launch 1 on; > 0: a hypothesis takes the graph once
  * 4 x its last MSE x kappa is below the mean outer bound of the rows), "cold_graph" (default 1: launch 0 of such a batch
- * takes its candidates from a greedy descent on the graph instead of a 3 x 3 x 3 probe), "warm_graph_peek" (default 1: in graph launches 1 .. this, a query whose row cannot certify
+ * takes its candidates from a greedy descent on the graph instead of a 3 x 3 x 3 probe), "warm_graph_flat" (default 1) with "warm_graph_flat_from" / "warm_graph_flat_until"
+ * (default 2 / 15: the iteration launches whose graph searches also try the flatness certificate of nn_graph.cuh — a residual
+ * along the local surface normal is proven far beyond the triangle inequality), "warm_graph_peek" (default 1: in graph launches 1 .. this, a query whose row cannot certify
  * looks at the four nearest neighbours of its previous match before it walks the grid), "warm_graph_queue" (default 0;
  * 8 / 16: every warp queues the unproven queries of a tile of that many passes and walks the grid for them 32 at a
  * time — icp.cu : icp_iteration_graphq_kernel; byte-identical, measured -7 %, profiles/r2_ai_graph_queue.txt) */
